@@ -1,0 +1,229 @@
+/* sar.h — C-ABI boundary of the B200-native strange-attractor render path.
+ *
+ * One shared library, `libsar_b200.so`, replaces exactly one path of
+ * Icelk/strange-attractor-renderer: iterate the polynomial Sprott map, project,
+ * scatter into the count / z / Δp buffers, log tone-map and palette-colourise.
+ * Every entry point below names the reference interface (file:line into the
+ * reference repository, `src/lib.rs` unless stated) it stands in for.  The
+ * reference has no FFI of its own; the seam is its public Rust API
+ *   Runtime::{new,reset,merge}   lib.rs:660,682,708
+ *   render()                     lib.rs:747
+ *   colorize()                   lib.rs:841
+ *   ParallelRenderer::{new,shutdown}, render_parallel()   lib.rs:919,1020,1051
+ * and INTEGRATION.md shows the Rust `extern "C"` block a maintainer adds.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all structs are POD, little-endian, natural
+ *     alignment (`#[repr(C)]` on the Rust side);
+ *   - the caller owns every host buffer passed in or out; opaque handles own
+ *     device memory; nothing allocated on one side is freed on the other
+ *     (except via the matching sar_*_free / sar_host_free);
+ *   - every function returning `int` returns SAR_OK (0) or a negative sar_status;
+ *     sar_last_error() gives a thread-local message.  Nothing unwinds across
+ *     the boundary.  (The reference panics instead — lib.rs:678,709-710,1024 —
+ *     the Rust shim turns non-zero statuses back into those panics.)
+ *   - calls on one handle must be serialised by the caller (the reference takes
+ *     `&mut Runtime` / `&mut ParallelRenderer`, lib.rs:747,1052); different
+ *     handles may be used from different threads.  Every call sets the CUDA
+ *     device it needs itself; no thread-local CUDA state is assumed.
+ *   - there is NO CPU fallback: without a usable CUDA device every compute
+ *     entry point fails with SAR_ERR_CUDA.
+ *
+ * Determinism contract (what "parity" means)
+ *   The reference seeds every Runtime from the OS (lib.rs:656) and draws one
+ *   start point per render() (lib.rs:748), so it is not reproducible.  Here the
+ *   start points are an explicit input: either a caller-supplied list
+ *   (`init_xyz`, n_jobs×3 f64, the value of `rng.random::<Vec3>() * 0.1`
+ *   BEFORE the 1000 warm-up steps of lib.rs:750-752) or a documented
+ *   counter-based generator (sar_seed_points).  Given that list, the result of
+ *   sar_render(cfg, rt, init_xyz, n_jobs) is bit-identical — count (u32),
+ *   zbuf (f32) and steps (f64) — to calling the reference's render() n_jobs
+ *   times in list order on one non-reset Runtime.
+ */
+#ifndef SAR_B200_H
+#define SAR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SAR_ABI_VERSION 1u
+#define SAR_MAX_PALETTE 16u        /* palette entries carried across the boundary */
+#define SAR_WARMUP_ITERATIONS 1000u /* lib.rs:750 */
+
+typedef enum sar_status {
+    SAR_OK = 0,
+    SAR_ERR_INVALID = -1,   /* NULL pointer, zero size, bad enum, palette_len out of range */
+    SAR_ERR_DIMS = -2,      /* dimension mismatch (reference: assert_eq! in merge, lib.rs:709-710) */
+    SAR_ERR_CUDA = -3,      /* CUDA runtime error or no usable device */
+    SAR_ERR_NOMEM = -4,     /* host or device allocation failed */
+    SAR_ERR_UNSUPPORTED = -5 /* e.g. an Attractor/ColorTransform with no device form */
+} sar_status;
+
+/* config::RenderKind, lib.rs:234-239 */
+enum { SAR_RENDER_GAS = 0, SAR_RENDER_DEPTH = 1 };
+/* the two shipped ColorTransform instantiations, lib.rs:503-559 */
+enum { SAR_CT_POISSON_SATURNE = 0, SAR_CT_ADJUSTED_VELOCITY = 1 };
+
+/* Config<PolynomialSprott2Degree, {Function|AdjustedVelocity}>, lib.rs:265-287,
+ * flattened with Colors (lib.rs:475-479), Palette (lib.rs:408-411),
+ * BrighnessConstants (lib.rs:390-396), View (lib.rs:253-261) and
+ * EulerAxisRotation (lib.rs:170-175). */
+typedef struct sar_config {
+    uint64_t iterations;                 /* lib.rs:267 (usize) */
+    uint32_t width;                      /* lib.rs:269 */
+    uint32_t height;                     /* lib.rs:271 */
+    uint32_t render_kind;                /* lib.rs:273, SAR_RENDER_* */
+    uint32_t transparent;                /* lib.rs:275, 0/1 */
+    uint32_t silent;                     /* lib.rs:280, 0/1 */
+    uint32_t ct_kind;                    /* lib.rs:286, SAR_CT_* */
+    double   angle;                      /* lib.rs:277, RADIANS (lib.rs:745) */
+    double   coef[3][10];                /* attractor.x / .y / .z, lib.rs:577-579 */
+    double   center_camera[3];           /* view.center_camera, lib.rs:257 */
+    double   axis[3];                    /* view.rotation.axis, lib.rs:172 — NOT normalised (release build, lib.rs:181-183) */
+    double   rotation;                   /* view.rotation.rotation, lib.rs:174 */
+    double   scale;                      /* view.scale, lib.rs:260 */
+    double   ct_offset;                  /* AdjustedVelocity.offset, lib.rs:508 */
+    double   ct_factor;                  /* AdjustedVelocity.factor, lib.rs:509 */
+    uint32_t palette_len;                /* Palette::count(), lib.rs:435; 1..SAR_MAX_PALETTE */
+    uint32_t reserved0;
+    double   palette_rgb[SAR_MAX_PALETTE][3]; /* Palette list WITHOUT the duplicated sentinel of lib.rs:418 */
+    double   bright_offset;              /* colors.brighness.offset, lib.rs:394 */
+    double   bright_factor;              /* colors.brighness.factor, lib.rs:395 */
+} sar_config;
+
+typedef struct sar_runtime  sar_runtime;   /* Runtime, lib.rs:631-646 (device resident) */
+typedef struct sar_renderer sar_renderer;  /* ParallelRenderer, lib.rs:908-915 */
+
+/* ---- library ---------------------------------------------------------- */
+uint32_t    sar_abi_version(void);
+const char *sar_last_error(void);            /* thread-local, never NULL */
+int         sar_device_count(int *count);    /* SAR_ERR_CUDA when no driver/device */
+
+/* ---- Config presets --------------------------------------------------- */
+/* Config::new defaults, lib.rs:289-307 + Colors::default lib.rs:480-491, around
+ * the caller's attractor/view/transform fields (which are left untouched). */
+int sar_config_defaults(sar_config *cfg);
+/* Config::poisson_saturne(), lib.rs:310-352 */
+int sar_config_poisson_saturne(sar_config *cfg);
+/* Config::solar_sail(), lib.rs:355-386 */
+int sar_config_solar_sail(sar_config *cfg);
+
+/* ---- start points ----------------------------------------------------- */
+/* Stand-in for `runtime.rng.random::<Vec3>() * 0.1` (lib.rs:748, 161-166):
+ * point k, coordinate c = ((u >> 11) * 2^-53) * 0.1 with u the (3k+c)-th
+ * output of a SplitMix64 stream seeded with `seed`; written to
+ * out_xyz[3*(k-first) + c] for k in [first, first+n). */
+int sar_seed_points(uint64_t seed, uint64_t first, uint64_t n, double *out_xyz);
+
+/* ---- Runtime ---------------------------------------------------------- */
+/* Runtime::new, lib.rs:660 (allocate + reset) on CUDA device `device`. */
+int  sar_runtime_new(uint32_t width, uint32_t height, int device, sar_runtime **out);
+void sar_runtime_free(sar_runtime *rt);
+/* Runtime::reset, lib.rs:682: count=0, steps=0.0, zbuf=-1.0, max=0. */
+int  sar_runtime_reset(sar_runtime *rt);
+/* Runtime::merge, lib.rs:708: count+=, max, `other` wins a pixel iff its z is
+ * strictly greater (ties keep dst).  SAR_ERR_DIMS on mismatch.  src may live
+ * on another device. */
+int  sar_runtime_merge(sar_runtime *dst, const sar_runtime *src);
+int  sar_runtime_dims(const sar_runtime *rt, uint32_t *width, uint32_t *height, int *device);
+/* The three textures + max in the reference's layout (row-major, idx=y*w+x,
+ * as image::ImageBuffer; lib.rs:633-643).  Any pointer may be NULL. */
+int  sar_runtime_download(const sar_runtime *rt, uint32_t *count, double *steps,
+                          float *zbuf, uint32_t *max);
+/* Inverse of download (all three arrays required): the checkpoint/resume of
+ * the reference's progressive accumulation (lib.rs:742-743). */
+int  sar_runtime_upload(sar_runtime *rt, const uint32_t *count, const double *steps,
+                        const float *zbuf);
+
+/* ---- render() --------------------------------------------------------- */
+/* n_jobs reference render() calls (lib.rs:747) accumulated into `rt`: job k
+ * starts at init_xyz[3k..3k+3], runs SAR_WARMUP_ITERATIONS unrecorded steps and
+ * then cfg->iterations recorded steps.  Does not reset `rt`.  Blocking. */
+int sar_render(const sar_config *cfg, sar_runtime *rt,
+               const double *init_xyz, uint64_t n_jobs);
+/* Same, start points = sar_seed_points(seed, first_job, n_jobs) generated on
+ * the device (no host→device traffic). */
+int sar_render_seeded(const sar_config *cfg, sar_runtime *rt,
+                      uint64_t seed, uint64_t first_job, uint64_t n_jobs);
+
+/* ---- colorize() ------------------------------------------------------- */
+/* colorize, lib.rs:841: interleaved RGBA u16 (FinalImage::into_raw, lib.rs:625),
+ * width*height*4 values into caller memory.  rgba_f32 (optional, may be NULL)
+ * receives the pre-quantisation channel values `(c*factor+offset)*bf` and
+ * alpha as f32 (Gas) or z/1/1/1-normalised grey (Depth). */
+int sar_colorize(const sar_config *cfg, const sar_runtime *rt,
+                 uint16_t *rgba_u16, float *rgba_f32);
+
+/* ---- ParallelRenderer / render_parallel ------------------------------- */
+/* ParallelRenderer::new, lib.rs:919.  `devices`/`n_devices`: CUDA ordinals of
+ * this process's GPUs (NULL/0 = device 0).  `threads_per_device` plays the
+ * role of available_parallelism() (lib.rs:920-922): the number of concurrent
+ * trajectory lanes; 0 = default (SM count × 256). */
+int  sar_renderer_new(const int *devices, int n_devices, uint32_t threads_per_device,
+                      sar_renderer **out);
+/* ParallelRenderer::shutdown, lib.rs:1020. */
+void sar_renderer_shutdown(sar_renderer *r);
+/* num_threads(), lib.rs:1015 — total over the renderer's devices. */
+int  sar_renderer_num_threads(const sar_renderer *r, uint64_t *num_threads);
+/* render_parallel, lib.rs:1051: iterations/num_threads/jobs_per_thread per job
+ * (integer division, lib.rs:1058), num_threads*jobs_per_thread jobs
+ * (lib.rs:1062), merge (lib.rs:1072-1076), colorize (lib.rs:1080).
+ * Start points: init_xyz (n_jobs×3) if non-NULL, else sar_seed_points(seed).
+ * rgba_u16: width*height*4, caller-owned host memory.  Blocking. */
+int  sar_render_parallel(sar_renderer *r, const sar_config *cfg, uint64_t jobs_per_thread,
+                         uint64_t seed, const double *init_xyz, uint16_t *rgba_u16);
+/* The merged Runtime of the last sar_render_parallel on the renderer's first
+ * device (valid until the next call / shutdown); for inspection and tests. */
+int  sar_renderer_runtime(sar_renderer *r, sar_runtime **rt);
+
+/* ---- device-resident / multi-process plumbing -------------------------
+ * Used by bench.py (kernel-only timing) and by the one-process-per-GPU
+ * driver.  `stream` is a cudaStream_t passed as void*
+ * (NULL = the runtime's own stream); *_async calls do not synchronise. */
+int sar_render_seeded_async(const sar_config *cfg, sar_runtime *rt, uint64_t seed,
+                            uint64_t first_job, uint64_t n_jobs, uint32_t threads,
+                            void *stream);
+int sar_render_device_async(const sar_config *cfg, sar_runtime *rt, const double *d_init_xyz,
+                            uint64_t first_job, uint64_t n_jobs, uint32_t threads, void *stream);
+int sar_runtime_reset_async(sar_runtime *rt, void *stream);
+/* colourise rows [row0,row0+rows) into device memory d_rgba_u16 (full-image base pointer). */
+int sar_colorize_device_async(const sar_config *cfg, sar_runtime *rt, uint16_t *d_rgba_u16,
+                              float *d_rgba_f32, void *stream);
+int sar_stream_synchronize(sar_runtime *rt, void *stream);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+uint64_t sar_launch_count(void);
+
+/* Pinned host memory for callers that want full-rate PCIe copies. */
+int  sar_host_alloc(size_t bytes, void **out);
+void sar_host_free(void *p);
+
+/* Cross-process peer access (one process per GPU, NVLink P2P via CUDA IPC).
+ * export: 2 opaque 64-byte handles (accumulator buffers) into out[128].
+ * Each rank opens every peer's handles, then sar_runtime_merge_peers()
+ * reduces ITS row stripe [row0,row0+rows) over all ranks by reading peer
+ * memory directly: count sum, (z, job)-max of the Δp records — the
+ * deterministic form of Runtime::merge (lib.rs:708-738), see DESIGN.md §6. */
+#define SAR_IPC_HANDLE_BYTES 128u
+typedef struct sar_peer sar_peer;
+int  sar_runtime_ipc_export(const sar_runtime *rt, uint8_t out[SAR_IPC_HANDLE_BYTES]);
+int  sar_peer_open(const uint8_t handle[SAR_IPC_HANDLE_BYTES], uint32_t width, uint32_t height,
+                   int local_device, sar_peer **out);
+void sar_peer_close(sar_peer *p);
+int  sar_runtime_merge_peers(sar_runtime *rt, sar_peer *const *peers, int n_peers,
+                             uint32_t row0, uint32_t rows, void *stream);
+/* max over rows [row0,row0+rows) of the merged count (the stripe's share of Runtime.max). */
+int  sar_runtime_stripe_max(sar_runtime *rt, uint32_t row0, uint32_t rows, uint32_t *max_out);
+/* force Runtime.max (after an all-reduce over stripes). */
+int  sar_runtime_set_max(sar_runtime *rt, uint32_t max);
+/* colourise only rows [row0,row0+rows) to host memory (rgba_u16 = full-image base). */
+int  sar_colorize_rows(const sar_config *cfg, sar_runtime *rt, uint32_t row0, uint32_t rows,
+                       uint16_t *rgba_u16);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SAR_B200_H */
