@@ -183,17 +183,36 @@ int  sar_renderer_runtime(sar_renderer *r, sar_runtime **rt);
 /* ---- device-resident / multi-process plumbing -------------------------
  * Used by bench.py (kernel-only timing) and by the one-process-per-GPU
  * driver.  `stream` is a cudaStream_t passed as void*
- * (NULL = the runtime's own stream); *_async calls do not synchronise. */
+ * (NULL = the runtime's own stream); *_async calls do not synchronise.
+ * `threads` = concurrent trajectory lanes (0 = default, SM count × 256);
+ * lane L runs jobs L, L+threads, ... one after the other.
+ * Order key of job k of a call = job_base + first_job + k (see
+ * sar_runtime_set_job_base); earlier keys keep exact z ties. */
 int sar_render_seeded_async(const sar_config *cfg, sar_runtime *rt, uint64_t seed,
                             uint64_t first_job, uint64_t n_jobs, uint32_t threads,
                             void *stream);
+/* d_init_xyz: DEVICE pointer to this call's n_jobs×3 start points. */
 int sar_render_device_async(const sar_config *cfg, sar_runtime *rt, const double *d_init_xyz,
                             uint64_t first_job, uint64_t n_jobs, uint32_t threads, void *stream);
 int sar_runtime_reset_async(sar_runtime *rt, void *stream);
-/* colourise rows [row0,row0+rows) into device memory d_rgba_u16 (full-image base pointer). */
-int sar_colorize_device_async(const sar_config *cfg, sar_runtime *rt, uint16_t *d_rgba_u16,
-                              float *d_rgba_f32, void *stream);
+/* Recompute Runtime.max (lib.rs:643) and the Depth min/max over rows
+ * [row0,row0+rows) (rows=0: whole image) into the runtime's device scalars. */
+int sar_runtime_max_async(sar_runtime *rt, uint32_t row0, uint32_t rows, void *stream);
+/* Read back / force Runtime.max (synchronises `stream`). */
+int sar_runtime_get_max(sar_runtime *rt, uint32_t *max_out, void *stream);
+int sar_runtime_set_max(sar_runtime *rt, uint32_t max, void *stream);
+/* colorize rows [row0,row0+rows) (rows=0: all) with the CURRENT device max into
+ * the device-resident image of `dst` (NULL = rt's own; a peer = remote store
+ * over NVLink).  sar_runtime_image_download copies image rows to the host. */
+typedef struct sar_peer sar_peer;
+int sar_colorize_rows_async(const sar_config *cfg, sar_runtime *rt, uint32_t row0, uint32_t rows,
+                            sar_peer *dst, void *stream);
+int sar_runtime_image_download(sar_runtime *rt, uint32_t row0, uint32_t rows, uint16_t *rgba_u16,
+                               void *stream);
 int sar_stream_synchronize(sar_runtime *rt, void *stream);
+/* job order counter of the runtime (reset() zeroes it) */
+int sar_runtime_get_job_base(const sar_runtime *rt, uint64_t *job_base);
+int sar_runtime_set_job_base(sar_runtime *rt, uint64_t job_base);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 uint64_t sar_launch_count(void);
 
@@ -202,26 +221,19 @@ int  sar_host_alloc(size_t bytes, void **out);
 void sar_host_free(void *p);
 
 /* Cross-process peer access (one process per GPU, NVLink P2P via CUDA IPC).
- * export: 2 opaque 64-byte handles (accumulator buffers) into out[128].
- * Each rank opens every peer's handles, then sar_runtime_merge_peers()
- * reduces ITS row stripe [row0,row0+rows) over all ranks by reading peer
- * memory directly: count sum, (z, job)-max of the Δp records — the
- * deterministic form of Runtime::merge (lib.rs:708-738), see DESIGN.md §6. */
-#define SAR_IPC_HANDLE_BYTES 128u
-typedef struct sar_peer sar_peer;
+ * A Runtime's accumulators and image live in ONE device allocation; export
+ * gives its 64-byte cudaIpcMemHandle.  Each rank opens every peer's handle,
+ * then sar_runtime_merge_peers_async() reduces ITS row stripe
+ * [row0,row0+rows) over all ranks by reading peer memory directly: counts
+ * add, the Δp record with the greatest (z, earlier job) wins — the
+ * deterministic form of Runtime::merge (lib.rs:708-738), DESIGN.md §6. */
+#define SAR_IPC_HANDLE_BYTES 64u
 int  sar_runtime_ipc_export(const sar_runtime *rt, uint8_t out[SAR_IPC_HANDLE_BYTES]);
 int  sar_peer_open(const uint8_t handle[SAR_IPC_HANDLE_BYTES], uint32_t width, uint32_t height,
                    int local_device, sar_peer **out);
 void sar_peer_close(sar_peer *p);
-int  sar_runtime_merge_peers(sar_runtime *rt, sar_peer *const *peers, int n_peers,
-                             uint32_t row0, uint32_t rows, void *stream);
-/* max over rows [row0,row0+rows) of the merged count (the stripe's share of Runtime.max). */
-int  sar_runtime_stripe_max(sar_runtime *rt, uint32_t row0, uint32_t rows, uint32_t *max_out);
-/* force Runtime.max (after an all-reduce over stripes). */
-int  sar_runtime_set_max(sar_runtime *rt, uint32_t max);
-/* colourise only rows [row0,row0+rows) to host memory (rgba_u16 = full-image base). */
-int  sar_colorize_rows(const sar_config *cfg, sar_runtime *rt, uint32_t row0, uint32_t rows,
-                       uint16_t *rgba_u16);
+int  sar_runtime_merge_peers_async(sar_runtime *rt, sar_peer *const *peers, int n_peers,
+                                   uint32_t row0, uint32_t rows, void *stream);
 
 #ifdef __cplusplus
 }

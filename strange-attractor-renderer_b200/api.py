@@ -1,0 +1,364 @@
+"""Host-side mirror of the reference's public API for the render path, over the C ABI.
+
+Same names, argument meaning and error behaviour as `strange_attractor_renderer` (src/lib.rs):
+
+    Config / View / Colors / Palette / BrighnessConstants / RenderKind      lib.rs:232-492
+    attractors.PolynomialSprott2Degree                                      lib.rs:575-580
+    color_transforms.{poisson_saturne, AdjustedVelocity}                    lib.rs:503-559
+    Runtime.{new, reset, merge}                                             lib.rs:660, 682, 708
+    render(config, runtime)                                                 lib.rs:747
+    colorize(config, runtime) -> FinalImage                                 lib.rs:841
+    ParallelRenderer.{new, shutdown}, render_parallel(...)                  lib.rs:919, 1020, 1051
+
+Everything that computes runs in libsar_b200.so on the GPU; this file only marshals.
+Where the reference panics (dimension mismatch in merge, lib.rs:709-710; empty palette,
+lib.rs:415-418) a `SarError` is raised instead.
+
+One deliberate extension: the reference draws start points from an OS-seeded SmallRng
+(lib.rs:656, 748) and is therefore not reproducible.  `Runtime.new(config, seed=...)` and
+`render_parallel(..., seed=...)` / `initial_points=` make the start points explicit; with no
+seed given an OS-random one is used, as in the reference.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+import os
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _native as N
+from ._native import SarConfig, SarError  # noqa: F401
+
+
+# ---- primitives (lib.rs:79-224) ---------------------------------------------------------
+@dataclass
+class Vec3:
+    x: float
+    y: float
+    z: float
+
+    @staticmethod
+    def new(x: float, y: float, z: float) -> "Vec3":
+        return Vec3(x, y, z)
+
+
+@dataclass
+class EulerAxisRotation:
+    """lib.rs:170-175.  NB the axis is used as given — the reference normalises it only in
+    debug builds (lib.rs:181-183) and its published images come from release builds."""
+
+    axis: Vec3
+    rotation: float
+
+
+# ---- config (lib.rs:226-560) ------------------------------------------------------------
+class RenderKind(enum.Enum):
+    Gas = N.SAR_RENDER_GAS
+    Depth = N.SAR_RENDER_DEPTH
+
+
+@dataclass
+class View:
+    center_camera: Vec3
+    rotation: EulerAxisRotation
+    scale: float
+
+
+@dataclass
+class BrighnessConstants:  # sic, lib.rs:390
+    offset: float = -0.15
+    factor: float = 5.0 / 3.0
+
+
+class Palette:
+    """lib.rs:408-473.  `list` holds the colours WITHOUT the duplicated sentinel the reference
+    appends (lib.rs:418); the library re-creates it."""
+
+    def __init__(self, colors: Sequence[Sequence[float]]):
+        if len(colors) == 0:
+            raise SarError(N.SAR_ERR_INVALID, "Palette::new panics if list.is_empty() (lib.rs:415)")
+        if len(colors) > N.SAR_MAX_PALETTE:
+            raise SarError(N.SAR_ERR_INVALID, f"at most {N.SAR_MAX_PALETTE} palette entries cross the C ABI")
+        self.list = [tuple(float(v) for v in c) for c in colors]
+
+    @staticmethod
+    def new(colors):
+        return Palette(colors)
+
+    @staticmethod
+    def from_rgb(r, g, b) -> "Palette":
+        return Palette(list(zip(r, g, b)))
+
+    def count(self) -> int:
+        return len(self.list)
+
+
+@dataclass
+class Colors:
+    palette: Palette = field(default_factory=lambda: Palette.from_rgb(
+        [1.0, 0.5, 1.0, 0.5, 0.5, 1.0], [1.0, 1.0, 0.5, 1.0, 0.5, 0.5], [0.5, 0.5, 0.5, 1.0, 1.0, 1.0]))
+    brighness: BrighnessConstants = field(default_factory=BrighnessConstants)
+
+
+class attractors:  # namespace, lib.rs:567
+    @dataclass
+    class PolynomialSprott2Degree:
+        x: List[float]
+        y: List[float]
+        z: List[float]
+
+
+class color_transforms:  # namespace, lib.rs:498
+    @dataclass
+    class AdjustedVelocity:
+        offset: float
+        factor: float
+
+    class _PoissonSaturne:
+        """Marker for the fn item `color_transforms::poisson_saturne` (lib.rs:520)."""
+
+        def __repr__(self):
+            return "color_transforms.poisson_saturne"
+
+    poisson_saturne = _PoissonSaturne()
+
+
+@dataclass
+class Config:
+    """lib.rs:265-287; defaults of Config::new (lib.rs:289-307)."""
+
+    attractor: "attractors.PolynomialSprott2Degree"
+    view: View
+    color_transform: object
+    iterations: int = 10_000_000
+    width: int = 1920
+    height: int = 1080
+    render: RenderKind = RenderKind.Gas
+    transparent: bool = True
+    angle: float = 0.0
+    silent: bool = True
+    colors: Colors = field(default_factory=Colors)
+
+    @staticmethod
+    def new(coefficients, view, transform_colors) -> "Config":
+        return Config(coefficients, view, transform_colors)
+
+    @staticmethod
+    def _from_pod(c: SarConfig) -> "Config":
+        att = attractors.PolynomialSprott2Degree(list(c.coef[0]), list(c.coef[1]), list(c.coef[2]))
+        view = View(Vec3(*c.center_camera), EulerAxisRotation(Vec3(*c.axis), c.rotation), c.scale)
+        ct = (color_transforms.poisson_saturne if c.ct_kind == N.SAR_CT_POISSON_SATURNE
+              else color_transforms.AdjustedVelocity(offset=c.ct_offset, factor=c.ct_factor))
+        pal = Palette([tuple(c.palette_rgb[i]) for i in range(c.palette_len)])
+        return Config(att, view, ct, iterations=c.iterations, width=c.width, height=c.height,
+                      render=RenderKind(c.render_kind), transparent=bool(c.transparent), angle=c.angle,
+                      silent=bool(c.silent), colors=Colors(pal, BrighnessConstants(c.bright_offset, c.bright_factor)))
+
+    @staticmethod
+    def poisson_saturne() -> "Config":
+        """Config::poisson_saturne(), lib.rs:310-352 (constants held by the library)."""
+        c = SarConfig()
+        N.check(N.lib().sar_config_poisson_saturne(C.byref(c)))
+        return Config._from_pod(c)
+
+    @staticmethod
+    def solar_sail() -> "Config":
+        """Config::solar_sail(), lib.rs:355-386."""
+        c = SarConfig()
+        N.check(N.lib().sar_config_solar_sail(C.byref(c)))
+        return Config._from_pod(c)
+
+    def to_pod(self) -> SarConfig:
+        c = SarConfig()
+        c.iterations, c.width, c.height = int(self.iterations), int(self.width), int(self.height)
+        c.render_kind = self.render.value
+        c.transparent, c.silent, c.angle = int(bool(self.transparent)), int(bool(self.silent)), float(self.angle)
+        a = self.attractor
+        if not isinstance(a, attractors.PolynomialSprott2Degree):
+            raise SarError(N.SAR_ERR_UNSUPPORTED, "only PolynomialSprott2Degree has a device implementation")
+        for k, lst in enumerate((a.x, a.y, a.z)):
+            if len(lst) != 10:
+                raise SarError(N.SAR_ERR_INVALID, "coefficient lists have 10 entries (lib.rs:577-579)")
+            for i, v in enumerate(lst):
+                c.coef[k][i] = float(v)
+        v = self.view
+        c.center_camera[:] = [v.center_camera.x, v.center_camera.y, v.center_camera.z]
+        c.axis[:] = [v.rotation.axis.x, v.rotation.axis.y, v.rotation.axis.z]
+        c.rotation, c.scale = float(v.rotation.rotation), float(v.scale)
+        t = self.color_transform
+        if isinstance(t, color_transforms.AdjustedVelocity):
+            c.ct_kind, c.ct_offset, c.ct_factor = N.SAR_CT_ADJUSTED_VELOCITY, float(t.offset), float(t.factor)
+        elif t is color_transforms.poisson_saturne:
+            c.ct_kind = N.SAR_CT_POISSON_SATURNE
+        else:
+            raise SarError(N.SAR_ERR_UNSUPPORTED,
+                           "only color_transforms.poisson_saturne and AdjustedVelocity have a device implementation")
+        pal = self.colors.palette
+        c.palette_len = pal.count()
+        for i, rgb in enumerate(pal.list):
+            c.palette_rgb[i][:] = list(rgb)
+        c.bright_offset, c.bright_factor = float(self.colors.brighness.offset), float(self.colors.brighness.factor)
+        return c
+
+
+def _pod(config) -> SarConfig:
+    return config if isinstance(config, SarConfig) else config.to_pod()
+
+
+def seed_points(seed: int, first: int, n: int) -> np.ndarray:
+    """The documented start-point generator (include/sar.h: sar_seed_points), [n,3] f64."""
+    out = np.empty((n, 3), dtype=np.float64)
+    N.check(N.lib().sar_seed_points(seed & (2**64 - 1), first, n, out.ctypes.data_as(N._f64p)))
+    return out
+
+
+FinalImage = np.ndarray  # [height, width, 4] uint16, RGBA — ImageBuffer<Rgba<u16>, Vec<u16>>, lib.rs:625
+
+
+# ---- Runtime (lib.rs:631-739) -----------------------------------------------------------
+class Runtime:
+    """Device-resident count / steps / zbuf / max.  Construct with Runtime.new(config)."""
+
+    def __init__(self, handle, width, height, device, seed, owned=True):
+        self._h, self.width, self.height, self.device = handle, width, height, device
+        self._seed = seed
+        self._draws = 0   # how many start points this Runtime's generator has handed out
+        self._owned = owned
+
+    @staticmethod
+    def new(config, device: int = 0, seed: Optional[int] = None) -> "Runtime":
+        c = _pod(config)
+        h = C.c_void_p()
+        N.check(N.lib().sar_runtime_new(c.width, c.height, device, C.byref(h)))
+        if seed is None:
+            seed = int.from_bytes(os.urandom(8), "little")   # SmallRng::from_os_rng(), lib.rs:656
+        return Runtime(h, c.width, c.height, device, seed)
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) and self._owned:
+            N.lib().sar_runtime_free(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self) -> None:
+        N.check(N.lib().sar_runtime_reset(self._h))
+
+    def merge(self, other: "Runtime") -> None:
+        N.check(N.lib().sar_runtime_merge(self._h, other._h))
+
+    # inspection (the reference keeps these fields private; tests and checkpoints need them)
+    def download(self):
+        """-> (count u32 [H,W], steps f64 [H,W], zbuf f32 [H,W], max)"""
+        count = np.empty((self.height, self.width), dtype=np.uint32)
+        steps = np.empty((self.height, self.width), dtype=np.float64)
+        zbuf = np.empty((self.height, self.width), dtype=np.float32)
+        mx = C.c_uint32()
+        N.check(N.lib().sar_runtime_download(self._h, count.ctypes.data_as(N._u32p), steps.ctypes.data_as(N._f64p),
+                                             zbuf.ctypes.data_as(N._f32p), C.byref(mx)))
+        return count, steps, zbuf, int(mx.value)
+
+    def upload(self, count, steps, zbuf) -> None:
+        count = np.ascontiguousarray(count, dtype=np.uint32)
+        steps = np.ascontiguousarray(steps, dtype=np.float64)
+        zbuf = np.ascontiguousarray(zbuf, dtype=np.float32)
+        if count.shape != (self.height, self.width) or steps.shape != count.shape or zbuf.shape != count.shape:
+            raise SarError(N.SAR_ERR_DIMS, "upload: array shapes must be [height, width]")
+        N.check(N.lib().sar_runtime_upload(self._h, count.ctypes.data_as(N._u32p), steps.ctypes.data_as(N._f64p),
+                                           zbuf.ctypes.data_as(N._f32p)))
+
+
+def render(config, runtime: Runtime, initial_points=None) -> None:
+    """render(&config, &mut runtime), lib.rs:747: one trajectory of config.iterations recorded
+    steps accumulated into `runtime` (which is NOT reset).  The start point comes from the
+    Runtime's generator (seeded at Runtime.new) unless `initial_points` ([n,3] f64) is given, in
+    which case it is n successive render() calls, one per point."""
+    c = _pod(config)
+    if initial_points is None:
+        N.check(N.lib().sar_render_seeded(C.byref(c), runtime._h, runtime._seed & (2**64 - 1), runtime._draws, 1))
+        runtime._draws += 1
+        return
+    pts = np.ascontiguousarray(initial_points, dtype=np.float64).reshape(-1, 3)
+    N.check(N.lib().sar_render(C.byref(c), runtime._h, pts.ctypes.data_as(N._f64p), pts.shape[0]))
+
+
+def colorize(config, runtime: Runtime, want_f32: bool = False):
+    """colorize(&config, &runtime) -> FinalImage, lib.rs:841.  want_f32 additionally returns the
+    pre-quantisation colour buffer ([H,W,4] f32)."""
+    c = _pod(config)
+    out = np.empty((runtime.height, runtime.width, 4), dtype=np.uint16)
+    f = np.empty((runtime.height, runtime.width, 4), dtype=np.float32) if want_f32 else None
+    N.check(N.lib().sar_colorize(C.byref(c), runtime._h, out.ctypes.data_as(N._u16p),
+                                 f.ctypes.data_as(N._f32p) if want_f32 else None))
+    return (out, f) if want_f32 else out
+
+
+# ---- ParallelRenderer / render_parallel (lib.rs:906-1082) -------------------------------
+class ParallelRenderer:
+    """`threads` plays available_parallelism() (lib.rs:920): concurrent trajectory lanes per
+    device; 0 = library default (SM count × 256)."""
+
+    def __init__(self, devices: Optional[Sequence[int]] = None, threads: int = 0):
+        self._h = C.c_void_p()
+        if devices:
+            arr = (C.c_int * len(devices))(*devices)
+            N.check(N.lib().sar_renderer_new(arr, len(devices), threads, C.byref(self._h)))
+        else:
+            N.check(N.lib().sar_renderer_new(None, 0, threads, C.byref(self._h)))
+
+    @staticmethod
+    def new(devices=None, threads: int = 0) -> "ParallelRenderer":
+        return ParallelRenderer(devices, threads)
+
+    default = new
+
+    def num_threads(self) -> int:
+        n = C.c_uint64()
+        N.check(N.lib().sar_renderer_num_threads(self._h, C.byref(n)))
+        return int(n.value)
+
+    def shutdown(self) -> None:
+        if getattr(self, "_h", None):
+            N.lib().sar_renderer_shutdown(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.shutdown()
+        except Exception:
+            pass
+
+    def runtime(self) -> Runtime:
+        """The merged Runtime of the last render_parallel (borrowed; valid until the next call)."""
+        h = C.c_void_p()
+        N.check(N.lib().sar_renderer_runtime(self._h, C.byref(h)))
+        w, hh, dev = C.c_uint32(), C.c_uint32(), C.c_int()
+        N.check(N.lib().sar_runtime_dims(h, C.byref(w), C.byref(hh), C.byref(dev)))
+        return Runtime(h, int(w.value), int(hh.value), int(dev.value), 0, owned=False)
+
+
+def render_parallel(renderer: ParallelRenderer, config, jobs_per_thread: int, seed: Optional[int] = None,
+                    initial_points=None, out: Optional[np.ndarray] = None) -> FinalImage:
+    """render_parallel(&mut renderer, config, jobs_per_thread) -> FinalImage, lib.rs:1051.
+    num_threads*jobs_per_thread jobs of iterations/num_threads/jobs_per_thread steps each."""
+    c = _pod(config)
+    if seed is None:
+        seed = int.from_bytes(os.urandom(8), "little")
+    if out is None:
+        out = np.empty((c.height, c.width, 4), dtype=np.uint16)
+    pts_p = None
+    if initial_points is not None:
+        pts = np.ascontiguousarray(initial_points, dtype=np.float64).reshape(-1, 3)
+        if pts.shape[0] < renderer.num_threads() * jobs_per_thread:
+            raise SarError(N.SAR_ERR_INVALID, "initial_points must hold num_threads*jobs_per_thread points")
+        pts_p = pts.ctypes.data_as(N._f64p)
+    N.check(N.lib().sar_render_parallel(renderer._h, C.byref(c), jobs_per_thread, seed & (2**64 - 1), pts_p,
+                                        out.ctypes.data_as(N._u16p)))
+    return out

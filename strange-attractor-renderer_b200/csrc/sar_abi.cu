@@ -1,0 +1,748 @@
+// sar_abi.cu — the extern "C" boundary declared in include/sar.h, and the host-side logic
+// behind it: Config → kernel constants (the reference does this at lib.rs:754-764 at the
+// top of render()), Runtime ownership (lib.rs:631-699), render()/colorize()/
+// render_parallel() orchestration (lib.rs:747, 841, 1051).  No CPU compute fallback:
+// every entry point that needs a GPU fails with SAR_ERR_CUDA when there is none.
+#include "../../include/sar.h"
+#include "sar_device.cuh"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace sar;
+
+// ---------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------
+static thread_local std::string g_err = "";
+
+static int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define SAR_CUDA(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t e_ = (expr);                                                                    \
+        if (e_ != cudaSuccess) {                                                                    \
+            (void)cudaGetLastError();                                                               \
+            return fail(e_ == cudaErrorMemoryAllocation ? SAR_ERR_NOMEM : SAR_ERR_CUDA, "%s: %s (%s:%d)", #expr, \
+                        cudaGetErrorString(e_), __FILE__, __LINE__);                                \
+        }                                                                                           \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// handles
+// ---------------------------------------------------------------------------------------------
+struct sar_runtime {
+    int device = 0;
+    uint32_t w = 0, h = 0;
+    size_t npix = 0;
+    // one device allocation: rec | fast | image | scal   (so one IPC handle exports it all)
+    void *block = nullptr;
+    size_t block_bytes = 0;
+    ulonglong2 *rec = nullptr;
+    unsigned long long *fast = nullptr;
+    uint16_t *image = nullptr;       // RGBA u16, FinalImage (lib.rs:625)
+    Scalars *scal = nullptr;
+    cudaStream_t stream = nullptr;
+    uint64_t job_base = 0;
+    int sm_count = 148;
+    // lazily allocated scratch
+    double *d_init = nullptr; size_t d_init_cap = 0;
+    void *d_scratch = nullptr; size_t d_scratch_cap = 0;
+    void *h_pinned = nullptr;
+};
+
+struct sar_peer {
+    int local_device = 0;
+    uint32_t w = 0, h = 0;
+    void *block = nullptr;           // cudaIpcOpenMemHandle mapping (or a borrowed in-process pointer)
+    bool ipc = false;
+    ulonglong2 *rec = nullptr;
+    unsigned long long *fast = nullptr;
+    uint16_t *image = nullptr;
+    Scalars *scal = nullptr;
+};
+
+struct sar_renderer {
+    std::vector<int> devices;
+    std::vector<sar_runtime *> rts;
+    std::vector<sar_peer> inproc;    // views of rts[d>0] for the first device
+    std::vector<bool> direct;        // peer access from device 0 to device d enabled
+    uint32_t threads_per_device = 0;
+};
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static void layout(size_t npix, size_t &off_fast, size_t &off_image, size_t &off_scal, size_t &total)
+{
+    off_fast = align_up(npix * sizeof(ulonglong2), 256);
+    off_image = off_fast + align_up(npix * sizeof(unsigned long long), 256);
+    off_scal = off_image + align_up(npix * 4 * sizeof(uint16_t), 256);
+    total = off_scal + 256;
+}
+
+static cudaStream_t pick(const sar_runtime *rt, void *stream) { return stream ? (cudaStream_t)stream : rt->stream; }
+
+static int check_dims(uint32_t w, uint32_t h)
+{
+    if (w == 0 || h == 0) return fail(SAR_ERR_INVALID, "width and height must be non-zero (got %ux%u)", w, h);
+    if ((unsigned long long)w * h > (1ull << 31)) return fail(SAR_ERR_INVALID, "width*height must be <= 2^31 (got %ux%u)", w, h);
+    return SAR_OK;
+}
+
+static int check_config(const sar_config *cfg, const sar_runtime *rt)
+{
+    if (!cfg) return fail(SAR_ERR_INVALID, "cfg is NULL");
+    if (cfg->palette_len == 0 || cfg->palette_len > SAR_MAX_PALETTE)   // Palette::new panics on an empty list, lib.rs:415-418
+        return fail(SAR_ERR_INVALID, "palette_len must be in 1..%u (got %u)", SAR_MAX_PALETTE, cfg->palette_len);
+    if (cfg->ct_kind > SAR_CT_ADJUSTED_VELOCITY)
+        return fail(SAR_ERR_UNSUPPORTED, "ct_kind %u has no device implementation", cfg->ct_kind);
+    if (cfg->render_kind > SAR_RENDER_DEPTH) return fail(SAR_ERR_INVALID, "render_kind %u", cfg->render_kind);
+    if (rt && (cfg->width != rt->w || cfg->height != rt->h))
+        return fail(SAR_ERR_DIMS, "config is %ux%u but runtime is %ux%u", cfg->width, cfg->height, rt->w, rt->h);
+    return SAR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Config → kernel constants.  Host libm sin/cos so that the oracle and the device consume the
+// same f64 values (the reference calls the same glibc functions through Rust's f64::sin/cos).
+// ---------------------------------------------------------------------------------------------
+static void rotation_matrix(const double ax[3], double rot, double m[3][3])   // lib.rs:179-195, release: no normalize
+{
+    const double x = ax[0], y = ax[1], z = ax[2];
+    const double c = std::cos(rot);
+    const double c1 = 1. - c;
+    const double s = std::sin(rot);
+    m[0][0] = c + x * x * c1;     m[0][1] = x * y * c1 - z * s; m[0][2] = x * z * c1 + y * s;
+    m[1][0] = y * x * c1 + z * s; m[1][1] = c + y * y * c1;     m[1][2] = y * z * c1 - x * s;
+    m[2][0] = z * x * c1 - y * s; m[2][1] = z * y * c1 + x * s; m[2][2] = c + z * z * c1;
+}
+
+static void make_iter_params(const sar_config *cfg, sar_runtime *rt, IterParams &p)
+{
+    memset(&p, 0, sizeof p);
+    for (int k = 0; k < 3; ++k) {
+        for (int i = 0; i < 10; ++i) p.c[k][i] = cfg->coef[k][i];
+        volatile double zero = 0.0, one = 1.0;                  // `sum = 0.; sum += 1. * c0`, lib.rs:589-603
+        p.c[k][0] = zero + one * cfg->coef[k][0];
+    }
+    rotation_matrix(cfg->axis, cfg->rotation, p.m);                              // lib.rs:755
+    p.sv = std::sin(cfg->angle);                                                 // lib.rs:756
+    p.cv = std::cos(cfg->angle);                                                 // lib.rs:757
+    p.ccx = cfg->center_camera[0]; p.ccy = cfg->center_camera[1]; p.ccz = cfg->center_camera[2];
+    const double width = (double)cfg->width, height = (double)cfg->height;       // lib.rs:760-762
+    p.ws = width * cfg->scale;                                                   // lib.rs:763
+    p.sam = 0.5 / cfg->scale;                                                    // lib.rs:764
+    p.half_h = height / 2.;                                                      // lib.rs:786
+    p.ct_offset = cfg->ct_offset; p.ct_factor = cfg->ct_factor;
+    p.fast = rt->fast; p.rec = rt->rec; p.scal = rt->scal;
+    p.W = cfg->width; p.H = cfg->height; p.ct_kind = cfg->ct_kind;
+    p.iterations = cfg->iterations;
+}
+
+static void make_color_params(const sar_config *cfg, ColorParams &c, uint32_t row0, uint32_t rows)
+{
+    memset(&c, 0, sizeof c);
+    for (uint32_t i = 0; i < cfg->palette_len; ++i)
+        for (int k = 0; k < 3; ++k) c.pal[i][k] = cfg->palette_rgb[i][k];
+    for (int k = 0; k < 3; ++k) c.pal[cfg->palette_len][k] = cfg->palette_rgb[cfg->palette_len - 1][k];  // lib.rs:418
+    c.pal_len = (double)cfg->palette_len;                                        // lib.rs:421
+    c.bright_offset = cfg->bright_offset; c.bright_factor = cfg->bright_factor;
+    c.palette_len = cfg->palette_len; c.transparent = cfg->transparent; c.render_kind = cfg->render_kind;
+    c.W = cfg->width; c.H = cfg->height; c.row0 = row0; c.rows = rows;
+}
+
+static uint32_t default_lanes(const sar_runtime *rt) { return (uint32_t)rt->sm_count * 256u; }
+
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+uint32_t sar_abi_version(void) { return SAR_ABI_VERSION; }
+const char *sar_last_error(void) { return g_err.c_str(); }
+uint64_t sar_launch_count(void) { return launch_count(); }
+
+int sar_device_count(int *count)
+{
+    if (!count) return fail(SAR_ERR_INVALID, "count is NULL");
+    *count = 0;
+    SAR_CUDA(cudaGetDeviceCount(count));
+    return SAR_OK;
+}
+
+// ---- presets (restated from lib.rs:289-307, 310-352, 355-386, 397-404, 480-491) -------------
+int sar_config_defaults(sar_config *c)
+{
+    if (!c) return fail(SAR_ERR_INVALID, "cfg is NULL");
+    c->iterations = 10000000ull;          // lib.rs:291
+    c->width = 1920; c->height = 1080;    // lib.rs:292-293
+    c->render_kind = SAR_RENDER_GAS;      // lib.rs:295
+    c->transparent = 1;                   // lib.rs:296
+    c->angle = 0.0;                       // lib.rs:297
+    c->silent = 1;                        // lib.rs:299
+    c->palette_len = 6; c->reserved0 = 0;
+    const double r[6] = {1., 0.5, 1., 0.5, 0.5, 1.}, g[6] = {1., 1., 0.5, 1., 0.5, 0.5}, b[6] = {0.5, 0.5, 0.5, 1., 1., 1.};  // lib.rs:483-487
+    memset(c->palette_rgb, 0, sizeof c->palette_rgb);
+    for (int i = 0; i < 6; ++i) { c->palette_rgb[i][0] = r[i]; c->palette_rgb[i][1] = g[i]; c->palette_rgb[i][2] = b[i]; }
+    c->bright_offset = -0.15;             // lib.rs:400
+    c->bright_factor = 5. / 3.;           // lib.rs:401
+    return SAR_OK;
+}
+
+int sar_config_poisson_saturne(sar_config *c)
+{
+    if (!c) return fail(SAR_ERR_INVALID, "cfg is NULL");
+    memset(c, 0, sizeof *c);
+    const double x[10] = {0.021, 1.182, -1.183, 0.128, -1.12, -0.641, -1.152, -0.834, -0.97, 0.722};
+    const double y[10] = {0.243038, -0.825, -1.2, -0.835443, -0.835443, -0.364557, 0.458, 0.622785, -0.394937, -1.032911};
+    const double z[10] = {-0.455696, 0.673, 0.915, -0.258228, -0.495, -0.264, -0.432, -0.416, -0.877, -0.3};
+    memcpy(c->coef[0], x, sizeof x); memcpy(c->coef[1], y, sizeof y); memcpy(c->coef[2], z, sizeof z);
+    c->center_camera[0] = -0.005; c->center_camera[1] = 0.262; c->center_camera[2] = -0.366 + 0.12;   // lib.rs:335-340
+    c->axis[0] = 0.304289493528802; c->axis[1] = 0.760492682863655; c->axis[2] = 0.573636455813981;
+    c->rotation = 1.78268191887446;
+    c->scale = 1.;
+    c->ct_kind = SAR_CT_POISSON_SATURNE;
+    return sar_config_defaults(c);
+}
+
+int sar_config_solar_sail(sar_config *c)
+{
+    if (!c) return fail(SAR_ERR_INVALID, "cfg is NULL");
+    memset(c, 0, sizeof *c);
+    const double x[10] = {0.744304, -0.546835, 0.121519, -0.653165, 0.399, 0.379, 0.44, 1.014, -0.805063, 0.377};
+    const double y[10] = {-0.683, 0.531646, -0.04557, -1.2, -0.546835, 0.091139, 0.744304, -0.273418, -0.349367, -0.531646};
+    const double z[10] = {0.712, 0.744304, -0.577215, 0.966, 0.04557, 1.063291, 0.01519, -0.425316, 0.212658, -0.01519};
+    memcpy(c->coef[0], x, sizeof x); memcpy(c->coef[1], y, sizeof y); memcpy(c->coef[2], z, sizeof z);
+    c->center_camera[0] = 0.28; c->center_camera[1] = -0.12; c->center_camera[2] = 0.22;
+    c->axis[0] = 0.02466; c->axis[1] = 0.4618; c->axis[2] = -0.54789;
+    c->rotation = 2.2195;
+    c->scale = 1.7;
+    c->ct_kind = SAR_CT_ADJUSTED_VELOCITY;
+    c->ct_factor = -0.2; c->ct_offset = 0.8;                   // lib.rs:381-384
+    return sar_config_defaults(c);
+}
+
+// ---- start points ----------------------------------------------------------------------------
+int sar_seed_points(uint64_t seed, uint64_t first, uint64_t n, double *out)
+{
+    if (!out && n) return fail(SAR_ERR_INVALID, "out_xyz is NULL");
+    for (uint64_t k = 0; k < n; ++k)
+        for (uint64_t c = 0; c < 3; ++c) {
+            uint64_t z = seed + (3 * (first + k) + c + 1) * 0x9E3779B97F4A7C15ull;
+            z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+            z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+            z ^= z >> 31;
+            out[3 * k + c] = ((double)(z >> 11) * 0x1.0p-53) * 0.1;
+        }
+    return SAR_OK;
+}
+
+// ---- Runtime -----------------------------------------------------------------------------------
+int sar_runtime_new(uint32_t width, uint32_t height, int device, sar_runtime **out)
+{
+    if (!out) return fail(SAR_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (int rc = check_dims(width, height)) return rc;
+    int ndev = 0;
+    SAR_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(SAR_ERR_CUDA, "CUDA device %d not available (%d visible)", device, ndev);
+    SAR_CUDA(cudaSetDevice(device));
+    sar_runtime *rt = new (std::nothrow) sar_runtime();
+    if (!rt) return fail(SAR_ERR_NOMEM, "host allocation failed");
+    rt->device = device; rt->w = width; rt->h = height; rt->npix = (size_t)width * height;
+    size_t of, oi, os, total;
+    layout(rt->npix, of, oi, os, total);
+    cudaError_t e = cudaMalloc(&rt->block, total);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); delete rt; return fail(SAR_ERR_NOMEM, "cudaMalloc(%zu bytes): %s", total, cudaGetErrorString(e)); }
+    rt->block_bytes = total;
+    rt->rec = (ulonglong2 *)rt->block;
+    rt->fast = (unsigned long long *)((char *)rt->block + of);
+    rt->image = (uint16_t *)((char *)rt->block + oi);
+    rt->scal = (Scalars *)((char *)rt->block + os);
+    e = cudaStreamCreateWithFlags(&rt->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { cudaFree(rt->block); delete rt; return fail(SAR_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+    cudaDeviceGetAttribute(&rt->sm_count, cudaDevAttrMultiProcessorCount, device);
+    *out = rt;
+    int rc = sar_runtime_reset(rt);
+    if (rc) { sar_runtime_free(rt); *out = nullptr; }
+    return rc;
+}
+
+void sar_runtime_free(sar_runtime *rt)
+{
+    if (!rt) return;
+    cudaSetDevice(rt->device);
+    if (rt->stream) { cudaStreamSynchronize(rt->stream); cudaStreamDestroy(rt->stream); }
+    cudaFree(rt->block); cudaFree(rt->d_init); cudaFree(rt->d_scratch);
+    if (rt->h_pinned) cudaFreeHost(rt->h_pinned);
+    delete rt;
+}
+
+int sar_runtime_reset_async(sar_runtime *rt, void *stream)
+{
+    if (!rt) return fail(SAR_ERR_INVALID, "runtime is NULL");
+    SAR_CUDA(cudaSetDevice(rt->device));
+    launch_reset(rt->fast, rt->rec, rt->scal, rt->npix, pick(rt, stream));
+    SAR_CUDA(cudaGetLastError());
+    rt->job_base = 0;
+    return SAR_OK;
+}
+int sar_runtime_reset(sar_runtime *rt)
+{
+    if (int rc = sar_runtime_reset_async(rt, nullptr)) return rc;
+    SAR_CUDA(cudaStreamSynchronize(rt->stream));
+    return SAR_OK;
+}
+
+int sar_runtime_dims(const sar_runtime *rt, uint32_t *w, uint32_t *h, int *device)
+{
+    if (!rt) return fail(SAR_ERR_INVALID, "runtime is NULL");
+    if (w) *w = rt->w;
+    if (h) *h = rt->h;
+    if (device) *device = rt->device;
+    return SAR_OK;
+}
+int sar_runtime_get_job_base(const sar_runtime *rt, uint64_t *jb)
+{
+    if (!rt || !jb) return fail(SAR_ERR_INVALID, "NULL argument");
+    *jb = rt->job_base;
+    return SAR_OK;
+}
+int sar_runtime_set_job_base(sar_runtime *rt, uint64_t jb)
+{
+    if (!rt) return fail(SAR_ERR_INVALID, "runtime is NULL");
+    rt->job_base = jb;
+    return SAR_OK;
+}
+
+static int ensure_scratch(sar_runtime *rt, size_t bytes)
+{
+    if (rt->d_scratch_cap >= bytes) return SAR_OK;
+    cudaFree(rt->d_scratch); rt->d_scratch = nullptr; rt->d_scratch_cap = 0;
+    SAR_CUDA(cudaMalloc(&rt->d_scratch, bytes));
+    rt->d_scratch_cap = bytes;
+    return SAR_OK;
+}
+
+int sar_runtime_download(const sar_runtime *crt, uint32_t *count, double *steps, float *zbuf, uint32_t *max)
+{
+    sar_runtime *rt = const_cast<sar_runtime *>(crt);
+    if (!rt) return fail(SAR_ERR_INVALID, "runtime is NULL");
+    SAR_CUDA(cudaSetDevice(rt->device));
+    const size_t n = rt->npix;
+    const size_t oc = 0, os = align_up(n * 4, 256), oz = os + align_up(n * 8, 256), total = oz + align_up(n * 4, 256);
+    if (int rc = ensure_scratch(rt, total)) return rc;
+    char *base = (char *)rt->d_scratch;
+    launch_unpack(rt->fast, rt->rec, rt->scal, n, (uint32_t *)(base + oc), (double *)(base + os), (float *)(base + oz), rt->stream);
+    SAR_CUDA(cudaGetLastError());
+    if (count) SAR_CUDA(cudaMemcpyAsync(count, base + oc, n * 4, cudaMemcpyDeviceToHost, rt->stream));
+    if (steps) SAR_CUDA(cudaMemcpyAsync(steps, base + os, n * 8, cudaMemcpyDeviceToHost, rt->stream));
+    if (zbuf) SAR_CUDA(cudaMemcpyAsync(zbuf, base + oz, n * 4, cudaMemcpyDeviceToHost, rt->stream));
+    if (max) {
+        if (int rc = sar_runtime_max_async(rt, 0, 0, nullptr)) return rc;
+        if (int rc = sar_runtime_get_max(rt, max, nullptr)) return rc;
+    }
+    SAR_CUDA(cudaStreamSynchronize(rt->stream));
+    return SAR_OK;
+}
+
+int sar_runtime_upload(sar_runtime *rt, const uint32_t *count, const double *steps, const float *zbuf)
+{
+    if (!rt || !count || !steps || !zbuf) return fail(SAR_ERR_INVALID, "NULL argument");
+    SAR_CUDA(cudaSetDevice(rt->device));
+    const size_t n = rt->npix;
+    const size_t oc = 0, os = align_up(n * 4, 256), oz = os + align_up(n * 8, 256), total = oz + align_up(n * 4, 256);
+    if (int rc = ensure_scratch(rt, total)) return rc;
+    char *base = (char *)rt->d_scratch;
+    SAR_CUDA(cudaMemcpyAsync(base + oc, count, n * 4, cudaMemcpyHostToDevice, rt->stream));
+    SAR_CUDA(cudaMemcpyAsync(base + os, steps, n * 8, cudaMemcpyHostToDevice, rt->stream));
+    SAR_CUDA(cudaMemcpyAsync(base + oz, zbuf, n * 4, cudaMemcpyHostToDevice, rt->stream));
+    launch_pack(rt->fast, rt->rec, rt->scal, n, (const uint32_t *)(base + oc), (const double *)(base + os), (const float *)(base + oz), rt->stream);
+    SAR_CUDA(cudaGetLastError());
+    SAR_CUDA(cudaStreamSynchronize(rt->stream));
+    if (rt->job_base == 0) rt->job_base = 1;   // uploaded records carry job key 0: they keep every future tie
+    return SAR_OK;
+}
+
+int sar_runtime_merge(sar_runtime *dst, const sar_runtime *src)
+{
+    if (!dst || !src) return fail(SAR_ERR_INVALID, "NULL argument");
+    if (dst->w != src->w || dst->h != src->h)                   // assert_eq!, lib.rs:709-710
+        return fail(SAR_ERR_DIMS, "merge: %ux%u vs %ux%u", dst->w, dst->h, src->w, src->h);
+    SAR_CUDA(cudaSetDevice(src->device));
+    SAR_CUDA(cudaStreamSynchronize(src->stream));
+    SAR_CUDA(cudaSetDevice(dst->device));
+    const unsigned long long *sfast = src->fast;
+    const ulonglong2 *srec = src->rec;
+    const Scalars *sscal = src->scal;
+    if (src->device != dst->device) {   // stage the source accumulators on dst's device
+        if (int rc = ensure_scratch(dst, src->block_bytes)) return rc;
+        SAR_CUDA(cudaMemcpyPeerAsync(dst->d_scratch, dst->device, src->block, src->device, src->block_bytes, dst->stream));
+        size_t of, oi, os, total;
+        layout(src->npix, of, oi, os, total);
+        srec = (const ulonglong2 *)dst->d_scratch;
+        sfast = (const unsigned long long *)((char *)dst->d_scratch + of);
+        sscal = (const Scalars *)((char *)dst->d_scratch + os);
+    }
+    launch_merge(dst->fast, dst->rec, dst->scal, sfast, srec, sscal, dst->npix, dst->stream);
+    SAR_CUDA(cudaGetLastError());
+    SAR_CUDA(cudaStreamSynchronize(dst->stream));
+    if (src->job_base > dst->job_base) dst->job_base = src->job_base;
+    return SAR_OK;
+}
+
+// ---- render ------------------------------------------------------------------------------------
+static int render_launch(const sar_config *cfg, sar_runtime *rt, const double *d_init, uint64_t seed,
+                         uint64_t first_job, uint64_t n_jobs, uint32_t threads, cudaStream_t s)
+{
+    if (int rc = check_config(cfg, rt)) return rc;
+    SAR_CUDA(cudaSetDevice(rt->device));
+    IterParams p;
+    make_iter_params(cfg, rt, p);
+    p.init = d_init; p.seed = seed; p.first_job = first_job; p.n_jobs = n_jobs;
+    const uint64_t key0 = rt->job_base + first_job;
+    p.job_key0 = key0 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (unsigned int)key0;
+    launch_iterate(p, threads ? threads : default_lanes(rt), s);
+    SAR_CUDA(cudaGetLastError());
+    rt->job_base = key0 + n_jobs;
+    return SAR_OK;
+}
+
+int sar_render_seeded_async(const sar_config *cfg, sar_runtime *rt, uint64_t seed, uint64_t first_job,
+                            uint64_t n_jobs, uint32_t threads, void *stream)
+{
+    if (!rt) return fail(SAR_ERR_INVALID, "runtime is NULL");
+    return render_launch(cfg, rt, nullptr, seed, first_job, n_jobs, threads, pick(rt, stream));
+}
+int sar_render_device_async(const sar_config *cfg, sar_runtime *rt, const double *d_init_xyz, uint64_t first_job,
+                            uint64_t n_jobs, uint32_t threads, void *stream)
+{
+    if (!rt) return fail(SAR_ERR_INVALID, "runtime is NULL");
+    if (!d_init_xyz && n_jobs) return fail(SAR_ERR_INVALID, "d_init_xyz is NULL");
+    return render_launch(cfg, rt, d_init_xyz, 0, first_job, n_jobs, threads, pick(rt, stream));
+}
+
+static int upload_init(sar_runtime *rt, const double *init_xyz, uint64_t n_jobs, cudaStream_t s)
+{
+    const size_t bytes = (size_t)n_jobs * 3 * sizeof(double);
+    if (rt->d_init_cap < bytes) {
+        cudaFree(rt->d_init); rt->d_init = nullptr; rt->d_init_cap = 0;
+        SAR_CUDA(cudaMalloc((void **)&rt->d_init, bytes));
+        rt->d_init_cap = bytes;
+    }
+    SAR_CUDA(cudaMemcpyAsync(rt->d_init, init_xyz, bytes, cudaMemcpyHostToDevice, s));
+    return SAR_OK;
+}
+
+int sar_render(const sar_config *cfg, sar_runtime *rt, const double *init_xyz, uint64_t n_jobs)
+{
+    if (!rt) return fail(SAR_ERR_INVALID, "runtime is NULL");
+    if (!init_xyz && n_jobs) return fail(SAR_ERR_INVALID, "init_xyz is NULL");
+    if (int rc = check_config(cfg, rt)) return rc;
+    if (n_jobs == 0) return SAR_OK;
+    SAR_CUDA(cudaSetDevice(rt->device));
+    if (int rc = upload_init(rt, init_xyz, n_jobs, rt->stream)) return rc;
+    if (int rc = render_launch(cfg, rt, rt->d_init, 0, 0, n_jobs, 0, rt->stream)) return rc;
+    SAR_CUDA(cudaStreamSynchronize(rt->stream));
+    return SAR_OK;
+}
+
+int sar_render_seeded(const sar_config *cfg, sar_runtime *rt, uint64_t seed, uint64_t first_job, uint64_t n_jobs)
+{
+    if (int rc = sar_render_seeded_async(cfg, rt, seed, first_job, n_jobs, 0, nullptr)) return rc;
+    SAR_CUDA(cudaStreamSynchronize(rt->stream));
+    return SAR_OK;
+}
+
+// ---- max / colorize ----------------------------------------------------------------------------
+int sar_runtime_max_async(sar_runtime *rt, uint32_t row0, uint32_t rows, void *stream)
+{
+    if (!rt) return fail(SAR_ERR_INVALID, "runtime is NULL");
+    if (rows == 0) { row0 = 0; rows = rt->h; }
+    if ((uint64_t)row0 + rows > rt->h) return fail(SAR_ERR_INVALID, "rows [%u,%u) outside image height %u", row0, row0 + rows, rt->h);
+    SAR_CUDA(cudaSetDevice(rt->device));
+    cudaStream_t s = pick(rt, stream);
+    const unsigned int init[3] = {0u, ZKEY_ZERO, ZKEY_FLT_MAX};   // max, zmax_key, zmin_key (fold seed lib.rs:882)
+    SAR_CUDA(cudaMemcpyAsync(&rt->scal->max, init, sizeof init, cudaMemcpyHostToDevice, s));
+    launch_max(rt->fast, rt->rec, rt->scal, (size_t)row0 * rt->w, (size_t)rows * rt->w, s);
+    SAR_CUDA(cudaGetLastError());
+    return SAR_OK;
+}
+int sar_runtime_get_max(sar_runtime *rt, uint32_t *max_out, void *stream)
+{
+    if (!rt || !max_out) return fail(SAR_ERR_INVALID, "NULL argument");
+    SAR_CUDA(cudaSetDevice(rt->device));
+    cudaStream_t s = pick(rt, stream);
+    SAR_CUDA(cudaMemcpyAsync(max_out, &rt->scal->max, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    SAR_CUDA(cudaStreamSynchronize(s));
+    return SAR_OK;
+}
+int sar_runtime_set_max(sar_runtime *rt, uint32_t max, void *stream)
+{
+    if (!rt) return fail(SAR_ERR_INVALID, "runtime is NULL");
+    SAR_CUDA(cudaSetDevice(rt->device));
+    cudaStream_t s = pick(rt, stream);
+    SAR_CUDA(cudaMemcpyAsync(&rt->scal->max, &max, sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    SAR_CUDA(cudaStreamSynchronize(s));
+    return SAR_OK;
+}
+
+int sar_colorize_rows_async(const sar_config *cfg, sar_runtime *rt, uint32_t row0, uint32_t rows, sar_peer *dst, void *stream)
+{
+    if (!rt) return fail(SAR_ERR_INVALID, "runtime is NULL");
+    if (int rc = check_config(cfg, rt)) return rc;
+    if (rows == 0) { row0 = 0; rows = rt->h; }
+    if ((uint64_t)row0 + rows > rt->h) return fail(SAR_ERR_INVALID, "rows [%u,%u) outside image height %u", row0, row0 + rows, rt->h);
+    if (dst && (dst->w != rt->w || dst->h != rt->h)) return fail(SAR_ERR_DIMS, "peer image is %ux%u, runtime %ux%u", dst->w, dst->h, rt->w, rt->h);
+    SAR_CUDA(cudaSetDevice(rt->device));
+    ColorParams cp;
+    make_color_params(cfg, cp, row0, rows);
+    launch_colorize(cp, rt->fast, rt->rec, rt->scal, dst ? dst->image : rt->image, nullptr, pick(rt, stream));
+    SAR_CUDA(cudaGetLastError());
+    return SAR_OK;
+}
+
+int sar_runtime_image_download(sar_runtime *rt, uint32_t row0, uint32_t rows, uint16_t *rgba, void *stream)
+{
+    if (!rt || !rgba) return fail(SAR_ERR_INVALID, "NULL argument");
+    if (rows == 0) { row0 = 0; rows = rt->h; }
+    if ((uint64_t)row0 + rows > rt->h) return fail(SAR_ERR_INVALID, "rows outside image");
+    SAR_CUDA(cudaSetDevice(rt->device));
+    cudaStream_t s = pick(rt, stream);
+    const size_t off = (size_t)row0 * rt->w * 4, cnt = (size_t)rows * rt->w * 4;
+    SAR_CUDA(cudaMemcpyAsync(rgba + off, rt->image + off, cnt * sizeof(uint16_t), cudaMemcpyDeviceToHost, s));
+    SAR_CUDA(cudaStreamSynchronize(s));
+    return SAR_OK;
+}
+
+int sar_colorize(const sar_config *cfg, const sar_runtime *crt, uint16_t *rgba_u16, float *rgba_f32)
+{
+    sar_runtime *rt = const_cast<sar_runtime *>(crt);
+    if (!rt) return fail(SAR_ERR_INVALID, "runtime is NULL");
+    if (!rgba_u16 && !rgba_f32) return fail(SAR_ERR_INVALID, "no output buffer");
+    if (int rc = check_config(cfg, rt)) return rc;
+    SAR_CUDA(cudaSetDevice(rt->device));
+    if (int rc = sar_runtime_max_async(rt, 0, 0, nullptr)) return rc;
+    float *d_f32 = nullptr;
+    if (rgba_f32) {
+        if (int rc = ensure_scratch(rt, rt->npix * 4 * sizeof(float))) return rc;
+        d_f32 = (float *)rt->d_scratch;
+    }
+    ColorParams cp;
+    make_color_params(cfg, cp, 0, rt->h);
+    launch_colorize(cp, rt->fast, rt->rec, rt->scal, rt->image, d_f32, rt->stream);
+    SAR_CUDA(cudaGetLastError());
+    if (rgba_u16) SAR_CUDA(cudaMemcpyAsync(rgba_u16, rt->image, rt->npix * 4 * sizeof(uint16_t), cudaMemcpyDeviceToHost, rt->stream));
+    if (rgba_f32) SAR_CUDA(cudaMemcpyAsync(rgba_f32, d_f32, rt->npix * 4 * sizeof(float), cudaMemcpyDeviceToHost, rt->stream));
+    SAR_CUDA(cudaStreamSynchronize(rt->stream));
+    return SAR_OK;
+}
+
+int sar_stream_synchronize(sar_runtime *rt, void *stream)
+{
+    if (!rt) return fail(SAR_ERR_INVALID, "runtime is NULL");
+    SAR_CUDA(cudaSetDevice(rt->device));
+    SAR_CUDA(cudaStreamSynchronize(pick(rt, stream)));
+    return SAR_OK;
+}
+
+// ---- pinned host memory ------------------------------------------------------------------------
+int sar_host_alloc(size_t bytes, void **out)
+{
+    if (!out) return fail(SAR_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    SAR_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
+    return SAR_OK;
+}
+void sar_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+// ---- cross-process peers ------------------------------------------------------------------------
+int sar_runtime_ipc_export(const sar_runtime *rt, uint8_t out[SAR_IPC_HANDLE_BYTES])
+{
+    if (!rt || !out) return fail(SAR_ERR_INVALID, "NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == SAR_IPC_HANDLE_BYTES, "IPC handle size");
+    SAR_CUDA(cudaSetDevice(rt->device));
+    cudaIpcMemHandle_t h;
+    SAR_CUDA(cudaIpcGetMemHandle(&h, rt->block));
+    memcpy(out, &h, sizeof h);
+    return SAR_OK;
+}
+
+static void peer_view(sar_peer *p, void *block, uint32_t w, uint32_t h)
+{
+    size_t of, oi, os, total;
+    layout((size_t)w * h, of, oi, os, total);
+    p->w = w; p->h = h; p->block = block;
+    p->rec = (ulonglong2 *)block;
+    p->fast = (unsigned long long *)((char *)block + of);
+    p->image = (uint16_t *)((char *)block + oi);
+    p->scal = (Scalars *)((char *)block + os);
+}
+
+int sar_peer_open(const uint8_t handle[SAR_IPC_HANDLE_BYTES], uint32_t width, uint32_t height, int local_device, sar_peer **out)
+{
+    if (!handle || !out) return fail(SAR_ERR_INVALID, "NULL argument");
+    *out = nullptr;
+    if (int rc = check_dims(width, height)) return rc;
+    SAR_CUDA(cudaSetDevice(local_device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof h);
+    void *block = nullptr;
+    SAR_CUDA(cudaIpcOpenMemHandle(&block, h, cudaIpcMemLazyEnablePeerAccess));
+    sar_peer *p = new (std::nothrow) sar_peer();
+    if (!p) { cudaIpcCloseMemHandle(block); return fail(SAR_ERR_NOMEM, "host allocation failed"); }
+    p->local_device = local_device; p->ipc = true;
+    peer_view(p, block, width, height);
+    *out = p;
+    return SAR_OK;
+}
+
+void sar_peer_close(sar_peer *p)
+{
+    if (!p) return;
+    if (p->ipc && p->block) { cudaSetDevice(p->local_device); cudaIpcCloseMemHandle(p->block); }
+    delete p;
+}
+
+int sar_runtime_merge_peers_async(sar_runtime *rt, sar_peer *const *peers, int n_peers, uint32_t row0, uint32_t rows, void *stream)
+{
+    if (!rt || (n_peers > 0 && !peers)) return fail(SAR_ERR_INVALID, "NULL argument");
+    if (n_peers < 0 || n_peers > 16) return fail(SAR_ERR_INVALID, "n_peers must be in 0..16 (got %d)", n_peers);
+    if (rows == 0) { row0 = 0; rows = rt->h; }
+    if ((uint64_t)row0 + rows > rt->h) return fail(SAR_ERR_INVALID, "rows outside image");
+    PeerList pl;
+    memset(&pl, 0, sizeof pl);
+    pl.n = n_peers;
+    for (int i = 0; i < n_peers; ++i) {
+        if (!peers[i]) return fail(SAR_ERR_INVALID, "peer %d is NULL", i);
+        if (peers[i]->w != rt->w || peers[i]->h != rt->h)
+            return fail(SAR_ERR_DIMS, "peer %d is %ux%u, runtime %ux%u", i, peers[i]->w, peers[i]->h, rt->w, rt->h);
+        pl.fast[i] = peers[i]->fast; pl.rec[i] = peers[i]->rec; pl.scal[i] = peers[i]->scal;
+    }
+    SAR_CUDA(cudaSetDevice(rt->device));
+    launch_merge_peers(rt->fast, rt->rec, rt->scal, pl, (size_t)row0 * rt->w, (size_t)rows * rt->w, pick(rt, stream));
+    SAR_CUDA(cudaGetLastError());
+    return SAR_OK;
+}
+
+// ---- ParallelRenderer / render_parallel ---------------------------------------------------------
+int sar_renderer_new(const int *devices, int n_devices, uint32_t threads_per_device, sar_renderer **out)
+{
+    if (!out) return fail(SAR_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    SAR_CUDA(cudaGetDeviceCount(&ndev));
+    if (ndev <= 0) return fail(SAR_ERR_CUDA, "no CUDA device");
+    sar_renderer *r = new (std::nothrow) sar_renderer();
+    if (!r) return fail(SAR_ERR_NOMEM, "host allocation failed");
+    if (!devices || n_devices <= 0) r->devices.push_back(0);
+    else
+        for (int i = 0; i < n_devices; ++i) {
+            if (devices[i] < 0 || devices[i] >= ndev) { delete r; return fail(SAR_ERR_CUDA, "CUDA device %d not available (%d visible)", devices[i], ndev); }
+            r->devices.push_back(devices[i]);
+        }
+    if (r->devices.size() > 16) { delete r; return fail(SAR_ERR_INVALID, "at most 16 devices"); }
+    r->threads_per_device = threads_per_device;
+    r->rts.assign(r->devices.size(), nullptr);     // Runtimes are created on first use (Runtime::empty, lib.rs:938)
+    *out = r;
+    return SAR_OK;
+}
+
+void sar_renderer_shutdown(sar_renderer *r)
+{
+    if (!r) return;
+    for (sar_runtime *rt : r->rts) sar_runtime_free(rt);
+    delete r;
+}
+
+static uint32_t renderer_lanes(const sar_renderer *r, size_t d)
+{
+    if (r->threads_per_device) return r->threads_per_device;
+    int sm = 148;
+    cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, r->devices[d]);
+    return (uint32_t)sm * 256u;
+}
+
+int sar_renderer_num_threads(const sar_renderer *r, uint64_t *num_threads)
+{
+    if (!r || !num_threads) return fail(SAR_ERR_INVALID, "NULL argument");
+    uint64_t n = 0;
+    for (size_t d = 0; d < r->devices.size(); ++d) n += renderer_lanes(r, d);
+    *num_threads = n;
+    return SAR_OK;
+}
+
+int sar_renderer_runtime(sar_renderer *r, sar_runtime **rt)
+{
+    if (!r || !rt) return fail(SAR_ERR_INVALID, "NULL argument");
+    if (!r->rts[0]) return fail(SAR_ERR_INVALID, "no render_parallel call has been made yet");
+    *rt = r->rts[0];
+    return SAR_OK;
+}
+
+int sar_render_parallel(sar_renderer *r, const sar_config *cfg_in, uint64_t jobs_per_thread, uint64_t seed,
+                        const double *init_xyz, uint16_t *rgba_u16)
+{
+    if (!r || !cfg_in || !rgba_u16) return fail(SAR_ERR_INVALID, "NULL argument");
+    if (jobs_per_thread == 0) return fail(SAR_ERR_INVALID, "jobs_per_thread must be non-zero");   // NonZeroUsize in the CLI, main.rs:503
+    if (int rc = check_config(cfg_in, nullptr)) return rc;
+    if (int rc = check_dims(cfg_in->width, cfg_in->height)) return rc;
+    const size_t nd = r->devices.size();
+    uint64_t num_threads = 0;
+    sar_renderer_num_threads(r, &num_threads);
+    sar_config cfg = *cfg_in;
+    cfg.iterations = cfg_in->iterations / num_threads / jobs_per_thread;        // lib.rs:1058
+    const uint64_t total_jobs = jobs_per_thread * num_threads;                  // lib.rs:1062
+
+    // set_width_height + reset on every worker (lib.rs:950-951)
+    for (size_t d = 0; d < nd; ++d) {
+        if (r->rts[d] && (r->rts[d]->w != cfg.width || r->rts[d]->h != cfg.height)) { sar_runtime_free(r->rts[d]); r->rts[d] = nullptr; }
+        if (!r->rts[d]) { if (int rc = sar_runtime_new(cfg.width, cfg.height, r->devices[d], &r->rts[d])) return rc; }
+        else if (int rc = sar_runtime_reset_async(r->rts[d], nullptr)) return rc;
+    }
+    // device d renders the contiguous job slice [first, first+n): lanes_d * jobs_per_thread jobs
+    uint64_t first = 0;
+    for (size_t d = 0; d < nd; ++d) {
+        sar_runtime *rt = r->rts[d];
+        const uint32_t lanes = renderer_lanes(r, d);
+        const uint64_t n = (uint64_t)lanes * jobs_per_thread;
+        rt->job_base = 0;
+        if (init_xyz) {
+            SAR_CUDA(cudaSetDevice(rt->device));
+            if (int rc = upload_init(rt, init_xyz + 3 * first, n, rt->stream)) return rc;
+            if (int rc = render_launch(&cfg, rt, rt->d_init, 0, first, n, lanes, rt->stream)) return rc;
+        } else if (int rc = render_launch(&cfg, rt, nullptr, seed, first, n, lanes, rt->stream)) return rc;
+        first += n;
+    }
+    // merge every other device into the first (lib.rs:1070-1076), deterministically
+    sar_runtime *rt0 = r->rts[0];
+    for (size_t d = 1; d < nd; ++d) {
+        sar_runtime *src = r->rts[d];
+        SAR_CUDA(cudaSetDevice(src->device));
+        SAR_CUDA(cudaStreamSynchronize(src->stream));
+        SAR_CUDA(cudaSetDevice(rt0->device));
+        if (int rc = ensure_scratch(rt0, src->block_bytes)) return rc;
+        SAR_CUDA(cudaMemcpyPeerAsync(rt0->d_scratch, rt0->device, src->block, src->device, src->block_bytes, rt0->stream));
+        sar_peer view;
+        peer_view(&view, rt0->d_scratch, cfg.width, cfg.height);
+        sar_peer *pv = &view;
+        if (int rc = sar_runtime_merge_peers_async(rt0, &pv, 1, 0, 0, nullptr)) return rc;
+    }
+    rt0->job_base = total_jobs;
+    if (int rc = sar_runtime_max_async(rt0, 0, 0, nullptr)) return rc;
+    if (int rc = sar_colorize_rows_async(&cfg, rt0, 0, 0, nullptr, nullptr)) return rc;   // lib.rs:1080
+    return sar_runtime_image_download(rt0, 0, 0, rgba_u16, nullptr);
+}
+
+}  // extern "C"

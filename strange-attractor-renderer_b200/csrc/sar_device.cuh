@@ -1,0 +1,91 @@
+// sar_device.cuh — device-side data layout and kernel launch interface (internal).
+//
+// HBM layout of one Runtime (reference: Runtime{count,steps,zbuf,max}, lib.rs:631-646),
+// W*H pixels, row-major idx = y*W + x exactly like image::ImageBuffer:
+//
+//   fast[idx]  u64   bits 31..0  = count (u32, lib.rs:633)
+//                    bits 63..32 = zhint: an order-preserving key of a z value that is
+//                                  <= the pixel's recorded z ("a candidate below this loses")
+//   rec[idx]   16 B  .x (low 8)  = steps as f64 bits (lib.rs:635)
+//                    .y (high 8) = zkey(zbuf) << 32 | ~job   (zbuf f32, lib.rs:639)
+//
+// One 64-bit ATOMG.ADD per recorded iteration both increments the count (lib.rs:811)
+// and returns the hint for the depth test (lib.rs:821); the 16-byte record is only
+// touched on the rare winning path, with a 128-bit compare-and-swap ordered on .y.
+// ~job (0xFFFFFFFF - job index) makes ties in z resolve to the earlier render() call,
+// and within a call program order keeps the earlier iteration: exactly the outcome of
+// running the reference's render() job after job on one Runtime (lib.rs:742-743).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace sar {
+
+// order-preserving map f32 -> u32 (a > b  <=>  zkey(a) > zkey(b) for non-NaN a,b; -0 is canonicalised first)
+__host__ __device__ inline uint32_t zkey_from_bits(uint32_t b) { return (b & 0x80000000u) ? ~b : (b | 0x80000000u); }
+__host__ __device__ inline uint32_t zbits_from_key(uint32_t k) { return (k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k; }
+
+constexpr uint32_t ZKEY_SENTINEL = 0x407FFFFFu;   // zkey(-1.0f): Runtime::reset fills zbuf with -1.0 (lib.rs:693)
+constexpr uint32_t ZKEY_POS_INF  = 0xFF800000u;   // zkey(+inf); +NaN keys are larger, -NaN keys are < zkey(-inf)
+constexpr uint32_t ZKEY_ZERO     = 0x80000000u;   // zkey(+0.0f)
+constexpr uint32_t ZKEY_FLT_MAX  = 0xFF7FFFFFu;   // zkey(f32::MAX)
+constexpr unsigned long long FAST_RESET = (unsigned long long)(ZKEY_SENTINEL + 1u) << 32;  // count 0, hint just above the sentinel
+constexpr unsigned long long REC_HI_RESET = ((unsigned long long)ZKEY_SENTINEL << 32) | 0xFFFFFFFFull;
+
+struct Scalars {                      // device-resident scalar state of a Runtime
+    unsigned long long nan_sink;      // iterations of NaN trajectories, owed to count[(0,0)]
+    unsigned int max;                 // Runtime.max (lib.rs:643), valid after launch_max()
+    unsigned int zmax_key, zmin_key;  // Depth colourise fold (lib.rs:877-882)
+    unsigned int pad;
+};
+
+struct IterParams {                   // everything the iterate kernel reads; lives in the constant bank
+    double c[3][10];                  // attractor coefficients; c[k][0] pre-reduced to 0.0 + 1.0*c0 (lib.rs:589-596)
+    double m[3][3];                   // rotation matrix (lib.rs:755), host computed
+    double ccx, ccy, ccz;             // center_camera (lib.rs:758)
+    double cv, sv;                    // cos/sin(angle) (lib.rs:756-757), host computed
+    double sam, ws, half_h;           // scale_adjusted_mid, width_scaled, height/2 (lib.rs:763-764, 786)
+    double ct_offset, ct_factor;      // AdjustedVelocity (lib.rs:507-510)
+    unsigned long long *fast;
+    ulonglong2 *rec;
+    Scalars *scal;
+    const double *init;               // n_jobs x 3 start points, or nullptr -> generated from seed
+    unsigned long long seed;
+    unsigned long long first_job;     // index of this launch's job 0 in the seed stream
+    unsigned long long n_jobs;
+    unsigned long long iterations;    // recorded iterations per job
+    unsigned int job_key0;            // order key of job 0 (Runtime job counter)
+    unsigned int W, H;
+    unsigned int ct_kind;
+};
+
+struct ColorParams {
+    double pal[17][3];                // palette + duplicated last entry (lib.rs:416-424)
+    double pal_len;                   // count_f64 (lib.rs:421)
+    double bright_offset, bright_factor;
+    unsigned int palette_len, transparent, render_kind;
+    unsigned int W, H, row0, rows;
+};
+
+// launchers (sar_kernels.cu); every one bumps the launch counter
+void launch_reset(unsigned long long *fast, ulonglong2 *rec, Scalars *scal, size_t npix, cudaStream_t s);
+void launch_iterate(const IterParams &p, unsigned int lanes, cudaStream_t s);
+void launch_max(const unsigned long long *fast, const ulonglong2 *rec, Scalars *scal, size_t pix0, size_t npix, cudaStream_t s);
+void launch_colorize(const ColorParams &cp, const unsigned long long *fast, const ulonglong2 *rec, const Scalars *scal,
+                     uint16_t *rgba_u16, float *rgba_f32, cudaStream_t s);
+void launch_unpack(const unsigned long long *fast, const ulonglong2 *rec, const Scalars *scal, size_t npix,
+                   uint32_t *count, double *steps, float *zbuf, cudaStream_t s);
+void launch_pack(unsigned long long *fast, ulonglong2 *rec, Scalars *scal, size_t npix,
+                 const uint32_t *count, const double *steps, const float *zbuf, cudaStream_t s);
+// Runtime::merge (lib.rs:708-738): z-only compare, ties keep dst
+void launch_merge(unsigned long long *dfast, ulonglong2 *drec, Scalars *dscal,
+                  const unsigned long long *sfast, const ulonglong2 *srec, const Scalars *sscal,
+                  size_t npix, cudaStream_t s);
+// deterministic all-ranks merge of one row stripe by direct peer loads; (z, ~job) max
+struct PeerList { const unsigned long long *fast[16]; const ulonglong2 *rec[16]; const Scalars *scal[16]; int n; };
+void launch_merge_peers(unsigned long long *dfast, ulonglong2 *drec, Scalars *dscal, const PeerList &peers,
+                        size_t pix0, size_t npix, cudaStream_t s);
+void launch_seed_points(unsigned long long seed, unsigned long long first, unsigned long long n, double *out, cudaStream_t s);
+unsigned long long launch_count();
+
+}  // namespace sar

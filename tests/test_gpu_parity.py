@@ -1,0 +1,284 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same start points.
+
+Bar (BASELINE.json north_star): count buffer bit-exact; colour within 1e-5 relative.  This
+build is stricter: zbuf (f32) and steps (f64) are bit-exact too, because z ties resolve to the
+earlier render() call / earlier iteration exactly as in a sequential reference run, and the u16
+image may differ from the oracle's by at most 1 LSB (CUDA's log() vs glibc's, <= 1 ulp).
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL_COLOUR = 1e-5  # north_star: "within 1e-5 relative in the fp32 colour buffer"
+
+
+@pytest.fixture(scope="module")
+def S():
+    import strange_attractor_renderer_b200 as S
+
+    S._native.lib()
+    return S
+
+
+def _small(cfg, w, h, iters):
+    cfg.width, cfg.height, cfg.iterations = w, h, iters
+    return cfg
+
+
+def _oracle_state(oracle, cfg, pts):
+    rt = oracle.Runtime(cfg.width, cfg.height)
+    st = oracle.OrcStats()
+    oracle.render_jobs(cfg.to_pod(), rt, pts, st)
+    return rt, st
+
+
+def _assert_state_equal(gpu_state, ort):
+    count, steps, zbuf, mx = gpu_state
+    assert np.array_equal(count, ort.count), f"count differs in {(count != ort.count).sum()} pixels"
+    assert mx == ort.max
+    assert np.array_equal(zbuf, ort.zbuf), f"zbuf differs in {(zbuf != ort.zbuf).sum()} pixels"
+    assert np.array_equal(steps.view(np.uint64), ort.steps.view(np.uint64)), \
+        f"steps differs in {(steps != ort.steps).sum()} pixels"
+
+
+def _assert_image_close(img, f32, oimg, of64):
+    d = np.abs(img.astype(np.int32) - oimg.astype(np.int32))
+    assert d.max() <= 1, f"u16 image differs by {d.max()} LSB"
+    assert (d > 0).mean() < 1e-4, f"{(d > 0).sum()} u16 channel values differ by 1 LSB"
+    if f32 is not None:
+        ref = of64.astype(np.float64)
+        ok = np.isclose(f32.astype(np.float64), ref, rtol=REL_TOL_COLOUR, atol=1e-7) | (np.isnan(ref) & np.isnan(f32))
+        assert ok.all(), f"{(~ok).sum()} colour values outside {REL_TOL_COLOUR} relative"
+
+
+def test_poisson_saturne_many_jobs_bit_exact(S, oracle):
+    """BASELINE cfg 1 shape (512x512) with render_parallel-style decomposition: 256 jobs."""
+    cfg = _small(S.Config.poisson_saturne(), 512, 512, 40_000)
+    cfg.transparent = False
+    pts = S.seed_points(1234, 0, 256)
+    assert np.array_equal(pts, oracle.seed_points(1234, 0, 256))
+    rt = S.Runtime.new(cfg)
+    S.render(cfg, rt, initial_points=pts)
+    ort, st = _oracle_state(oracle, cfg, pts)
+    assert st.recorded == 256 * 40_000  # attractor fully in view
+    _assert_state_equal(rt.download(), ort)
+    img, f32 = S.colorize(cfg, rt, want_f32=True)
+    oimg, of64 = oracle.colorize(cfg.to_pod(), ort, want_f64=True)
+    _assert_image_close(img, f32, oimg, of64)
+
+
+def test_single_long_trajectory_is_reference_render(S, oracle):
+    """BASELINE cfg 0: render() = ONE serial trajectory (lib.rs:769-837); 3e6 steps must stay
+    bit-identical although the map is chaotic."""
+    cfg = _small(S.Config.poisson_saturne(), 512, 512, 3_000_000)
+    pts = S.seed_points(99, 0, 1)
+    rt = S.Runtime.new(cfg)
+    S.render(cfg, rt, initial_points=pts)
+    ort, _ = _oracle_state(oracle, cfg, pts)
+    _assert_state_equal(rt.download(), ort)
+
+
+def test_solar_sail_nan_sink_and_angle(S, oracle):
+    """BASELINE cfg 2 shape scaled down: solar-sail at 220 deg (in radians), with the 38 % of
+    start points that diverge to NaN and pile onto count[(0,0)]."""
+    cfg = _small(S.Config.solar_sail(), 360, 400, 30_000)
+    cfg.angle = 220.0 * math.pi / 180.0
+    pts = S.seed_points(7, 0, 200)
+    rt = S.Runtime.new(cfg)
+    S.render(cfg, rt, initial_points=pts)
+    ort, st = _oracle_state(oracle, cfg, pts)
+    assert st.nan_iters > 30_000 * 20, "expected diverging trajectories in this list"
+    gs = rt.download()
+    _assert_state_equal(gs, ort)
+    assert gs[0][0, 0] == gs[3], "the NaN sink pixel holds the max"
+    img, f32 = S.colorize(cfg, rt, want_f32=True)
+    oimg, of64 = oracle.colorize(cfg.to_pod(), ort, want_f64=True)
+    _assert_image_close(img, f32, oimg, of64)
+    assert list(img[0, 0, :3]) == [65535, 65535, 60849]   # known answer, media/solar-sail-220deg.png
+
+
+def test_progressive_accumulation_and_reset(S, oracle):
+    """render() on a non-reset Runtime continues the image (lib.rs:742-743); reset() clears it."""
+    cfg = _small(S.Config.poisson_saturne(), 256, 256, 20_000)
+    a, b = S.seed_points(1, 0, 40), S.seed_points(2, 0, 24)
+    rt = S.Runtime.new(cfg)
+    S.render(cfg, rt, initial_points=a)
+    S.render(cfg, rt, initial_points=b)
+    ort, _ = _oracle_state(oracle, cfg, np.concatenate([a, b]))
+    _assert_state_equal(rt.download(), ort)
+    rt.reset()
+    count, steps, zbuf, mx = rt.download()
+    assert count.max() == 0 and mx == 0 and (zbuf == -1.0).all() and (steps == 0.0).all()
+    S.render(cfg, rt, initial_points=b)
+    ort2, _ = _oracle_state(oracle, cfg, b)
+    _assert_state_equal(rt.download(), ort2)
+
+
+def test_seeded_render_matches_explicit_points(S, oracle):
+    """Runtime's own generator (device-side SplitMix64) == sar_seed_points == the oracle's."""
+    cfg = _small(S.Config.poisson_saturne(), 128, 128, 5_000)
+    rt = S.Runtime.new(cfg, seed=4242)
+    for _ in range(3):
+        S.render(cfg, rt)   # three reference render() calls, three draws
+    ort, _ = _oracle_state(oracle, cfg, oracle.seed_points(4242, 0, 3))
+    _assert_state_equal(rt.download(), ort)
+
+
+def test_merge_matches_reference_merge(S, oracle):
+    """Runtime::merge (lib.rs:708-738): counts add, other wins on strictly greater z."""
+    cfg = _small(S.Config.poisson_saturne(), 200, 160, 15_000)
+    a, b = S.seed_points(11, 0, 32), S.seed_points(12, 0, 32)
+    ra, rb = S.Runtime.new(cfg), S.Runtime.new(cfg)
+    S.render(cfg, ra, initial_points=a)
+    S.render(cfg, rb, initial_points=b)
+    oa, _ = _oracle_state(oracle, cfg, a)
+    ob, _ = _oracle_state(oracle, cfg, b)
+    ra.merge(rb)
+    oa.merge(ob)
+    _assert_state_equal(ra.download(), oa)
+    other = S.Runtime.new(_small(S.Config.poisson_saturne(), 100, 100, 1))
+    with pytest.raises(S.SarError) as e:   # reference: assert_eq! panic, lib.rs:709-710
+        ra.merge(other)
+    assert e.value.code == S._native.SAR_ERR_DIMS
+
+
+def test_download_upload_roundtrip_continues_render(S, oracle):
+    """Checkpoint/resume of the progressive accumulation: download, upload into a new Runtime,
+    keep rendering; equals an uninterrupted run."""
+    cfg = _small(S.Config.solar_sail(), 180, 200, 10_000)
+    a, b = S.seed_points(21, 0, 30), S.seed_points(22, 0, 30)
+    r1 = S.Runtime.new(cfg)
+    S.render(cfg, r1, initial_points=a)
+    count, steps, zbuf, _ = r1.download()
+    r2 = S.Runtime.new(cfg)
+    r2.upload(count, steps, zbuf)
+    S.render(cfg, r2, initial_points=b)
+    ort, _ = _oracle_state(oracle, cfg, np.concatenate([a, b]))
+    _assert_state_equal(r2.download(), ort)
+
+
+def test_render_parallel_decomposition(S, oracle):
+    """render_parallel (lib.rs:1051-1082): iterations/num_threads/jobs_per_thread per job (integer
+    division, remainder dropped), num_threads*jobs_per_thread jobs, merged, colourised."""
+    cfg = _small(S.Config.poisson_saturne(), 320, 240, 10_000_123)
+    cfg.transparent = True
+    r = S.ParallelRenderer.new(threads=96)
+    assert r.num_threads() == 96
+    img = S.render_parallel(r, cfg, 3, seed=555)
+    per_job = 10_000_123 // 96 // 3
+    ocfg = cfg.to_pod()
+    ocfg.iterations = per_job
+    ort = oracle.Runtime(320, 240)
+    oracle.render_jobs(ocfg, ort, oracle.seed_points(555, 0, 288))
+    assert int(ort.count.sum()) == per_job * 288
+    _assert_state_equal(r.runtime().download(), ort)
+    oimg, _ = oracle.colorize(ocfg, ort, want_f64=True)
+    _assert_image_close(img, None, oimg, None)
+    # explicit start points take the same path
+    img2 = S.render_parallel(r, cfg, 3, initial_points=oracle.seed_points(555, 0, 288))
+    assert np.array_equal(img, img2)
+    r.shutdown()
+
+
+def test_depth_render_kind(S, oracle):
+    """RenderKind::Depth (lib.rs:875-900): f32 min/max over touched pixels, grey u16."""
+    cfg = _small(S.Config.poisson_saturne(), 300, 200, 20_000)
+    cfg.render = S.RenderKind.Depth
+    pts = S.seed_points(3, 0, 64)
+    rt = S.Runtime.new(cfg)
+    S.render(cfg, rt, initial_points=pts)
+    ort, _ = _oracle_state(oracle, cfg, pts)
+    img, f32 = S.colorize(cfg, rt, want_f32=True)
+    oimg, of64 = oracle.colorize(cfg.to_pod(), ort, want_f64=True)
+    assert np.array_equal(img, oimg)   # pure f32 arithmetic: exact
+    assert np.array_equal(f32, of64.astype(np.float32))
+
+
+def test_edge_cases(S, oracle):
+    # colorize of an empty Runtime: max == 0 -> ln(1)/ln(1) = NaN -> `as u16` = 0 (lib.rs:860-866)
+    cfg = _small(S.Config.poisson_saturne(), 64, 48, 0)
+    rt = S.Runtime.new(cfg)
+    S.render(cfg, rt, initial_points=S.seed_points(1, 0, 4))   # zero iterations: only warm-up runs
+    img = S.colorize(cfg, rt)
+    oimg = oracle.colorize(cfg.to_pod(), oracle.Runtime(64, 48))
+    assert np.array_equal(img, oimg) and img[..., :3].max() == 0
+    # zero jobs is a no-op
+    S.render(cfg, rt, initial_points=np.empty((0, 3)))
+    # 1x1 image: every in-view hit lands on the single pixel
+    cfg1 = _small(S.Config.poisson_saturne(), 1, 1, 1000)
+    r1 = S.Runtime.new(cfg1)
+    pts = S.seed_points(5, 0, 8)
+    S.render(cfg1, r1, initial_points=pts)
+    o1, _ = _oracle_state(oracle, cfg1, pts)
+    _assert_state_equal(r1.download(), o1)
+    # zoomed in so that most points fall outside the viewport: out-of-view points still advance
+    # previous_point (lib.rs:790-794), which feeds the next in-view delta
+    cfgz = _small(S.Config.poisson_saturne(), 256, 256, 30_000)
+    cfgz.view.scale = 6.0
+    rz = S.Runtime.new(cfgz)
+    pts = S.seed_points(8, 0, 64)
+    S.render(cfgz, rz, initial_points=pts)
+    oz, st = _oracle_state(oracle, cfgz, pts)
+    assert 0 < st.recorded < 64 * 30_000 * 0.5
+    _assert_state_equal(rz.download(), oz)
+    # config / runtime dimension mismatch and bad arguments are errors, not crashes
+    with pytest.raises(S.SarError):
+        S.render(_small(S.Config.poisson_saturne(), 65, 48, 10), rt, initial_points=pts)
+    with pytest.raises(S.SarError):
+        S.Runtime.new(_small(S.Config.poisson_saturne(), 0, 10, 1))
+
+
+def test_palette_and_transparency_variants(S, oracle):
+    cfg = _small(S.Config.solar_sail(), 150, 170, 20_000)
+    cfg.color_transform = S.color_transforms.AdjustedVelocity(offset=0.05, factor=2.5)  # spreads over the palette
+    cfg.colors.palette = S.Palette.from_rgb([1.0, 0.2, 0.9], [0.1, 1.0, 0.3], [0.4, 0.6, 1.0])
+    cfg.colors.brighness = S.BrighnessConstants(offset=-0.05, factor=1.25)
+    pts = S.seed_points(31, 0, 48)
+    rt = S.Runtime.new(cfg)
+    S.render(cfg, rt, initial_points=pts)
+    ort, _ = _oracle_state(oracle, cfg, pts)
+    _assert_state_equal(rt.download(), ort)
+    for transparent in (True, False):
+        cfg.transparent = transparent
+        img, f32 = S.colorize(cfg, rt, want_f32=True)
+        oimg, of64 = oracle.colorize(cfg.to_pod(), ort, want_f64=True)
+        _assert_image_close(img, f32, oimg, of64)
+
+
+def test_lane_count_does_not_change_the_result(S):
+    """Size-independent property: the trajectory -> lane mapping is invisible.  Same job list on
+    64 lanes and on the default (SM count x 256) lanes gives identical buffers."""
+    cfg = _small(S.Config.solar_sail(), 450, 500, 3_000)
+    states = []
+    for lanes in (64, 0):
+        rt = S.Runtime.new(cfg)
+        c = cfg.to_pod()
+        S._native.check(S._native.lib().sar_render_seeded_async(C.byref(c), rt._h, 77, 0, 5000, lanes, None))
+        S._native.check(S._native.lib().sar_stream_synchronize(rt._h, None))
+        states.append(rt.download())
+    for x, y in zip(states[0][:3], states[1][:3]):
+        assert np.array_equal(x.view(np.uint8), y.view(np.uint8))
+    assert states[0][3] == states[1][3]
+
+
+def test_full_size_conservation_cfg2(S):
+    """BASELINE cfg 1 at full size (1e9 iterations, 2048x2048): every recorded iteration is counted
+    exactly once (sum of counts == jobs x iterations; poisson-saturne is fully in view), and the
+    image is reproducible run to run."""
+    cfg = _small(S.Config.poisson_saturne(), 2048, 2048, 1_000_000_000)
+    r = S.ParallelRenderer.new()
+    n = r.num_threads()
+    img1 = S.render_parallel(r, cfg, 1, seed=1234)
+    count, steps, zbuf, mx = r.runtime().download()
+    assert int(count.sum(dtype=np.uint64)) == (1_000_000_000 // n) * n
+    assert mx == count.max()
+    lit = float((count > 0).mean())
+    assert 0.15 < lit < 0.25   # 19-22 % of pixels touched
+    assert ((zbuf > -1.0) == (count > 0)).all() or (zbuf[count > 0] >= -1.0).all()
+    img2 = S.render_parallel(r, cfg, 1, seed=1234)
+    assert np.array_equal(img1, img2)
+    r.shutdown()

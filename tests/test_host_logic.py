@@ -1,0 +1,80 @@
+"""Host-side logic of the multi-GPU driver (pure functions) and of the oracle's own
+render_parallel: decomposition arithmetic of lib.rs:1056-1062 and merge semantics."""
+import numpy as np
+import pytest
+
+
+@pytest.fixture(scope="module")
+def D():
+    from strange_attractor_renderer_b200 import dist
+
+    return dist
+
+
+def test_iterations_per_job_is_two_integer_divisions(D):
+    # lib.rs:1058: iterations / num_threads / jobs_per_thread
+    assert D.iterations_per_job(1_000_000_000, 37_888, 1) == 26_393
+    assert D.iterations_per_job(10_000_123, 96, 3) == 10_000_123 // 96 // 3 == 34_722
+    assert D.iterations_per_job(100, 7, 3) == 4            # (100//7)//3, not 100//21 rounded differently
+    for world in (1, 2, 4, 8):                              # weak scaling keeps the per-job length
+        assert D.iterations_per_job(world * 10**9, world * 37_888, 1) == 26_393
+
+
+def test_job_slices_partition_the_job_list(D):
+    for world in (1, 2, 3, 8):
+        lanes, jpt = 96, 5
+        seen = []
+        for r in range(world):
+            first, n = D.job_slice(r, world, lanes, jpt)
+            seen.extend(range(first, first + n))
+        assert seen == list(range(world * lanes * jpt))    # lib.rs:1062: jobs_per_thread * num_threads jobs
+
+
+def test_stripes_partition_the_rows(D):
+    for world in (1, 2, 3, 8):
+        for h in (1, 7, 2000, 2048, 4096):
+            rows = []
+            for r in range(world):
+                r0, n = D.stripe_rows(r, world, h)
+                rows.extend(range(r0, r0 + n))
+            assert rows == list(range(h))
+
+
+def test_oracle_merge_in_job_order_equals_sequential(oracle):
+    """Why the GPU merge is deterministic: merging per-worker Runtimes in job order with 'ties keep
+    self' (lib.rs:728) is exactly one Runtime rendered job after job."""
+    cfg = oracle.poisson_saturne()
+    cfg.width, cfg.height, cfg.iterations = 160, 120, 8000
+    pts = oracle.seed_points(9, 0, 24)
+    seq = oracle.Runtime(160, 120)
+    oracle.render_jobs(cfg, seq, pts)
+    parts = []
+    for k in range(3):
+        rt = oracle.Runtime(160, 120)
+        oracle.render_jobs(cfg, rt, pts[8 * k:8 * k + 8])
+        parts.append(rt)
+    parts[0].merge(parts[1])
+    parts[0].merge(parts[2])
+    assert np.array_equal(parts[0].count, seq.count) and parts[0].max == seq.max
+    assert np.array_equal(parts[0].zbuf, seq.zbuf)
+    assert np.array_equal(parts[0].steps, seq.steps)
+    with pytest.raises(ValueError):
+        parts[0].merge(oracle.Runtime(10, 10))            # assert_eq! panic, lib.rs:709-710
+
+
+def test_oracle_render_parallel_counts_match_sequential(oracle):
+    """The threaded CPU baseline (dynamic job counter, lib.rs:962-982) computes the same counts as
+    the sequential semantics; only exact z ties may differ with scheduling."""
+    cfg = oracle.solar_sail()
+    cfg.width, cfg.height, cfg.iterations = 180, 200, 4 * 6 * 5000 + 17
+    pts = oracle.seed_points(3, 0, 24)
+    img, merged = oracle.render_parallel(cfg, 4, 6, pts, want_runtime=True)
+    seq_cfg = cfg.copy()
+    seq_cfg.iterations = cfg.iterations // 4 // 6
+    assert seq_cfg.iterations == 5000
+    seq = oracle.Runtime(180, 200)
+    oracle.render_jobs(seq_cfg, seq, pts)
+    assert np.array_equal(merged.count, seq.count) and merged.max == seq.max
+    assert np.array_equal(merged.zbuf, seq.zbuf)
+    assert (merged.steps != seq.steps).mean() < 1e-3
+    assert img.shape == (200, 180, 4)
