@@ -102,6 +102,15 @@ typedef struct sar_renderer sar_renderer;  /* ParallelRenderer, lib.rs:908-915 *
 uint32_t    sar_abi_version(void);
 const char *sar_last_error(void);            /* thread-local, never NULL */
 int         sar_device_count(int *count);    /* SAR_ERR_CUDA when no driver/device */
+/* Default number of concurrent trajectory lanes on `device` (SM count × 768):
+ * the GPU's answer to available_parallelism(), lib.rs:920-922. */
+int         sar_default_threads(int device, uint32_t *threads);
+/* Tuning knobs that never change results.  "defer": depth (0..4) of the iterate
+ * kernel's deferred depth-test queue (default 0, env SAR_DEFER).
+ * "diagnostic_mode": 0 = product path (default); 1..3 run the iterate kernel
+ * with parts of the scatter removed, for roofline experiments only — their
+ * results are incomplete by design (tools/sweep_iterate.py). */
+int         sar_set_option(const char *name, int64_t value);
 
 /* ---- Config presets --------------------------------------------------- */
 /* Config::new defaults, lib.rs:289-307 + Colors::default lib.rs:480-491, around
@@ -162,7 +171,7 @@ int sar_colorize(const sar_config *cfg, const sar_runtime *rt,
 /* ParallelRenderer::new, lib.rs:919.  `devices`/`n_devices`: CUDA ordinals of
  * this process's GPUs (NULL/0 = device 0).  `threads_per_device` plays the
  * role of available_parallelism() (lib.rs:920-922): the number of concurrent
- * trajectory lanes; 0 = default (SM count × 256). */
+ * trajectory lanes; 0 = default (sar_default_threads). */
 int  sar_renderer_new(const int *devices, int n_devices, uint32_t threads_per_device,
                       sar_renderer **out);
 /* ParallelRenderer::shutdown, lib.rs:1020. */
@@ -184,7 +193,7 @@ int  sar_renderer_runtime(sar_renderer *r, sar_runtime **rt);
  * Used by bench.py (kernel-only timing) and by the one-process-per-GPU
  * driver.  `stream` is a cudaStream_t passed as void*
  * (NULL = the runtime's own stream); *_async calls do not synchronise.
- * `threads` = concurrent trajectory lanes (0 = default, SM count × 256);
+ * `threads` = concurrent trajectory lanes (0 = default, sar_default_threads);
  * lane L runs jobs L, L+threads, ... one after the other.
  * Order key of job k of a call = job_base + first_job + k (see
  * sar_runtime_set_job_base); earlier keys keep exact z ties. */

@@ -58,6 +58,8 @@ SYMBOLS = {
     "sar_abi_version": (C.c_uint32, []),
     "sar_last_error": (C.c_char_p, []),
     "sar_device_count": (C.c_int, [_P(C.c_int)]),
+    "sar_set_option": (C.c_int, [C.c_char_p, C.c_int64]),
+    "sar_default_threads": (C.c_int, [C.c_int, _u32p]),
     "sar_config_defaults": (C.c_int, [_cfgp]),
     "sar_config_poisson_saturne": (C.c_int, [_cfgp]),
     "sar_config_solar_sail": (C.c_int, [_cfgp]),

@@ -164,7 +164,10 @@ static void make_color_params(const sar_config *cfg, ColorParams &c, uint32_t ro
     c.W = cfg->width; c.H = cfg->height; c.row0 = row0; c.rows = rows;
 }
 
-static uint32_t default_lanes(const sar_runtime *rt) { return (uint32_t)rt->sm_count * 256u; }
+// Concurrent trajectory lanes per SM: 6 warps per scheduler is where the L2 atomic-with-return
+// rate saturates (profiles/r1_sweep.md); more lanes only add 1000-step warm-ups (lib.rs:750).
+static const uint32_t LANES_PER_SM = 768u;
+static uint32_t default_lanes(const sar_runtime *rt) { return (uint32_t)rt->sm_count * LANES_PER_SM; }
 
 // ---------------------------------------------------------------------------------------------
 extern "C" {
@@ -172,6 +175,29 @@ extern "C" {
 uint32_t sar_abi_version(void) { return SAR_ABI_VERSION; }
 const char *sar_last_error(void) { return g_err.c_str(); }
 uint64_t sar_launch_count(void) { return launch_count(); }
+
+int sar_set_option(const char *name, int64_t value)
+{
+    if (!name) return fail(SAR_ERR_INVALID, "name is NULL");
+    if (strcmp(name, "defer") == 0) {
+        if (!set_defer((int)value)) return fail(SAR_ERR_INVALID, "defer must be in 0..4");
+        return SAR_OK;
+    }
+    if (strcmp(name, "diagnostic_mode") == 0) {
+        if (!set_mode((int)value)) return fail(SAR_ERR_INVALID, "diagnostic_mode must be in 0..6");
+        return SAR_OK;
+    }
+    return fail(SAR_ERR_INVALID, "unknown option '%s'", name);
+}
+
+int sar_default_threads(int device, uint32_t *threads)
+{
+    if (!threads) return fail(SAR_ERR_INVALID, "threads is NULL");
+    int sm = 0;
+    SAR_CUDA(cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device));
+    *threads = (uint32_t)sm * LANES_PER_SM;
+    return SAR_OK;
+}
 
 int sar_device_count(int *count)
 {
@@ -671,7 +697,7 @@ static uint32_t renderer_lanes(const sar_renderer *r, size_t d)
     if (r->threads_per_device) return r->threads_per_device;
     int sm = 148;
     cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, r->devices[d]);
-    return (uint32_t)sm * 256u;
+    return (uint32_t)sm * LANES_PER_SM;
 }
 
 int sar_renderer_num_threads(const sar_renderer *r, uint64_t *num_threads)

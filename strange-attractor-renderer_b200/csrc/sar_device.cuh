@@ -87,5 +87,7 @@ void launch_merge_peers(unsigned long long *dfast, ulonglong2 *drec, Scalars *ds
                         size_t pix0, size_t npix, cudaStream_t s);
 void launch_seed_points(unsigned long long seed, unsigned long long first, unsigned long long n, double *out, cudaStream_t s);
 unsigned long long launch_count();
+bool set_mode(int mode);     // diagnostics: 0 = product path; 1..3 = roofline experiments (incomplete results)
+bool set_defer(int depth);   // tuning: depth of the deferred depth-test queue (0..4)
 
 }  // namespace sar

@@ -8,6 +8,7 @@
 #include "sar_device.cuh"
 
 #include <atomic>
+#include <cstdlib>
 
 namespace sar {
 
@@ -87,21 +88,44 @@ __device__ __forceinline__ double magnitude(double x, double y, double z)
 //   value = color_transform.transform(delta, screen_space, view)   lib.rs:826-828
 //   steps[idx] = value; zbuf[idx] = z2 as f32                       lib.rs:830-832
 // made atomic and order-independent: the record is replaced iff (zkey, ~job) is strictly
-// greater than the stored one.
-__device__ __noinline__ void record_win(unsigned long long *fast, ulonglong2 *rec, unsigned int idx,
-                                        uint32_t key, uint32_t job_inv, unsigned int ct_kind,
-                                        double ct_offset, double ct_factor, double vccx, double vccy,
-                                        double dx, double dy, double dz, double sx, double sy, double sz)
+// greater than the stored one.  The candidate is re-derived from the point BEFORE the step
+// (px,py,pz): the same instructions on the same inputs give the same bits as the hot loop.
+__device__ __noinline__ void record_win(const IterParams *Pp, unsigned int idx, uint32_t key, uint32_t job_inv,
+                                        unsigned long long old, double px, double py, double pz)
 {
+    const IterParams &P = *Pp;
+    const unsigned long long hi = ((unsigned long long)key << 32) | job_inv;
+    ulonglong2 *r = P.rec + idx;
+    // Current record: known without a load if the pixel was untouched when our atomic hit it,
+    // otherwise loaded now (may be stale or torn — the CAS validates it) so that the round trip
+    // overlaps the arithmetic below.
+    ulonglong2 cur = make_ulonglong2(0ull, REC_HI_RESET);
+    if ((uint32_t)(old >> 32) != ZKEY_SENTINEL + 1u) {
+        cur.y = __ldcg(&r->y);
+        cur.x = __ldcg(&r->x);
+    }
+    // Best-effort raise of the hint so later candidates below this z skip this path: one
+    // compare-and-swap against the value our own atomic produced, result ignored.  If other hits
+    // landed in between it fails and the hint stays low, which only costs a later visit here.
+    {
+        const unsigned long long expect = old + 1ull;
+        const unsigned long long want = ((unsigned long long)key << 32) | (expect & 0xFFFFFFFFull);
+        if ((uint32_t)(expect >> 32) < key) (void)atomicCAS(P.fast + idx, expect, want);
+    }
+    double nx, ny, nz;
+    SAR_NEXT_POINT(P, px, py, pz, nx, ny, nz);
+    const double sx = __dadd_rn(__dadd_rn(__dmul_rn(P.m[0][0], nx), __dmul_rn(P.m[0][1], ny)), __dmul_rn(P.m[0][2], nz));
+    const double sy = __dadd_rn(__dadd_rn(__dmul_rn(P.m[1][0], nx), __dmul_rn(P.m[1][1], ny)), __dmul_rn(P.m[1][2], nz));
+    const double sz = __dadd_rn(__dadd_rn(__dmul_rn(P.m[2][0], nx), __dmul_rn(P.m[2][1], ny)), __dmul_rn(P.m[2][2], nz));
+    const double mag = magnitude(__dsub_rn(nx, px), __dsub_rn(ny, py), __dsub_rn(nz, pz));   // delta, lib.rs:822
     double value;
-    const double mag = magnitude(dx, dy, dz);
-    if (ct_kind == 1u) {
-        value = __dmul_rn(__dadd_rn(mag, ct_offset), ct_factor);             // AdjustedVelocity, lib.rs:514
+    if (P.ct_kind == 1u) {
+        value = __dmul_rn(__dadd_rn(mag, P.ct_offset), P.ct_factor);          // AdjustedVelocity, lib.rs:514
     } else {
         // color_transforms::poisson_saturne, lib.rs:520-558 (COS/SIN literals lib.rs:529-536)
         const double COS = 0.7009092642998508981833083453238941729068756103515625;
         const double SIN = 0.7132504491541815649924274111981503665447235107421875;
-        const double x2 = __dadd_rn(__dmul_rn(__dadd_rn(sx, vccx), COS), __dmul_rn(__dadd_rn(sz, vccy), SIN));
+        const double x2 = __dadd_rn(__dmul_rn(__dadd_rn(sx, P.ccx), COS), __dmul_rn(__dadd_rn(sz, P.ccy), SIN));
         const bool out = (x2 < -0.0839) ||
                          (__dadd_rn(__dmul_rn(10.55, x2), sy) < (0.46 - 1.0941)) ||
                          (__dadd_rn(__dmul_rn(1.0426, x2), sy) < (0.179 - 0.1576)) ||
@@ -110,35 +134,172 @@ __device__ __noinline__ void record_win(unsigned long long *fast, ulonglong2 *re
         const double color = __ddiv_rn(__dadd_rn(part, mag), 2.);            // lib.rs:556
         value = __ddiv_rn(__dsub_rn(color, 0.1), 0.9);                       // lib.rs:557
     }
-    const unsigned long long hi = ((unsigned long long)key << 32) | job_inv;
-    ulonglong2 *r = rec + idx;
-    ulonglong2 cur;
-    cur.y = __ldcg(&r->y);
-    cur.x = __ldcg(&r->x);            // may be torn against a concurrent writer; the CAS validates it
+    const ulonglong2 want = make_ulonglong2((unsigned long long)__double_as_longlong(value), hi);
     while (hi > cur.y) {
-        const ulonglong2 want = make_ulonglong2((unsigned long long)__double_as_longlong(value), hi);
-        const ulonglong2 old = cas128(r, cur, want);
-        if (old.x == cur.x && old.y == cur.y) break;
-        cur = old;
+        const ulonglong2 prev = cas128(r, cur, want);
+        if (prev.x == cur.x && prev.y == cur.y) break;
+        cur = prev;
     }
-    // raise the hint so later candidates below this z skip the slow path
-    unsigned long long f = __ldcg(fast + idx);
-    while ((uint32_t)(f >> 32) < key) {
-        const unsigned long long nf = ((unsigned long long)key << 32) | (f & 0xFFFFFFFFull);
-        const unsigned long long old = atomicCAS(fast + idx, f, nf);
-        if (old == f) break;
-        f = old;
-    }
+}
+
+// Everything that is not a plain in-view hit: out of view, non-finite coordinates, and the
+// corner pixel.  Evaluates lib.rs:789-802 literally.  Returns action << 32 | idx with action
+// 0 = not recorded (continue), 1 = record at idx, 2 = the state is NaN: this and every later iteration of the job hits
+// count[(0,0)] and can never win the depth test (NaN is absorbing).
+__device__ __noinline__ unsigned long long classify_rare(double fi, double fj, unsigned int W, unsigned int H,
+                                                         double nx, double ny, double nz)
+{
+    const double w = (double)W, h = (double)H;
+    if (fi >= w || fj >= h || fi < 0. || fj < 0.) return 0ull;  // lib.rs:789; NaN passes every test
+    if (nx != nx || ny != ny || nz != nz) return 2ull << 32;    // all of screen_space is NaN -> i = j = 0
+    const unsigned int i = (fi != fi) ? 0u : __double2uint_rz(fi);   // `as u32`: truncates, NaN -> 0 (lib.rs:800-802)
+    const unsigned int j = (fj != fj) ? 0u : __double2uint_rz(fj);
+    return (1ull << 32) | (unsigned long long)(j * W + i);
 }
 
 // ---------------------------------------------------------------------------------------------
 // iterate → project → scatter: render() (lib.rs:747-838), one lane per trajectory.
 // Lane L runs jobs L, L+lanes, L+2*lanes, ...; each job is one reference render() call:
 // start point, 1000 warm-up steps (lib.rs:750-752), `iterations` recorded steps.
+//
+// DEFER: the depth test needs the value the L2 atomic returns (~1000 cycles under load).
+// Instead of stalling, the test for iteration n is made DEFER iterations later, from a small
+// register queue {point before the step, pixel, z key, atomic result}; entries retire in order,
+// so within a job the earlier iteration still wins exact z ties.
 // ---------------------------------------------------------------------------------------------
+// One recorded iteration up to (and including) the count atomic.  In: the current point.
+// Out: the next point in (x,y,z); act 0 = out of view, 1 = recorded at idx with the atomic's
+// return value in `old` and the candidate depth key in `key` (0 = cannot win), 2 = NaN state.
+// MODE is a diagnostic switch for roofline experiments (tools/sweep_iterate.py); only MODE 0
+// is the product: 1 = arithmetic only (no memory traffic), 2 = count with a fire-and-forget
+// reduction and no depth test, 3 = reduction + separate 4-byte load of the depth hint.
+template <int MODE>
+__device__ __forceinline__ int step_point(const IterParams &P, double &x, double &y, double &z,
+                                          unsigned int &idx, uint32_t &key, unsigned long long &old)
+{
+    double nx, ny, nz;
+    SAR_NEXT_POINT(P, x, y, z, nx, ny, nz);                                   // lib.rs:770
+    // screen_space = rotation_matrix.mul_right(current_point), lib.rs:773 / 208-215
+    const double sx = __dadd_rn(__dadd_rn(__dmul_rn(P.m[0][0], nx), __dmul_rn(P.m[0][1], ny)), __dmul_rn(P.m[0][2], nz));
+    const double sy = __dadd_rn(__dadd_rn(__dmul_rn(P.m[1][0], nx), __dmul_rn(P.m[1][1], ny)), __dmul_rn(P.m[1][2], nz));
+    const double sz = __dadd_rn(__dadd_rn(__dmul_rn(P.m[2][0], nx), __dmul_rn(P.m[2][1], ny)), __dmul_rn(P.m[2][2], nz));
+    // rotate around center_camera, lib.rs:776-779 (center_camera.y pairs with screen_space.z)
+    const double a = __dadd_rn(sx, P.ccx);
+    const double b = __dadd_rn(sz, P.ccy);
+    const double x2 = __dadd_rn(__dmul_rn(a, P.cv), __dmul_rn(b, P.sv));
+    const double z2 = __dsub_rn(__dmul_rn(a, P.sv), __dmul_rn(b, P.cv));
+    const double fi = __dmul_rn(__dsub_rn(P.sam, x2), P.ws);                       // lib.rs:783
+    const double fj = __dsub_rn(P.half_h, __dmul_rn(__dadd_rn(sy, P.ccz), P.ws));  // lib.rs:786
+    // Bounds test + `as u32` (lib.rs:789-802) for the common case in one step: floor-convert
+    // (saturating) and compare unsigned.  i in [0,W) <=> 0 <= floor(i) < W, and floor == trunc
+    // there.  Anything else — out of view, NaN, pixel 0 — takes classify_rare(), which applies
+    // the reference's comparisons literally.
+    const unsigned int ii = (unsigned int)__double2int_rd(fi);
+    const unsigned int jj = (unsigned int)__double2int_rd(fj);
+    idx = jj * P.W + ii;
+    int act = 1;
+    if (!(ii < P.W && jj < P.H) || idx == 0u) {
+        const unsigned long long r = classify_rare(fi, fj, P.W, P.H, nx, ny, nz);
+        act = (int)(r >> 32);
+        idx = (unsigned int)r;
+    }
+    key = 0u;
+    old = ~0ull;
+    if (act == 1) {
+        if (MODE == 0) {
+            old = atomicAdd(P.fast + idx, 1ull);      // count += 1 (lib.rs:811) + fetch the depth hint, one L2 atomic
+        } else if (MODE == 1) {
+            old = ~0ull ^ (unsigned long long)(idx == 0xFFFFFFFFu);
+        } else if (MODE == 2) {
+            asm volatile("red.global.add.u64 [%0], 1;" ::"l"(P.fast + idx) : "memory");
+        } else if (MODE == 3) {
+            asm volatile("red.global.add.u64 [%0], 1;" ::"l"(P.fast + idx) : "memory");
+            old = (unsigned long long)__ldcg(reinterpret_cast<const unsigned int *>(P.fast + idx) + 1) << 32;
+        } else if (MODE == 4) {
+            old = atomicAdd(P.fast + idx, 1ull);
+        } else if (MODE == 5) {
+            asm volatile("red.global.add.u64 [%0], 1;" ::"l"(P.fast + idx) : "memory");
+        } else if (MODE == 6) {
+            asm volatile("red.global.add.u64 [%0], 1;" ::"l"(P.fast + idx) : "memory");
+            unsigned int h;
+            asm volatile("ld.global.ca.u32 %0, [%1];" : "=r"(h) : "l"(reinterpret_cast<const unsigned int *>(P.fast + idx) + 1));
+            old = (unsigned long long)h << 32;
+        }
+        const float zf = __double2float_rn(z2) + 0.0f;                        // `z2 as f32`; -0 -> +0
+        key = zkey_of(zf);
+        if (key > ZKEY_POS_INF) key = 0u;                                     // NaN never passes `>` (lib.rs:821)
+        if (MODE == 5) {
+            const unsigned long long packed = ((unsigned long long)key << 32) | idx;
+            asm volatile("red.global.max.u64 [%0], %1;" ::"l"(&P.rec[idx].y), "l"(packed) : "memory");
+            key = 0u;
+        }
+        if (MODE == 4) {                              // keep the returned value live, never take the slow path
+            if (key >= (uint32_t)(old >> 32) && key != 0u && idx == 0xFFFFFFF0u) P.scal->pad = key;
+            key = 0u;
+        }
+    }
+    x = nx; y = ny; z = nz;                           // previous_point = current_point, lib.rs:793/836
+    return act;
+}
+
+// Register queue of pending depth tests (struct of arrays; every index is a template constant,
+// so the whole queue stays in registers).
+template <int NQ>
+struct Queue {
+    double x[NQ], y[NQ], z[NQ];       // the point BEFORE the step (previous_point, lib.rs:766/836)
+    unsigned long long old[NQ];       // what the atomic returned: zhint << 32 | count
+    unsigned int idx[NQ];
+    uint32_t key[NQ];                 // 0 = nothing to test (the hint is never 0)
+};
+
+template <int K, int END, int NQ>
+__device__ __forceinline__ void retire_range(const IterParams &P, const Queue<NQ> &q, uint32_t job_inv)
+{
+    if constexpr (K < END) {
+        if (q.key[K] >= (uint32_t)(q.old[K] >> 32) && q.key[K] != 0u)        // may beat zbuf, lib.rs:821
+            record_win(&P, q.idx[K], q.key[K], job_inv, q.old[K], q.x[K], q.y[K], q.z[K]);
+        retire_range<K + 1, END, NQ>(P, q, job_inv);
+    }
+}
+
+// NQ consecutive iterations; slot J holds the entry of NQ iterations ago.  Returns true when the
+// trajectory went NaN (queue drained oldest-first, debt paid): the job is over.
+template <int J, int NQ, int MODE>
+__device__ __forceinline__ bool group_steps(const IterParams &P, Queue<NQ> &q, double &x, double &y, double &z,
+                                            unsigned long long it, uint32_t job_inv)
+{
+    if constexpr (J < NQ) {
+        const double px = x, py = y, pz = z;
+        unsigned int idx; uint32_t key; unsigned long long old;
+        const int act = step_point<MODE>(P, x, y, z, idx, key, old);
+        if (act == 2) {
+            atomicAdd(&P.scal->nan_sink, P.iterations - (it + J));            // pay the whole debt at once
+            retire_range<J, NQ, NQ>(P, q, job_inv);
+            retire_range<0, J, NQ>(P, q, job_inv);
+            return true;
+        }
+        retire_range<J, J + 1, NQ>(P, q, job_inv);                            // the test of NQ iterations ago
+        q.x[J] = px; q.y[J] = py; q.z[J] = pz; q.old[J] = old; q.idx[J] = idx; q.key[J] = key;
+        return group_steps<J + 1, NQ, MODE>(P, q, x, y, z, it, job_inv);
+    } else {
+        return false;
+    }
+}
+
+template <int K, int NQ>
+__device__ __forceinline__ void clear_queue(Queue<NQ> &q)
+{
+    if constexpr (K < NQ) {
+        q.key[K] = 0u; q.old[K] = ~0ull; q.idx[K] = 0u; q.x[K] = q.y[K] = q.z[K] = 0.;
+        clear_queue<K + 1, NQ>(q);
+    }
+}
+
+template <int DEFER, int MODE>
 __global__ void __launch_bounds__(128)
 iterate_kernel(const __grid_constant__ IterParams P)
 {
+    constexpr int NQ = DEFER > 0 ? DEFER : 1;
     const unsigned long long lanes = (unsigned long long)gridDim.x * blockDim.x;
     for (unsigned long long job = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; job < P.n_jobs; job += lanes) {
         double x, y, z;
@@ -157,55 +318,73 @@ iterate_kernel(const __grid_constant__ IterParams P)
         const unsigned long long jk = (unsigned long long)P.job_key0 + job;
         const uint32_t job_inv = 0xFFFFFFFFu - (uint32_t)(jk > 0xFFFFFFFFull ? 0xFFFFFFFFull : jk);
 
-        for (unsigned long long it = 0; it < P.iterations; ++it) {            // lib.rs:769
-            double nx, ny, nz;
-            SAR_NEXT_POINT(P, x, y, z, nx, ny, nz);                           // lib.rs:770
-            // screen_space = rotation_matrix.mul_right(current_point), lib.rs:773 / 208-215
-            const double sx = __dadd_rn(__dadd_rn(__dmul_rn(P.m[0][0], nx), __dmul_rn(P.m[0][1], ny)), __dmul_rn(P.m[0][2], nz));
-            const double sy = __dadd_rn(__dadd_rn(__dmul_rn(P.m[1][0], nx), __dmul_rn(P.m[1][1], ny)), __dmul_rn(P.m[1][2], nz));
-            const double sz = __dadd_rn(__dadd_rn(__dmul_rn(P.m[2][0], nx), __dmul_rn(P.m[2][1], ny)), __dmul_rn(P.m[2][2], nz));
-            // rotate around center_camera, lib.rs:776-779 (center_camera.y pairs with screen_space.z)
-            const double a = __dadd_rn(sx, P.ccx);
-            const double b = __dadd_rn(sz, P.ccy);
-            const double x2 = __dadd_rn(__dmul_rn(a, P.cv), __dmul_rn(b, P.sv));
-            const double z2 = __dsub_rn(__dmul_rn(a, P.sv), __dmul_rn(b, P.cv));
-            const double fi = __dmul_rn(__dsub_rn(P.sam, x2), P.ws);                       // lib.rs:783
-            const double fj = __dsub_rn(P.half_h, __dmul_rn(__dadd_rn(sy, P.ccz), P.ws));  // lib.rs:786
-            // Bounds test + `as u32` (lib.rs:789-802) in one step: floor-convert (saturating,
-            // NaN -> 0) and compare unsigned.  i in [0,W) <=> 0 <= floor(i) < W; floor == trunc
-            // there; -0.0 -> 0 and NaN -> 0 pass exactly as in the reference.
-            const unsigned int ii = (unsigned int)__double2int_rd(fi);
-            const unsigned int jj = (unsigned int)__double2int_rd(fj);
-            if (ii < P.W && jj < P.H) {
-                const unsigned int idx = jj * P.W + ii;
-                if (idx == 0u && (nx != nx || ny != ny || nz != nz)) {
-                    // NaN is absorbing: this and every remaining iteration lands on count[(0,0)]
-                    // and can never win the z test.  Pay the debt in one atomic.
-                    atomicAdd(&P.scal->nan_sink, P.iterations - it);
-                    break;
-                }
-                // count += 1 (lib.rs:811) and fetch the depth hint in one L2 atomic
-                const unsigned long long old = atomicAdd(P.fast + idx, 1ull);
-                const float zf = __double2float_rn(z2) + 0.0f;                // `z2 as f32`; -0 -> +0
-                const uint32_t key = zkey_of(zf);
-                if (key >= (uint32_t)(old >> 32) && key <= ZKEY_POS_INF) {    // may beat zbuf (lib.rs:821); NaN never does
-                    record_win(P.fast, P.rec, idx, key, job_inv, P.ct_kind, P.ct_offset, P.ct_factor, P.ccx, P.ccy,
-                               __dsub_rn(nx, x), __dsub_rn(ny, y), __dsub_rn(nz, z), sx, sy, sz);   // delta, lib.rs:822
-                }
+        unsigned long long it = 0;
+        bool dead = false;
+        if (DEFER > 0) {
+            Queue<NQ> q;
+            clear_queue<0, NQ>(q);
+            const unsigned long long n_main = P.iterations - P.iterations % (unsigned long long)NQ;
+            for (; it < n_main; it += NQ) {                                   // lib.rs:769, NQ at a time
+                dead = group_steps<0, NQ, MODE>(P, q, x, y, z, it, job_inv);
+                if (dead) break;
             }
-            x = nx; y = ny; z = nz;                                           // previous_point = current_point, lib.rs:793/836
+            if (!dead) retire_range<0, NQ, NQ>(P, q, job_inv);
+        }
+        for (; it < P.iterations && !dead; ++it) {                            // DEFER == 0, or the < NQ tail
+            const double px = x, py = y, pz = z;
+            unsigned int idx; uint32_t key; unsigned long long old;
+            const int act = step_point<MODE>(P, x, y, z, idx, key, old);
+            if (act == 2) { atomicAdd(&P.scal->nan_sink, P.iterations - it); break; }
+            if (key >= (uint32_t)(old >> 32) && key != 0u) record_win(&P, idx, key, job_inv, old, px, py, pz);
         }
     }
 }
 
+static std::atomic<int> g_defer{-1};
+static std::atomic<int> g_mode{0};
+bool set_mode(int m)
+{
+    if (m < 0 || m > 6) return false;
+    g_mode = m;
+    return true;
+}
+bool set_defer(int d)
+{
+    if (d < 0 || d > 4) return false;
+    g_defer = d;
+    return true;
+}
 void launch_iterate(const IterParams &p, unsigned int lanes, cudaStream_t s)
 {
     if (p.n_jobs == 0) return;
+    if (g_defer < 0) {                       // tuning knob; the default is what the sweep measured best
+        const char *e = getenv("SAR_DEFER");
+        int d = e ? atoi(e) : 0;
+        g_defer = (d < 0 || d > 4) ? 0 : d;
+    }
     unsigned long long want = p.n_jobs < lanes ? p.n_jobs : lanes;
     // small launches: narrow blocks so the jobs spread over the SMs
     const unsigned int block = want >= 148ull * 128ull ? 128u : 32u;
     const unsigned int grid = (unsigned int)((want + block - 1) / block);
-    iterate_kernel<<<grid, block, 0, s>>>(p);
+    if (g_mode != 0) {                       // diagnostics only (incomplete results by design)
+        switch (g_mode.load()) {
+        case 1: iterate_kernel<1, 1><<<grid, block, 0, s>>>(p); break;
+        case 2: iterate_kernel<1, 2><<<grid, block, 0, s>>>(p); break;
+        case 3: iterate_kernel<1, 3><<<grid, block, 0, s>>>(p); break;
+        case 4: iterate_kernel<1, 4><<<grid, block, 0, s>>>(p); break;
+        case 5: iterate_kernel<1, 5><<<grid, block, 0, s>>>(p); break;
+        default: iterate_kernel<1, 6><<<grid, block, 0, s>>>(p); break;
+        }
+        ++g_launches;
+        return;
+    }
+    switch (g_defer.load()) {
+    case 0: iterate_kernel<0, 0><<<grid, block, 0, s>>>(p); break;
+    case 1: iterate_kernel<1, 0><<<grid, block, 0, s>>>(p); break;
+    case 2: iterate_kernel<2, 0><<<grid, block, 0, s>>>(p); break;
+    case 3: iterate_kernel<3, 0><<<grid, block, 0, s>>>(p); break;
+    default: iterate_kernel<4, 0><<<grid, block, 0, s>>>(p); break;
+    }
     ++g_launches;
 }
 
@@ -282,11 +461,13 @@ void launch_max(const unsigned long long *fast, const ulonglong2 *rec, Scalars *
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint16_t sat_u16(double v)          // Rust `as u16`: saturating, NaN -> 0
 {
+    if (!(v > 0.)) return 0;                                    // NaN, negative, zero
     const unsigned int u = __double2uint_rz(v);
     return (uint16_t)(u > 65535u ? 65535u : u);
 }
 __device__ __forceinline__ uint16_t sat_u16f(float v)
 {
+    if (!(v > 0.f)) return 0;
     const unsigned int u = __float2uint_rz(v);
     return (uint16_t)(u > 65535u ? 65535u : u);
 }
@@ -316,7 +497,7 @@ colorize_kernel(const __grid_constant__ ColorParams C, const unsigned long long 
             if (v < 0.) v = 0.; else if (v >= 1.) v = 0.999999;
             v = __dmul_rn(v, C.pal_len);
             const double fl = floor(v);
-            unsigned int n = __double2uint_rz(fl);              // `as usize`, NaN -> 0
+            unsigned int n = (fl > 0.) ? __double2uint_rz(fl) : 0u;   // `as usize`: NaN -> 0
             if (n > C.palette_len - 1u) n = C.palette_len - 1u;
             const double t = fmod(v, 1.);                       // `value % 1.`, lib.rs:454
             const double t1 = __dsub_rn(1.0, t);

@@ -131,7 +131,11 @@ class Frame:
 
         self.N, self.L = N, N.lib()
         self.world, self.rank, self.group, self.device, self.seed = world, rank, group, device, seed
-        self.lanes = lanes or torch.cuda.get_device_properties(device).multi_processor_count * 256
+        if not lanes:
+            t = C.c_uint32()
+            N.check(N.lib().sar_default_threads(device, C.byref(t)))
+            lanes = int(t.value)
+        self.lanes = lanes
         self.jpt = jobs_per_thread
         self.total_iterations = iterations_per_gpu * world
         self.iterations_per_job = iterations_per_job(self.total_iterations, self.lanes * world, jobs_per_thread)
