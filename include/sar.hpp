@@ -1,0 +1,180 @@
+// sar.hpp — C++17 host mirror of the reference's public API for the render path, header-only,
+// over the C ABI of sar.h.  The reference is a Rust library; this is the same surface for
+// compiled callers where no Rust toolchain exists (names, argument meaning and failure points
+// follow src/lib.rs; where the reference panics, sar::Error is thrown):
+//
+//   sar::Vec3, EulerAxisRotation, View, RenderKind, BrighnessConstants, Palette, Colors   lib.rs:115-175, 232-492
+//   sar::attractors::PolynomialSprott2Degree                                               lib.rs:575-580
+//   sar::color_transforms::{PoissonSaturne, AdjustedVelocity}                              lib.rs:503-559
+//   sar::Config::{poisson_saturne, solar_sail}                                             lib.rs:310-387
+//   sar::Runtime::{Runtime(config), reset, merge}                                          lib.rs:660, 682, 708
+//   sar::render(config, runtime), sar::colorize(config, runtime) -> FinalImage             lib.rs:747, 841
+//   sar::ParallelRenderer::{ParallelRenderer(), shutdown}, sar::render_parallel(...)       lib.rs:919, 1020, 1051
+#pragma once
+#include <array>
+#include <cstdint>
+#include <random>
+#include <stdexcept>
+#include <string>
+#include <variant>
+#include <vector>
+
+#include "sar.h"
+
+namespace sar {
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string &m) : std::runtime_error("sar error " + std::to_string(c) + ": " + m), code(c) {}
+};
+inline void check(int rc) { if (rc != SAR_OK) throw Error(rc, sar_last_error()); }
+
+struct Vec3 { double x, y, z; };                                   // lib.rs:115-119
+struct EulerAxisRotation { Vec3 axis; double rotation; };          // lib.rs:170-175 (axis used as given, lib.rs:181-183)
+struct View { Vec3 center_camera; EulerAxisRotation rotation; double scale; };   // lib.rs:253-261
+enum class RenderKind { Gas = SAR_RENDER_GAS, Depth = SAR_RENDER_DEPTH };          // lib.rs:234-239
+struct BrighnessConstants { double offset = -0.15, factor = 5. / 3.; };           // lib.rs:390-404 (sic)
+
+struct Palette {                                                   // lib.rs:408-473
+    std::vector<std::array<double, 3>> list;                       // without the duplicated sentinel of lib.rs:418
+    explicit Palette(std::vector<std::array<double, 3>> l) : list(std::move(l)) {
+        if (list.empty()) throw Error(SAR_ERR_INVALID, "Palette::new panics if list.is_empty() (lib.rs:415)");
+        if (list.size() > SAR_MAX_PALETTE) throw Error(SAR_ERR_INVALID, "too many palette entries for the C ABI");
+    }
+    template <size_t LEN>
+    static Palette from_rgb(const std::array<double, LEN> &r, const std::array<double, LEN> &g, const std::array<double, LEN> &b) {
+        std::vector<std::array<double, 3>> l;
+        for (size_t i = 0; i < LEN; ++i) l.push_back({r[i], g[i], b[i]});
+        return Palette(std::move(l));
+    }
+    size_t count() const { return list.size(); }
+};
+struct Colors {                                                    // lib.rs:475-492
+    Palette palette = Palette::from_rgb<6>({1., 0.5, 1., 0.5, 0.5, 1.}, {1., 1., 0.5, 1., 0.5, 0.5}, {0.5, 0.5, 0.5, 1., 1., 1.});
+    BrighnessConstants brighness;
+};
+
+namespace attractors {
+struct PolynomialSprott2Degree { std::array<double, 10> x, y, z; };  // lib.rs:575-580
+}
+namespace color_transforms {
+struct PoissonSaturne {};                                          // the fn item color_transforms::poisson_saturne, lib.rs:520
+struct AdjustedVelocity { double offset, factor; };               // lib.rs:507-510
+}
+using ColorTransform = std::variant<color_transforms::PoissonSaturne, color_transforms::AdjustedVelocity>;
+
+struct Config {                                                    // lib.rs:265-287, defaults lib.rs:289-307
+    size_t iterations = 10'000'000;
+    uint32_t width = 1920, height = 1080;
+    RenderKind render = RenderKind::Gas;
+    bool transparent = true;
+    double angle = 0.0;                                            // radians (lib.rs:745)
+    bool silent = true;
+    attractors::PolynomialSprott2Degree attractor{};
+    Colors colors;
+    View view{};
+    ColorTransform color_transform;
+
+    static Config from_pod(const sar_config &c) {
+        Config k;
+        k.iterations = c.iterations; k.width = c.width; k.height = c.height;
+        k.render = static_cast<RenderKind>(c.render_kind); k.transparent = c.transparent != 0; k.angle = c.angle; k.silent = c.silent != 0;
+        for (int i = 0; i < 10; ++i) { k.attractor.x[i] = c.coef[0][i]; k.attractor.y[i] = c.coef[1][i]; k.attractor.z[i] = c.coef[2][i]; }
+        k.view = View{{c.center_camera[0], c.center_camera[1], c.center_camera[2]}, {{c.axis[0], c.axis[1], c.axis[2]}, c.rotation}, c.scale};
+        if (c.ct_kind == SAR_CT_ADJUSTED_VELOCITY) k.color_transform = color_transforms::AdjustedVelocity{c.ct_offset, c.ct_factor};
+        else k.color_transform = color_transforms::PoissonSaturne{};
+        std::vector<std::array<double, 3>> l;
+        for (uint32_t i = 0; i < c.palette_len; ++i) l.push_back({c.palette_rgb[i][0], c.palette_rgb[i][1], c.palette_rgb[i][2]});
+        k.colors.palette = Palette(std::move(l));
+        k.colors.brighness = {c.bright_offset, c.bright_factor};
+        return k;
+    }
+    static Config poisson_saturne() { sar_config c; check(sar_config_poisson_saturne(&c)); return from_pod(c); }   // lib.rs:310
+    static Config solar_sail() { sar_config c; check(sar_config_solar_sail(&c)); return from_pod(c); }             // lib.rs:355
+
+    sar_config to_pod() const {
+        sar_config c{};
+        c.iterations = iterations; c.width = width; c.height = height;
+        c.render_kind = static_cast<uint32_t>(render); c.transparent = transparent; c.silent = silent; c.angle = angle;
+        for (int i = 0; i < 10; ++i) { c.coef[0][i] = attractor.x[i]; c.coef[1][i] = attractor.y[i]; c.coef[2][i] = attractor.z[i]; }
+        c.center_camera[0] = view.center_camera.x; c.center_camera[1] = view.center_camera.y; c.center_camera[2] = view.center_camera.z;
+        c.axis[0] = view.rotation.axis.x; c.axis[1] = view.rotation.axis.y; c.axis[2] = view.rotation.axis.z;
+        c.rotation = view.rotation.rotation; c.scale = view.scale;
+        if (auto *av = std::get_if<color_transforms::AdjustedVelocity>(&color_transform)) {
+            c.ct_kind = SAR_CT_ADJUSTED_VELOCITY; c.ct_offset = av->offset; c.ct_factor = av->factor;
+        } else c.ct_kind = SAR_CT_POISSON_SATURNE;
+        c.palette_len = static_cast<uint32_t>(colors.palette.count());
+        for (uint32_t i = 0; i < c.palette_len; ++i) for (int k = 0; k < 3; ++k) c.palette_rgb[i][k] = colors.palette.list[i][k];
+        c.bright_offset = colors.brighness.offset; c.bright_factor = colors.brighness.factor;
+        return c;
+    }
+};
+
+// ImageBuffer<Rgba<u16>, Vec<u16>> (lib.rs:625): interleaved RGBA, row-major.
+struct FinalImage {
+    uint32_t width = 0, height = 0;
+    std::vector<uint16_t> raw;
+    const uint16_t *pixel(uint32_t x, uint32_t y) const { return raw.data() + (size_t(y) * width + x) * 4; }
+};
+
+class Runtime {                                                    // lib.rs:631-739
+public:
+    // Runtime::new(&config).  seed: the reference seeds from the OS (lib.rs:656); pass one for reproducibility.
+    explicit Runtime(const Config &config, int device = 0, uint64_t seed = std::random_device{}() | (uint64_t(std::random_device{}()) << 32))
+        : seed_(seed) { check(sar_runtime_new(config.width, config.height, device, &h_)); }
+    Runtime(const Runtime &) = delete;
+    Runtime &operator=(const Runtime &) = delete;
+    ~Runtime() { sar_runtime_free(h_); }
+    void reset() { check(sar_runtime_reset(h_)); }                                   // lib.rs:682
+    void merge(const Runtime &other) { check(sar_runtime_merge(h_, other.h_)); }     // lib.rs:708 (throws on dimension mismatch)
+    sar_runtime *handle() const { return h_; }
+    uint64_t seed_;
+    uint64_t draws_ = 0;
+private:
+    sar_runtime *h_ = nullptr;
+};
+
+// render(&config, &mut runtime), lib.rs:747 — one trajectory, accumulates, does not reset.
+inline void render(const Config &config, Runtime &runtime) {
+    const sar_config c = config.to_pod();
+    check(sar_render_seeded(&c, runtime.handle(), runtime.seed_, runtime.draws_, 1));
+    ++runtime.draws_;
+}
+// the parity form: explicit start points (n×3 f64), one render() per point
+inline void render(const Config &config, Runtime &runtime, const std::vector<double> &init_xyz) {
+    const sar_config c = config.to_pod();
+    check(sar_render(&c, runtime.handle(), init_xyz.data(), init_xyz.size() / 3));
+}
+// colorize(&config, &runtime) -> FinalImage, lib.rs:841
+inline FinalImage colorize(const Config &config, const Runtime &runtime) {
+    const sar_config c = config.to_pod();
+    FinalImage img{config.width, config.height, std::vector<uint16_t>(size_t(config.width) * config.height * 4)};
+    check(sar_colorize(&c, runtime.handle(), img.raw.data(), nullptr));
+    return img;
+}
+
+class ParallelRenderer {                                           // lib.rs:908-1030
+public:
+    explicit ParallelRenderer(const std::vector<int> &devices = {}, uint32_t threads_per_device = 0) {
+        check(sar_renderer_new(devices.empty() ? nullptr : devices.data(), int(devices.size()), threads_per_device, &h_));
+    }
+    ParallelRenderer(const ParallelRenderer &) = delete;
+    ParallelRenderer &operator=(const ParallelRenderer &) = delete;
+    ~ParallelRenderer() { shutdown(); }
+    void shutdown() { sar_renderer_shutdown(h_); h_ = nullptr; }   // lib.rs:1020
+    uint64_t num_threads() const { uint64_t n = 0; check(sar_renderer_num_threads(h_, &n)); return n; }   // lib.rs:1015
+    sar_renderer *handle() const { return h_; }
+private:
+    sar_renderer *h_ = nullptr;
+};
+
+// render_parallel(&mut renderer, config, jobs_per_thread) -> FinalImage, lib.rs:1051
+inline FinalImage render_parallel(ParallelRenderer &renderer, const Config &config, size_t jobs_per_thread,
+                                  uint64_t seed = std::random_device{}() | (uint64_t(std::random_device{}()) << 32)) {
+    const sar_config c = config.to_pod();
+    FinalImage img{config.width, config.height, std::vector<uint16_t>(size_t(config.width) * config.height * 4)};
+    check(sar_render_parallel(renderer.handle(), &c, jobs_per_thread, seed, nullptr, img.raw.data()));
+    return img;
+}
+
+}  // namespace sar

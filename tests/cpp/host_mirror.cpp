@@ -1,0 +1,64 @@
+// Drives the C++ host mirror (include/sar.hpp) the way the reference's only in-repo caller does
+// (src/bin/main.rs:482-518): single-thread path Runtime::new → render → colorize → reset, and
+// the parallel path ParallelRenderer::new → render_parallel → shutdown.  Prints FNV-1a hashes of
+// the images so the Python test can compare them with the same calls made through api.py.
+#include <cstdio>
+#include <cstring>
+
+#include "sar.hpp"
+
+static unsigned long long fnv(const std::vector<uint16_t> &v)
+{
+    unsigned long long h = 1469598103934665603ull;
+    const unsigned char *p = reinterpret_cast<const unsigned char *>(v.data());
+    for (size_t i = 0; i < v.size() * 2; ++i) { h ^= p[i]; h *= 1099511628211ull; }
+    return h;
+}
+
+int main(int argc, char **argv)
+{
+    using namespace sar;
+    Config cfg = Config::poisson_saturne();
+    Config sol = Config::solar_sail();
+    // presets round-trip through the POD
+    const sar_config a = cfg.to_pod(), b = Config::from_pod(a).to_pod();
+    if (std::memcmp(&a, &b, sizeof a) != 0) { std::puts("POD_ROUNDTRIP_FAILED"); return 2; }
+    if (!std::holds_alternative<color_transforms::AdjustedVelocity>(sol.color_transform) || sol.view.scale != 1.7) { std::puts("PRESET_FAILED"); return 2; }
+    std::puts("PRESETS_OK");
+
+    if (argc > 1 && std::strcmp(argv[1], "--no-gpu") == 0) {
+        try {
+            Runtime rt(cfg);
+            std::puts("UNEXPECTED_RUNTIME");
+            return 3;
+        } catch (const Error &e) {
+            std::printf("NO_GPU_ERROR code=%d\n", e.code);
+            return e.code == SAR_ERR_CUDA ? 0 : 4;
+        }
+    }
+
+    // single-thread path, main.rs:482-491
+    cfg.iterations = 200000; cfg.width = 320; cfg.height = 200;
+    Runtime runtime(cfg, 0, /*seed=*/42);
+    for (int frame = 0; frame < 2; ++frame) {
+        cfg.angle = 0.3 * frame;
+        render(cfg, runtime);
+        FinalImage image = colorize(cfg, runtime);
+        std::printf("SINGLE frame=%d hash=%llu\n", frame, fnv(image.raw));
+        runtime.reset();
+    }
+    // merge panics on a dimension mismatch (lib.rs:709-710)
+    Config other = cfg; other.width = 100;
+    Runtime small(other, 0, 1);
+    try { runtime.merge(small); std::puts("MERGE_DID_NOT_FAIL"); return 5; }
+    catch (const Error &e) { std::printf("MERGE_MISMATCH code=%d\n", e.code); }
+
+    // parallel path, main.rs:492-518
+    sol.iterations = 3000000; sol.width = 180; sol.height = 200; sol.angle = 3.839724354387525;
+    ParallelRenderer renderer({}, 256);
+    FinalImage img = render_parallel(renderer, sol, 12, /*seed=*/7);
+    std::printf("PARALLEL threads=%llu hash=%llu px00=%u,%u,%u\n", (unsigned long long)renderer.num_threads(), fnv(img.raw),
+                img.pixel(0, 0)[0], img.pixel(0, 0)[1], img.pixel(0, 0)[2]);
+    renderer.shutdown();
+    return 0;
+}
