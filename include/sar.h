@@ -176,8 +176,15 @@ int  sar_renderer_new(const int *devices, int n_devices, uint32_t threads_per_de
                       sar_renderer **out);
 /* ParallelRenderer::shutdown, lib.rs:1020. */
 void sar_renderer_shutdown(sar_renderer *r);
-/* num_threads(), lib.rs:1015 — total over the renderer's devices. */
-int  sar_renderer_num_threads(const sar_renderer *r, uint64_t *num_threads);
+/* num_threads(), lib.rs:1015 — total over the renderer's devices.  With an
+ * explicit threads_per_device it is fixed.  In auto mode (0) it depends on
+ * jobs_per_thread: every job already gets its own lane and all jobs have the
+ * same length, so the renderer keeps the number of JOBS at the device's lane
+ * count: num_threads = lanes / jobs_per_thread (multiple of 32, >= 32), and
+ * num_threads × jobs_per_thread jobs of iterations/num_threads/jobs_per_thread
+ * steps run, exactly as lib.rs:1058-1062 prescribes for that num_threads. */
+int  sar_renderer_num_threads(const sar_renderer *r, uint64_t *num_threads);   /* jobs_per_thread = 1 */
+int  sar_renderer_num_threads_for(const sar_renderer *r, uint64_t jobs_per_thread, uint64_t *num_threads);
 /* render_parallel, lib.rs:1051: iterations/num_threads/jobs_per_thread per job
  * (integer division, lib.rs:1058), num_threads*jobs_per_thread jobs
  * (lib.rs:1062), merge (lib.rs:1072-1076), colorize (lib.rs:1080).
@@ -185,6 +192,24 @@ int  sar_renderer_num_threads(const sar_renderer *r, uint64_t *num_threads);
  * rgba_u16: width*height*4, caller-owned host memory.  Blocking. */
 int  sar_render_parallel(sar_renderer *r, const sar_config *cfg, uint64_t jobs_per_thread,
                          uint64_t seed, const double *init_xyz, uint16_t *rgba_u16);
+/* A sequence of frames: the per-frame loop of the reference's binary around
+ * render_parallel (src/bin/main.rs:496-512; angles as AngleIter yields them,
+ * main.rs:107-176, in RADIANS).  Frame f is a one-device render_parallel of
+ * `cfg` with angle = angles_rad[f]; frames round-robin over the renderer's
+ * devices (independent replicas) and each frame's device→host copy overlaps
+ * the next frame's render.  Start points: by default frame f takes the next
+ * num_threads*jobs_per_thread points of the seed stream (fresh points every
+ * frame, like the reference).  With SAR_SEQ_SHARED_POINTS every frame uses
+ * points [0, jobs): the trajectories are then identical across frames and the
+ * 1000-step warm-up (lib.rs:750-752) runs once for the whole sequence.
+ * Output: rgba_frames (n_frames × width*height*4 u16, caller-owned, may be
+ * NULL) and/or cb(user, frame, pixels), called in frame order from the calling
+ * thread; without rgba_frames the pixels pointer is only valid inside cb. */
+#define SAR_SEQ_SHARED_POINTS 1u
+typedef void (*sar_frame_callback)(void *user, uint32_t frame, const uint16_t *rgba_u16);
+int  sar_render_sequence(sar_renderer *r, const sar_config *cfg, const double *angles_rad,
+                         uint32_t n_frames, uint64_t jobs_per_thread, uint64_t seed, uint32_t flags,
+                         uint16_t *rgba_frames, sar_frame_callback cb, void *user);
 /* The merged Runtime of the last sar_render_parallel on the renderer's first
  * device (valid until the next call / shutdown); for inspection and tests. */
 int  sar_renderer_runtime(sar_renderer *r, sar_runtime **rt);

@@ -7,7 +7,7 @@ The directory name carries a hyphen (it mirrors the reference's crate name); imp
 from .api import (  # noqa: F401
     BrighnessConstants, Colors, Config, EulerAxisRotation, FinalImage, Palette, ParallelRenderer,
     RenderKind, Runtime, SarConfig, SarError, Vec3, View, attractors, color_transforms, colorize,
-    render, render_parallel, seed_points,
+    render, render_parallel, seed_points, angle_iter, render_sequence,
 )
 from . import _native, build  # noqa: F401
 
@@ -15,4 +15,5 @@ __all__ = [
     "BrighnessConstants", "Colors", "Config", "EulerAxisRotation", "FinalImage", "Palette",
     "ParallelRenderer", "RenderKind", "Runtime", "SarConfig", "SarError", "Vec3", "View",
     "attractors", "color_transforms", "colorize", "render", "render_parallel", "seed_points",
+    "angle_iter", "render_sequence",
 ]

@@ -13,6 +13,8 @@ SAR_IPC_HANDLE_BYTES = 64
 SAR_OK, SAR_ERR_INVALID, SAR_ERR_DIMS, SAR_ERR_CUDA, SAR_ERR_NOMEM, SAR_ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 SAR_RENDER_GAS, SAR_RENDER_DEPTH = 0, 1
 SAR_CT_POISSON_SATURNE, SAR_CT_ADJUSTED_VELOCITY = 0, 1
+SAR_SEQ_SHARED_POINTS = 1
+FRAME_CALLBACK = C.CFUNCTYPE(None, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint16))
 
 
 class SarConfig(C.Structure):
@@ -77,8 +79,10 @@ SYMBOLS = {
     "sar_renderer_new": (C.c_int, [_P(C.c_int), C.c_int, C.c_uint32, _P(_vp)]),
     "sar_renderer_shutdown": (None, [_vp]),
     "sar_renderer_num_threads": (C.c_int, [_vp, _P(C.c_uint64)]),
+    "sar_renderer_num_threads_for": (C.c_int, [_vp, C.c_uint64, _P(C.c_uint64)]),
     "sar_render_parallel": (C.c_int, [_vp, _cfgp, C.c_uint64, C.c_uint64, _f64p, _u16p]),
     "sar_renderer_runtime": (C.c_int, [_vp, _P(_vp)]),
+    "sar_render_sequence": (C.c_int, [_vp, _cfgp, _f64p, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32, _u16p, _vp, _vp]),
     "sar_render_seeded_async": (C.c_int, [_cfgp, _vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, _vp]),
     "sar_render_device_async": (C.c_int, [_cfgp, _vp, _vp, C.c_uint64, C.c_uint64, C.c_uint32, _vp]),
     "sar_runtime_reset_async": (C.c_int, [_vp, _vp]),

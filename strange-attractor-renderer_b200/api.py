@@ -319,9 +319,11 @@ class ParallelRenderer:
 
     default = new
 
-    def num_threads(self) -> int:
+    def num_threads(self, jobs_per_thread: int = 1) -> int:
+        """lib.rs:1015.  In auto mode (threads=0) the count adapts to jobs_per_thread so that the
+        number of jobs stays at the device's lane count (include/sar.h)."""
         n = C.c_uint64()
-        N.check(N.lib().sar_renderer_num_threads(self._h, C.byref(n)))
+        N.check(N.lib().sar_renderer_num_threads_for(self._h, jobs_per_thread, C.byref(n)))
         return int(n.value)
 
     def shutdown(self) -> None:
@@ -356,9 +358,54 @@ def render_parallel(renderer: ParallelRenderer, config, jobs_per_thread: int, se
     pts_p = None
     if initial_points is not None:
         pts = np.ascontiguousarray(initial_points, dtype=np.float64).reshape(-1, 3)
-        if pts.shape[0] < renderer.num_threads() * jobs_per_thread:
+        if pts.shape[0] < renderer.num_threads(jobs_per_thread) * jobs_per_thread:
             raise SarError(N.SAR_ERR_INVALID, "initial_points must hold num_threads*jobs_per_thread points")
         pts_p = pts.ctypes.data_as(N._f64p)
     N.check(N.lib().sar_render_parallel(renderer._h, C.byref(c), jobs_per_thread, seed & (2**64 - 1), pts_p,
                                         out.ctypes.data_as(N._u16p)))
+    return out
+
+
+# ---- frame sequences (src/bin/main.rs:107-176, 459-517) ---------------------------------
+def angle_iter(start: float, end: float, step: float) -> List[float]:
+    """The angles AngleIter yields (main.rs:107-176): while curr + step/2 < end, curr (DEGREES)
+    converted to radians (main.rs:166), curr += step.  If that yields nothing, the single value
+    `start` is returned unconverted, exactly like the reference's single-image branch
+    (main.rs:169-171) — i.e. it is then taken as radians."""
+    import math
+
+    out, curr = [], float(start)
+    while curr + step / 2.0 < end:
+        out.append(curr * math.pi / 180.0)
+        curr += step
+    return out if out else [float(start)]
+
+
+def render_sequence(renderer: ParallelRenderer, config, angles: Sequence[float], jobs_per_thread: int,
+                    seed: Optional[int] = None, shared_points: bool = False, out: Optional[np.ndarray] = None,
+                    callback=None) -> Optional[np.ndarray]:
+    """The binary's frame loop (main.rs:496-512): for each angle (radians) set config.angle and
+    render_parallel.  Returns [n_frames, H, W, 4] uint16 (or streams frames to
+    callback(frame_index, image_view) when given and out is None).  shared_points=True uses one
+    list of start points for every frame, so the 1000-step warm-up runs once (include/sar.h)."""
+    c = _pod(config)
+    if seed is None:
+        seed = int.from_bytes(os.urandom(8), "little")
+    ang = np.ascontiguousarray(angles, dtype=np.float64)
+    n = int(ang.shape[0])
+    if out is None and callback is None:
+        out = np.empty((n, c.height, c.width, 4), dtype=np.uint16)
+    cb_c = None
+    if callback is not None:
+        shape = (c.height, c.width, 4)
+
+        def _cb(_user, frame, ptr):
+            callback(int(frame), np.ctypeslib.as_array(ptr, shape=shape))
+
+        cb_c = N.FRAME_CALLBACK(_cb)
+    N.check(N.lib().sar_render_sequence(
+        renderer._h, C.byref(c), ang.ctypes.data_as(N._f64p), n, jobs_per_thread, seed & (2**64 - 1),
+        N.SAR_SEQ_SHARED_POINTS if shared_points else 0,
+        out.ctypes.data_as(N._u16p) if out is not None else None,
+        C.cast(cb_c, C.c_void_p) if cb_c is not None else None, None))
     return out

@@ -75,11 +75,19 @@ struct sar_peer {
     Scalars *scal = nullptr;
 };
 
+struct seq_device {                  // per-device pipeline state of sar_render_sequence
+    uint16_t *img[2] = {nullptr, nullptr};          // device images, double buffered
+    uint16_t *stage[2] = {nullptr, nullptr};        // pinned host staging (when the caller gives no frame array)
+    cudaEvent_t rendered[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr};
+    cudaStream_t copy_stream = nullptr;
+    double *warm = nullptr; size_t warm_cap = 0;    // warmed states shared by all frames (SAR_SEQ_SHARED_POINTS)
+    size_t img_bytes = 0;
+};
+
 struct sar_renderer {
     std::vector<int> devices;
     std::vector<sar_runtime *> rts;
-    std::vector<sar_peer> inproc;    // views of rts[d>0] for the first device
-    std::vector<bool> direct;        // peer access from device 0 to device d enabled
+    std::vector<seq_device> seq;
     uint32_t threads_per_device = 0;
 };
 
@@ -150,6 +158,7 @@ static void make_iter_params(const sar_config *cfg, sar_runtime *rt, IterParams 
     p.fast = rt->fast; p.rec = rt->rec; p.scal = rt->scal;
     p.W = cfg->width; p.H = cfg->height; p.ct_kind = cfg->ct_kind;
     p.iterations = cfg->iterations;
+    p.warmup = SAR_WARMUP_ITERATIONS;                                            // lib.rs:750
 }
 
 static void make_color_params(const sar_config *cfg, ColorParams &c, uint32_t row0, uint32_t rows)
@@ -430,13 +439,15 @@ int sar_runtime_merge(sar_runtime *dst, const sar_runtime *src)
 
 // ---- render ------------------------------------------------------------------------------------
 static int render_launch(const sar_config *cfg, sar_runtime *rt, const double *d_init, uint64_t seed,
-                         uint64_t first_job, uint64_t n_jobs, uint32_t threads, cudaStream_t s)
+                         uint64_t first_job, uint64_t n_jobs, uint32_t threads, cudaStream_t s,
+                         bool init_is_warm = false)
 {
     if (int rc = check_config(cfg, rt)) return rc;
     SAR_CUDA(cudaSetDevice(rt->device));
     IterParams p;
     make_iter_params(cfg, rt, p);
     p.init = d_init; p.seed = seed; p.first_job = first_job; p.n_jobs = n_jobs;
+    if (init_is_warm) p.warmup = 0;
     const uint64_t key0 = rt->job_base + first_job;
     p.job_key0 = key0 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (unsigned int)key0;
     launch_iterate(p, threads ? threads : default_lanes(rt), s);
@@ -681,13 +692,30 @@ int sar_renderer_new(const int *devices, int n_devices, uint32_t threads_per_dev
     if (r->devices.size() > 16) { delete r; return fail(SAR_ERR_INVALID, "at most 16 devices"); }
     r->threads_per_device = threads_per_device;
     r->rts.assign(r->devices.size(), nullptr);     // Runtimes are created on first use (Runtime::empty, lib.rs:938)
+    r->seq.resize(r->devices.size());
     *out = r;
     return SAR_OK;
+}
+
+static void seq_release(sar_renderer *r, size_t d)
+{
+    seq_device &q = r->seq[d];
+    cudaSetDevice(r->devices[d]);
+    if (q.copy_stream) { cudaStreamSynchronize(q.copy_stream); cudaStreamDestroy(q.copy_stream); }
+    for (int k = 0; k < 2; ++k) {
+        cudaFree(q.img[k]);
+        if (q.stage[k]) cudaFreeHost(q.stage[k]);
+        if (q.rendered[k]) cudaEventDestroy(q.rendered[k]);
+        if (q.copied[k]) cudaEventDestroy(q.copied[k]);
+    }
+    cudaFree(q.warm);
+    q = seq_device();
 }
 
 void sar_renderer_shutdown(sar_renderer *r)
 {
     if (!r) return;
+    for (size_t d = 0; d < r->seq.size(); ++d) seq_release(r, d);
     for (sar_runtime *rt : r->rts) sar_runtime_free(rt);
     delete r;
 }
@@ -700,13 +728,33 @@ static uint32_t renderer_lanes(const sar_renderer *r, size_t d)
     return (uint32_t)sm * LANES_PER_SM;
 }
 
-int sar_renderer_num_threads(const sar_renderer *r, uint64_t *num_threads)
+// "Threads" of device d for a given jobs_per_thread.  With an explicit threads_per_device this
+// is that number (each lane then runs jobs_per_thread jobs one after the other, like a reference
+// worker, lib.rs:956-988).  In auto mode the GPU needs no over-decomposition for load balance —
+// every job has the same length and gets its own lane — so the job count is kept at the
+// device's lane count: threads = lanes / jobs_per_thread (multiple of 32, at least 32), which
+// keeps the 1000-step warm-up per job (lib.rs:750) from swamping short frames.
+static uint32_t renderer_threads_for(const sar_renderer *r, size_t d, uint64_t jobs_per_thread)
+{
+    const uint32_t lanes = renderer_lanes(r, d);
+    if (r->threads_per_device || jobs_per_thread <= 1) return lanes;
+    uint64_t t = (lanes / jobs_per_thread) & ~31ull;
+    return (uint32_t)(t < 32 ? 32 : t);
+}
+
+int sar_renderer_num_threads_for(const sar_renderer *r, uint64_t jobs_per_thread, uint64_t *num_threads)
 {
     if (!r || !num_threads) return fail(SAR_ERR_INVALID, "NULL argument");
+    if (jobs_per_thread == 0) return fail(SAR_ERR_INVALID, "jobs_per_thread must be non-zero");
     uint64_t n = 0;
-    for (size_t d = 0; d < r->devices.size(); ++d) n += renderer_lanes(r, d);
+    for (size_t d = 0; d < r->devices.size(); ++d) n += renderer_threads_for(r, d, jobs_per_thread);
     *num_threads = n;
     return SAR_OK;
+}
+
+int sar_renderer_num_threads(const sar_renderer *r, uint64_t *num_threads)
+{
+    return sar_renderer_num_threads_for(r, 1, num_threads);
 }
 
 int sar_renderer_runtime(sar_renderer *r, sar_runtime **rt)
@@ -726,7 +774,7 @@ int sar_render_parallel(sar_renderer *r, const sar_config *cfg_in, uint64_t jobs
     if (int rc = check_dims(cfg_in->width, cfg_in->height)) return rc;
     const size_t nd = r->devices.size();
     uint64_t num_threads = 0;
-    sar_renderer_num_threads(r, &num_threads);
+    sar_renderer_num_threads_for(r, jobs_per_thread, &num_threads);
     sar_config cfg = *cfg_in;
     cfg.iterations = cfg_in->iterations / num_threads / jobs_per_thread;        // lib.rs:1058
     const uint64_t total_jobs = jobs_per_thread * num_threads;                  // lib.rs:1062
@@ -741,8 +789,10 @@ int sar_render_parallel(sar_renderer *r, const sar_config *cfg_in, uint64_t jobs
     uint64_t first = 0;
     for (size_t d = 0; d < nd; ++d) {
         sar_runtime *rt = r->rts[d];
-        const uint32_t lanes = renderer_lanes(r, d);
-        const uint64_t n = (uint64_t)lanes * jobs_per_thread;
+        const uint32_t threads = renderer_threads_for(r, d, jobs_per_thread);
+        const uint64_t n = (uint64_t)threads * jobs_per_thread;
+        // explicit thread count: that many lanes, jobs_per_thread jobs each; auto: one lane per job
+        const uint32_t lanes = r->threads_per_device ? threads : (uint32_t)(n < renderer_lanes(r, d) ? n : renderer_lanes(r, d));
         rt->job_base = 0;
         if (init_xyz) {
             SAR_CUDA(cudaSetDevice(rt->device));
@@ -769,6 +819,116 @@ int sar_render_parallel(sar_renderer *r, const sar_config *cfg_in, uint64_t jobs
     if (int rc = sar_runtime_max_async(rt0, 0, 0, nullptr)) return rc;
     if (int rc = sar_colorize_rows_async(&cfg, rt0, 0, 0, nullptr, nullptr)) return rc;   // lib.rs:1080
     return sar_runtime_image_download(rt0, 0, 0, rgba_u16, nullptr);
+}
+
+// ---- frame sequences -------------------------------------------------------------------------
+// The per-frame loop of the reference's binary (src/bin/main.rs:496-512): for each angle,
+// config.angle = angle; image = render_parallel(...); hand the image to an encoder thread.
+// Frames are independent, so they round-robin over the renderer's devices (replicas, no
+// collective); on each device the frame's device→host copy overlaps the next frame's render.
+static int seq_prepare(sar_renderer *r, size_t d, const sar_config &cfg, bool need_stage)
+{
+    seq_device &q = r->seq[d];
+    const size_t bytes = (size_t)cfg.width * cfg.height * 4 * sizeof(uint16_t);
+    SAR_CUDA(cudaSetDevice(r->devices[d]));
+    if (q.img_bytes != bytes) {
+        seq_release(r, d);
+        q.img_bytes = bytes;
+    }
+    if (!q.copy_stream) SAR_CUDA(cudaStreamCreateWithFlags(&q.copy_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; ++k) {
+        if (!q.img[k]) SAR_CUDA(cudaMalloc((void **)&q.img[k], bytes));
+        if (need_stage && !q.stage[k]) SAR_CUDA(cudaHostAlloc((void **)&q.stage[k], bytes, cudaHostAllocPortable));
+        if (!q.rendered[k]) SAR_CUDA(cudaEventCreateWithFlags(&q.rendered[k], cudaEventDisableTiming));
+        if (!q.copied[k]) SAR_CUDA(cudaEventCreateWithFlags(&q.copied[k], cudaEventDisableTiming));
+    }
+    return SAR_OK;
+}
+
+int sar_render_sequence(sar_renderer *r, const sar_config *cfg_in, const double *angles_rad, uint32_t n_frames,
+                        uint64_t jobs_per_thread, uint64_t seed, uint32_t flags, uint16_t *rgba_frames,
+                        sar_frame_callback cb, void *user)
+{
+    if (!r || !cfg_in || (!angles_rad && n_frames)) return fail(SAR_ERR_INVALID, "NULL argument");
+    if (!rgba_frames && !cb) return fail(SAR_ERR_INVALID, "need a frame array or a callback");
+    if (jobs_per_thread == 0) return fail(SAR_ERR_INVALID, "jobs_per_thread must be non-zero");
+    if (flags & ~SAR_SEQ_SHARED_POINTS) return fail(SAR_ERR_INVALID, "unknown flags 0x%x", flags);
+    if (int rc = check_config(cfg_in, nullptr)) return rc;
+    if (int rc = check_dims(cfg_in->width, cfg_in->height)) return rc;
+    if (n_frames == 0) return SAR_OK;
+    const size_t nd = r->devices.size();
+    const bool shared = (flags & SAR_SEQ_SHARED_POINTS) != 0;
+    const size_t frame_u16 = (size_t)cfg_in->width * cfg_in->height * 4;
+
+    // every device renders whole frames with its own lanes: the decomposition of a frame is that
+    // of a one-device render_parallel (lib.rs:1058-1062)
+    std::vector<uint32_t> threads(nd), lanes(nd);
+    std::vector<uint64_t> jobs(nd);
+    std::vector<sar_config> cfgs(nd, *cfg_in);
+    for (size_t d = 0; d < nd; ++d) {
+        threads[d] = renderer_threads_for(r, d, jobs_per_thread);
+        jobs[d] = (uint64_t)threads[d] * jobs_per_thread;
+        lanes[d] = r->threads_per_device ? threads[d] : (uint32_t)(jobs[d] < renderer_lanes(r, d) ? jobs[d] : renderer_lanes(r, d));
+        cfgs[d].iterations = cfg_in->iterations / threads[d] / jobs_per_thread;
+        if (r->rts[d] && (r->rts[d]->w != cfg_in->width || r->rts[d]->h != cfg_in->height)) { sar_runtime_free(r->rts[d]); r->rts[d] = nullptr; }
+        if (!r->rts[d]) if (int rc = sar_runtime_new(cfg_in->width, cfg_in->height, r->devices[d], &r->rts[d])) return rc;
+        if (int rc = seq_prepare(r, d, *cfg_in, rgba_frames == nullptr)) return rc;
+        if (shared) {   // warm the one shared list of start points once (lib.rs:748-752)
+            seq_device &q = r->seq[d];
+            const size_t need = (size_t)jobs[d] * 3 * sizeof(double);
+            if (q.warm_cap < need) { cudaFree(q.warm); q.warm = nullptr; q.warm_cap = 0; SAR_CUDA(cudaMalloc((void **)&q.warm, need)); q.warm_cap = need; }
+            IterParams p;
+            make_iter_params(&cfgs[d], r->rts[d], p);
+            p.init = nullptr; p.seed = seed; p.first_job = 0; p.n_jobs = jobs[d];
+            launch_warm(p, q.warm, r->rts[d]->stream);
+            SAR_CUDA(cudaGetLastError());
+        }
+    }
+
+    auto finalize = [&](uint32_t g) -> int {     // wait for frame g's host copy, hand it to the caller
+        const size_t d = g % nd;
+        const int slot = (int)((g / nd) % 2);
+        SAR_CUDA(cudaSetDevice(r->devices[d]));
+        SAR_CUDA(cudaEventSynchronize(r->seq[d].copied[slot]));
+        if (cb) cb(user, g, rgba_frames ? rgba_frames + (size_t)g * frame_u16 : r->seq[d].stage[slot]);
+        return SAR_OK;
+    };
+
+    for (uint32_t f = 0; f < n_frames; ++f) {
+        const size_t d = f % nd;
+        const int slot = (int)((f / nd) % 2);
+        sar_runtime *rt = r->rts[d];
+        seq_device &q = r->seq[d];
+        SAR_CUDA(cudaSetDevice(rt->device));
+        sar_config cfg = cfgs[d];
+        cfg.angle = angles_rad[f];                                             // main.rs:497
+        if (f >= 2 * nd) SAR_CUDA(cudaStreamWaitEvent(rt->stream, q.copied[slot], 0));   // image slot free again
+        if (int rc = sar_runtime_reset_async(rt, nullptr)) return rc;           // Runtime::reset per frame, lib.rs:951
+        if (shared) {
+            if (int rc = render_launch(&cfg, rt, q.warm, 0, 0, jobs[d], lanes[d], rt->stream, true)) return rc;
+        } else {
+            // fresh start points per frame, like the reference: frame f takes the next jobs[d] points of the stream
+            if (int rc = render_launch(&cfg, rt, nullptr, seed, (uint64_t)f * jobs[d], jobs[d], lanes[d], rt->stream)) return rc;
+        }
+        if (int rc = sar_runtime_max_async(rt, 0, 0, nullptr)) return rc;
+        ColorParams cp;
+        make_color_params(&cfg, cp, 0, rt->h);
+        launch_colorize(cp, rt->fast, rt->rec, rt->scal, q.img[slot], nullptr, rt->stream);   // colorize, lib.rs:1080
+        SAR_CUDA(cudaGetLastError());
+        SAR_CUDA(cudaEventRecord(q.rendered[slot], rt->stream));
+        SAR_CUDA(cudaStreamWaitEvent(q.copy_stream, q.rendered[slot], 0));
+        uint16_t *dst = rgba_frames ? rgba_frames + (size_t)f * frame_u16 : q.stage[slot];
+        SAR_CUDA(cudaMemcpyAsync(dst, q.img[slot], q.img_bytes, cudaMemcpyDeviceToHost, q.copy_stream));
+        SAR_CUDA(cudaEventRecord(q.copied[slot], q.copy_stream));
+        if (f >= nd) if (int rc = finalize(f - (uint32_t)nd)) return rc;        // in order, one round behind
+    }
+    for (uint32_t g = n_frames > nd ? n_frames - (uint32_t)nd : 0; g < n_frames; ++g)
+        if (int rc = finalize(g)) return rc;
+    for (size_t d = 0; d < nd; ++d) {
+        SAR_CUDA(cudaSetDevice(r->devices[d]));
+        SAR_CUDA(cudaStreamSynchronize(r->rts[d]->stream));
+    }
+    return SAR_OK;
 }
 
 }  // extern "C"

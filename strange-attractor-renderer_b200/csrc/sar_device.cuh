@@ -57,6 +57,7 @@ struct IterParams {                   // everything the iterate kernel reads; li
     unsigned int job_key0;            // order key of job 0 (Runtime job counter)
     unsigned int W, H;
     unsigned int ct_kind;
+    unsigned int warmup;              // unrecorded steps before the recorded ones: 1000 (lib.rs:750), or 0 when `init` holds warmed states
 };
 
 struct ColorParams {
@@ -70,6 +71,8 @@ struct ColorParams {
 // launchers (sar_kernels.cu); every one bumps the launch counter
 void launch_reset(unsigned long long *fast, ulonglong2 *rec, Scalars *scal, size_t npix, cudaStream_t s);
 void launch_iterate(const IterParams &p, unsigned int lanes, cudaStream_t s);
+// the warm-up alone (lib.rs:748-752): start points -> states after p.warmup steps, out[3*job..]
+void launch_warm(const IterParams &p, double *out, cudaStream_t s);
 void launch_max(const unsigned long long *fast, const ulonglong2 *rec, Scalars *scal, size_t pix0, size_t npix, cudaStream_t s);
 void launch_colorize(const ColorParams &cp, const unsigned long long *fast, const ulonglong2 *rec, const Scalars *scal,
                      uint16_t *rgba_u16, float *rgba_f32, cudaStream_t s);

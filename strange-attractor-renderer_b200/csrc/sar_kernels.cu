@@ -309,7 +309,7 @@ iterate_kernel(const __grid_constant__ IterParams P)
             const unsigned long long g = 3ull * (P.first_job + job);
             x = seed_coord(P.seed, g); y = seed_coord(P.seed, g + 1); z = seed_coord(P.seed, g + 2);
         }
-        for (int w = 0; w < 1000; ++w) {                                      // lib.rs:750-752
+        for (unsigned int w = 0; w < P.warmup; ++w) {                         // lib.rs:750-752
             double nx, ny, nz;
             SAR_NEXT_POINT(P, x, y, z, nx, ny, nz);
             x = nx; y = ny; z = nz;
@@ -338,6 +338,34 @@ iterate_kernel(const __grid_constant__ IterParams P)
             if (key >= (uint32_t)(old >> 32) && key != 0u) record_win(&P, idx, key, job_inv, old, px, py, pz);
         }
     }
+}
+
+// The warm-up of render() on its own (lib.rs:748-752): used when a frame sweep shares one list of
+// start points, so that the 1000 unrecorded steps run once instead of once per frame.
+__global__ void __launch_bounds__(128)
+warm_kernel(const __grid_constant__ IterParams P, double *__restrict__ out)
+{
+    const unsigned long long job = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (job >= P.n_jobs) return;
+    double x, y, z;
+    if (P.init != nullptr) {
+        x = P.init[3 * job + 0]; y = P.init[3 * job + 1]; z = P.init[3 * job + 2];
+    } else {
+        const unsigned long long g = 3ull * (P.first_job + job);
+        x = seed_coord(P.seed, g); y = seed_coord(P.seed, g + 1); z = seed_coord(P.seed, g + 2);
+    }
+    for (unsigned int w = 0; w < P.warmup; ++w) {
+        double nx, ny, nz;
+        SAR_NEXT_POINT(P, x, y, z, nx, ny, nz);
+        x = nx; y = ny; z = nz;
+    }
+    out[3 * job + 0] = x; out[3 * job + 1] = y; out[3 * job + 2] = z;
+}
+void launch_warm(const IterParams &p, double *out, cudaStream_t s)
+{
+    if (p.n_jobs == 0) return;
+    warm_kernel<<<(unsigned int)((p.n_jobs + 127) / 128), 128, 0, s>>>(p, out);
+    ++g_launches;
 }
 
 static std::atomic<int> g_defer{-1};

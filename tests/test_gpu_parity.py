@@ -282,3 +282,51 @@ def test_full_size_conservation_cfg2(S):
     img2 = S.render_parallel(r, cfg, 1, seed=1234)
     assert np.array_equal(img1, img2)
     r.shutdown()
+
+
+def test_render_parallel_auto_threads_with_cli_default_jobs(S, oracle):
+    """jobs_per_thread = 12 is the CLI default (main.rs:305).  In auto mode the renderer keeps the
+    number of jobs at its lane count: num_threads = lanes / 12, and the decomposition is the
+    reference's for that num_threads (lib.rs:1058-1062)."""
+    cfg = _small(S.Config.poisson_saturne(), 256, 192, 30_000_000)
+    r = S.ParallelRenderer.new()
+    lanes, n12 = r.num_threads(), r.num_threads(12)
+    assert n12 == (lanes // 12) // 32 * 32 and n12 * 12 <= lanes
+    img = S.render_parallel(r, cfg, 12, seed=99)
+    ocfg = cfg.to_pod()
+    ocfg.iterations = 30_000_000 // n12 // 12
+    ort = oracle.Runtime(256, 192)
+    oracle.render_jobs(ocfg, ort, oracle.seed_points(99, 0, n12 * 12))
+    _assert_state_equal(r.runtime().download(), ort)
+    _assert_image_close(img, None, oracle.colorize(ocfg, ort), None)
+    r.shutdown()
+
+
+def test_render_sequence_frames_equal_render_parallel(S, oracle):
+    """The binary's frame loop (main.rs:496-512): every frame of a sequence equals render_parallel
+    of that angle on the same start points — fresh points per frame by default, one shared list
+    (warm-up run once) with shared_points=True."""
+    cfg = _small(S.Config.solar_sail(), 200, 220, 3_000_000)
+    angles = S.angle_iter(0.0, 90.0, 30.0)                       # 0, 30, 60 degrees -> radians
+    assert np.allclose(angles, [0.0, math.pi / 6, math.pi / 3]) and S.angle_iter(220.0, 220.0, 1.0) == [220.0]
+    r = S.ParallelRenderer.new(threads=128)
+    jobs = 128 * 2
+    fresh = S.render_sequence(r, cfg, angles, 2, seed=5)
+    shared = S.render_sequence(r, cfg, angles, 2, seed=5, shared_points=True)
+    seen = []
+    S.render_sequence(r, cfg, angles, 2, seed=5, callback=lambda f, im: seen.append((f, im.copy())))
+    assert [f for f, _ in seen] == [0, 1, 2]
+    for f, a in enumerate(angles):
+        cfg.angle = a
+        want_fresh = S.render_parallel(r, cfg, 2, initial_points=S.seed_points(5, f * jobs, jobs))
+        want_shared = S.render_parallel(r, cfg, 2, initial_points=S.seed_points(5, 0, jobs))
+        assert np.array_equal(fresh[f], want_fresh)
+        assert np.array_equal(shared[f], want_shared)
+        assert np.array_equal(seen[f][1], want_fresh)
+    # and one frame against the oracle
+    ocfg = cfg.to_pod()
+    ocfg.iterations = 3_000_000 // 128 // 2
+    ort = oracle.Runtime(200, 220)
+    oracle.render_jobs(ocfg, ort, oracle.seed_points(5, 0, jobs))
+    _assert_image_close(shared[2], None, oracle.colorize(ocfg, ort), None)
+    r.shutdown()

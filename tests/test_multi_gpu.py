@@ -26,3 +26,32 @@ def test_two_rank_frame_equals_single_gpu(preset):
            "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tools", "dist_check.py"), preset]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0 and "DIST_CHECK_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_in_process_two_device_renderer_equals_one_device():
+    """ParallelRenderer over two devices in ONE process (frames' jobs split by device, merged by
+    peer copy) gives the image and buffers of one device running the same num_threads."""
+    if _gpu_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import numpy as np
+
+    import strange_attractor_renderer_b200 as S
+
+    cfg = S.Config.solar_sail()
+    cfg.width, cfg.height, cfg.iterations, cfg.angle = 300, 333, 20_000_000, 0.7
+    two = S.ParallelRenderer.new(devices=[0, 1], threads=512)
+    one = S.ParallelRenderer.new(devices=[0], threads=1024)
+    assert two.num_threads() == one.num_threads() == 1024
+    a = S.render_parallel(two, cfg, 3, seed=31)
+    b = S.render_parallel(one, cfg, 3, seed=31)
+    assert np.array_equal(a, b)
+    sa, sb = two.runtime().download(), one.runtime().download()
+    for x, y in zip(sa[:3], sb[:3]):
+        assert np.array_equal(x.view(np.uint8), y.view(np.uint8))
+    # a sequence round-robins frames over the devices; frames do not depend on which device ran them
+    angles = S.angle_iter(0.0, 40.0, 10.0)
+    fa = S.render_sequence(two, cfg, angles, 2, seed=9, shared_points=True)
+    fb = S.render_sequence(S.ParallelRenderer.new(devices=[1], threads=512), cfg, angles, 2, seed=9, shared_points=True)
+    assert np.array_equal(fa, fb)
+    two.shutdown()
+    one.shutdown()
