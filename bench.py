@@ -63,7 +63,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -157,9 +157,19 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("no CUDA device: the render path has no CPU fallback")
     torch.cuda.set_device(local)
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"       # keep stdout to the one JSON line (NCCL prints its version banner there)
     group = D.init_process_group(world, rank, local) if world > 1 else None
 
-    cfg = S.Config.poisson_saturne()
+    global WIDTH, HEIGHT, ITERATIONS, WORKLOAD
+    if args.size or args.iterations_per_gpu or args.preset != "poisson-saturne":      # other BASELINE configs (profiles/, not the default line)
+        if args.size:
+            WIDTH, HEIGHT = (int(v) for v in args.size.lower().split("x"))
+        ITERATIONS = int(float(args.iterations_per_gpu)) if args.iterations_per_gpu else ITERATIONS
+        WORKLOAD = f"{args.preset}, {ITERATIONS:.3g} iterations per GPU, {WIDTH}x{HEIGHT} (non-default)"
+    cfg = S.Config.poisson_saturne() if args.preset == "poisson-saturne" else S.Config.solar_sail()
+    if args.preset != "poisson-saturne":
+        cfg.angle = 3.839724354387525   # 220 degrees (BASELINE configs[2])
     cfg.width, cfg.height, cfg.transparent = WIDTH, HEIGHT, False
     lanes = args.lanes or 0
     jpt = args.jobs_per_thread
@@ -193,12 +203,13 @@ def run_ours(args):
         return total   # ms
 
     # ---- value: device-resident frame -------------------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                          # sampled from the warm-up steps (same load) through the timed region
+        time.sleep(0.3)
     for _ in range(args.warmup):
         frame.step_device(sp)
     sync_all()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     launches0 = L.sar_launch_count()
     ms_total = timed_steps(lambda: frame.step_device(sp), args.steps)
     launches = int(L.sar_launch_count() - launches0)
@@ -260,7 +271,7 @@ def run_ours(args):
                          "note": "f64 issue binds before HBM here: ~91 non-fusable DP instructions per iteration (DESIGN.md §5)"},
         }
     frame.close()
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not (args.size or args.iterations_per_gpu or args.preset != "poisson-saturne"):
         threads = os.cpu_count() or 8
         iters = cpu_sample_size(threads)
         v, dt = cpu_render_parallel(iters, threads)
@@ -282,6 +293,9 @@ def main():
     ap.add_argument("--lanes", type=int, default=0, help="trajectory lanes per GPU (0 = library default, SM count x 768)")
     ap.add_argument("--jobs-per-thread", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--preset", choices=["poisson-saturne", "solar-sail"], default="poisson-saturne")
+    ap.add_argument("--size", default="", help="WxH override (default 2048x2048)")
+    ap.add_argument("--iterations-per-gpu", default="", help="override of 1e9")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
