@@ -10,6 +10,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -57,6 +58,8 @@ struct sar_runtime {
     Scalars *scal = nullptr;
     cudaStream_t stream = nullptr;
     uint64_t job_base = 0;
+    uint32_t host_max = 0;           // Runtime.max as last read back / forced by the host ...
+    bool host_max_valid = false;     // ... valid until the accumulators change
     int sm_count = 148;
     // lazily allocated scratch
     double *d_init = nullptr; size_t d_init_cap = 0;
@@ -123,6 +126,26 @@ static int check_config(const sar_config *cfg, const sar_runtime *rt)
     return SAR_OK;
 }
 
+// ln(n), n < LNLUT_LEN, from the host libm (see ColorParams); one table per device, built once.
+static const unsigned int LNLUT_LEN = 1u << 20;
+static double *g_lnlut[64] = {nullptr};
+static std::mutex g_lnlut_mutex;
+static int ensure_lnlut(int device)
+{
+    if (device < 0 || device >= 64) return fail(SAR_ERR_INVALID, "device ordinal %d out of range", device);
+    std::lock_guard<std::mutex> lock(g_lnlut_mutex);
+    if (g_lnlut[device]) return SAR_OK;
+    std::vector<double> h(LNLUT_LEN);
+    for (unsigned int n = 0; n < LNLUT_LEN; ++n) h[n] = std::log((double)n);     // f64::ln, lib.rs:860
+    SAR_CUDA(cudaSetDevice(device));
+    double *d = nullptr;
+    SAR_CUDA(cudaMalloc((void **)&d, LNLUT_LEN * sizeof(double)));
+    SAR_CUDA(cudaMemcpy(d, h.data(), LNLUT_LEN * sizeof(double), cudaMemcpyHostToDevice));
+    g_lnlut[device] = d;
+    return SAR_OK;
+}
+
+
 // ---------------------------------------------------------------------------------------------
 // Config → kernel constants.  Host libm sin/cos so that the oracle and the device consume the
 // same f64 values (the reference calls the same glibc functions through Rust's f64::sin/cos).
@@ -161,9 +184,16 @@ static void make_iter_params(const sar_config *cfg, sar_runtime *rt, IterParams 
     p.warmup = SAR_WARMUP_ITERATIONS;                                            // lib.rs:750
 }
 
-static void make_color_params(const sar_config *cfg, ColorParams &c, uint32_t row0, uint32_t rows)
+static void make_color_params(const sar_config *cfg, const sar_runtime *rt, ColorParams &c, uint32_t row0, uint32_t rows,
+                              const uint32_t *host_max = nullptr)
 {
     memset(&c, 0, sizeof c);
+    c.lnlut = g_lnlut[rt->device];
+    c.lnlut_len = c.lnlut ? LNLUT_LEN : 0u;
+    if (host_max) {                                              // blocking callers read max back: exact ln(max+1) from the host libm
+        c.host_lnmax_valid = 1u;
+        c.ln_max1_host = std::log((double)(uint32_t)(*host_max + 1u));
+    }
     for (uint32_t i = 0; i < cfg->palette_len; ++i)
         for (int k = 0; k < 3; ++k) c.pal[i][k] = cfg->palette_rgb[i][k];
     for (int k = 0; k < 3; ++k) c.pal[cfg->palette_len][k] = cfg->palette_rgb[cfg->palette_len - 1][k];  // lib.rs:418
@@ -292,6 +322,7 @@ int sar_runtime_new(uint32_t width, uint32_t height, int device, sar_runtime **o
     int ndev = 0;
     SAR_CUDA(cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev) return fail(SAR_ERR_CUDA, "CUDA device %d not available (%d visible)", device, ndev);
+    if (int rc = ensure_lnlut(device)) return rc;
     SAR_CUDA(cudaSetDevice(device));
     sar_runtime *rt = new (std::nothrow) sar_runtime();
     if (!rt) return fail(SAR_ERR_NOMEM, "host allocation failed");
@@ -331,6 +362,7 @@ int sar_runtime_reset_async(sar_runtime *rt, void *stream)
     launch_reset(rt->fast, rt->rec, rt->scal, rt->npix, pick(rt, stream));
     SAR_CUDA(cudaGetLastError());
     rt->job_base = 0;
+    rt->host_max_valid = false;
     return SAR_OK;
 }
 int sar_runtime_reset(sar_runtime *rt)
@@ -406,6 +438,7 @@ int sar_runtime_upload(sar_runtime *rt, const uint32_t *count, const double *ste
     launch_pack(rt->fast, rt->rec, rt->scal, n, (const uint32_t *)(base + oc), (const double *)(base + os), (const float *)(base + oz), rt->stream);
     SAR_CUDA(cudaGetLastError());
     SAR_CUDA(cudaStreamSynchronize(rt->stream));
+    rt->host_max_valid = false;
     if (rt->job_base == 0) rt->job_base = 1;   // uploaded records carry job key 0: they keep every future tie
     return SAR_OK;
 }
@@ -432,6 +465,7 @@ int sar_runtime_merge(sar_runtime *dst, const sar_runtime *src)
     }
     launch_merge(dst->fast, dst->rec, dst->scal, sfast, srec, sscal, dst->npix, dst->stream);
     SAR_CUDA(cudaGetLastError());
+    dst->host_max_valid = false;
     SAR_CUDA(cudaStreamSynchronize(dst->stream));
     if (src->job_base > dst->job_base) dst->job_base = src->job_base;
     return SAR_OK;
@@ -452,6 +486,7 @@ static int render_launch(const sar_config *cfg, sar_runtime *rt, const double *d
     p.job_key0 = key0 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (unsigned int)key0;
     launch_iterate(p, threads ? threads : default_lanes(rt), s);
     SAR_CUDA(cudaGetLastError());
+    rt->host_max_valid = false;
     rt->job_base = key0 + n_jobs;
     return SAR_OK;
 }
@@ -514,6 +549,7 @@ int sar_runtime_max_async(sar_runtime *rt, uint32_t row0, uint32_t rows, void *s
     SAR_CUDA(cudaMemcpyAsync(&rt->scal->max, init, sizeof init, cudaMemcpyHostToDevice, s));
     launch_max(rt->fast, rt->rec, rt->scal, (size_t)row0 * rt->w, (size_t)rows * rt->w, s);
     SAR_CUDA(cudaGetLastError());
+    rt->host_max_valid = false;
     return SAR_OK;
 }
 int sar_runtime_get_max(sar_runtime *rt, uint32_t *max_out, void *stream)
@@ -523,6 +559,7 @@ int sar_runtime_get_max(sar_runtime *rt, uint32_t *max_out, void *stream)
     cudaStream_t s = pick(rt, stream);
     SAR_CUDA(cudaMemcpyAsync(max_out, &rt->scal->max, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     SAR_CUDA(cudaStreamSynchronize(s));
+    rt->host_max = *max_out; rt->host_max_valid = true;
     return SAR_OK;
 }
 int sar_runtime_set_max(sar_runtime *rt, uint32_t max, void *stream)
@@ -532,6 +569,7 @@ int sar_runtime_set_max(sar_runtime *rt, uint32_t max, void *stream)
     cudaStream_t s = pick(rt, stream);
     SAR_CUDA(cudaMemcpyAsync(&rt->scal->max, &max, sizeof(uint32_t), cudaMemcpyHostToDevice, s));
     SAR_CUDA(cudaStreamSynchronize(s));
+    rt->host_max = max; rt->host_max_valid = true;
     return SAR_OK;
 }
 
@@ -544,7 +582,7 @@ int sar_colorize_rows_async(const sar_config *cfg, sar_runtime *rt, uint32_t row
     if (dst && (dst->w != rt->w || dst->h != rt->h)) return fail(SAR_ERR_DIMS, "peer image is %ux%u, runtime %ux%u", dst->w, dst->h, rt->w, rt->h);
     SAR_CUDA(cudaSetDevice(rt->device));
     ColorParams cp;
-    make_color_params(cfg, cp, row0, rows);
+    make_color_params(cfg, rt, cp, row0, rows, rt->host_max_valid ? &rt->host_max : nullptr);
     launch_colorize(cp, rt->fast, rt->rec, rt->scal, dst ? dst->image : rt->image, nullptr, pick(rt, stream));
     SAR_CUDA(cudaGetLastError());
     return SAR_OK;
@@ -576,8 +614,10 @@ int sar_colorize(const sar_config *cfg, const sar_runtime *crt, uint16_t *rgba_u
         if (int rc = ensure_scratch(rt, rt->npix * 4 * sizeof(float))) return rc;
         d_f32 = (float *)rt->d_scratch;
     }
+    uint32_t host_max = 0;
+    if (int rc = sar_runtime_get_max(rt, &host_max, nullptr)) return rc;
     ColorParams cp;
-    make_color_params(cfg, cp, 0, rt->h);
+    make_color_params(cfg, rt, cp, 0, rt->h, &host_max);
     launch_colorize(cp, rt->fast, rt->rec, rt->scal, rt->image, d_f32, rt->stream);
     SAR_CUDA(cudaGetLastError());
     if (rgba_u16) SAR_CUDA(cudaMemcpyAsync(rgba_u16, rt->image, rt->npix * 4 * sizeof(uint16_t), cudaMemcpyDeviceToHost, rt->stream));
@@ -670,6 +710,7 @@ int sar_runtime_merge_peers_async(sar_runtime *rt, sar_peer *const *peers, int n
     SAR_CUDA(cudaSetDevice(rt->device));
     launch_merge_peers(rt->fast, rt->rec, rt->scal, pl, (size_t)row0 * rt->w, (size_t)rows * rt->w, pick(rt, stream));
     SAR_CUDA(cudaGetLastError());
+    rt->host_max_valid = false;
     return SAR_OK;
 }
 
@@ -817,7 +858,12 @@ int sar_render_parallel(sar_renderer *r, const sar_config *cfg_in, uint64_t jobs
     }
     rt0->job_base = total_jobs;
     if (int rc = sar_runtime_max_async(rt0, 0, 0, nullptr)) return rc;
-    if (int rc = sar_colorize_rows_async(&cfg, rt0, 0, 0, nullptr, nullptr)) return rc;   // lib.rs:1080
+    uint32_t host_max = 0;
+    if (int rc = sar_runtime_get_max(rt0, &host_max, nullptr)) return rc;
+    ColorParams cp;
+    make_color_params(&cfg, rt0, cp, 0, rt0->h, &host_max);
+    launch_colorize(cp, rt0->fast, rt0->rec, rt0->scal, rt0->image, nullptr, rt0->stream);   // lib.rs:1080
+    SAR_CUDA(cudaGetLastError());
     return sar_runtime_image_download(rt0, 0, 0, rgba_u16, nullptr);
 }
 
@@ -912,7 +958,7 @@ int sar_render_sequence(sar_renderer *r, const sar_config *cfg_in, const double 
         }
         if (int rc = sar_runtime_max_async(rt, 0, 0, nullptr)) return rc;
         ColorParams cp;
-        make_color_params(&cfg, cp, 0, rt->h);
+        make_color_params(&cfg, rt, cp, 0, rt->h);
         launch_colorize(cp, rt->fast, rt->rec, rt->scal, q.img[slot], nullptr, rt->stream);   // colorize, lib.rs:1080
         SAR_CUDA(cudaGetLastError());
         SAR_CUDA(cudaEventRecord(q.rendered[slot], rt->stream));

@@ -66,6 +66,13 @@ struct ColorParams {
     double bright_offset, bright_factor;
     unsigned int palette_len, transparent, render_kind;
     unsigned int W, H, row0, rows;
+    // ln(n) for n < lnlut_len, computed on the HOST with the platform libm — the function the
+    // reference's f64::ln resolves to — so that `ln(count+1)/ln(max+1)` (lib.rs:860) carries the
+    // same bits as a CPU run; larger arguments fall back to the device log (<= 1 ulp).
+    const double *lnlut;
+    unsigned int lnlut_len;
+    unsigned int host_lnmax_valid;    // ln_max1_host was computed on the host from the current max
+    double ln_max1_host;
 };
 
 // launchers (sar_kernels.cu); every one bumps the launch counter

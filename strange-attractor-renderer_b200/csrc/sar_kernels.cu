@@ -508,7 +508,8 @@ colorize_kernel(const __grid_constant__ ColorParams C, const unsigned long long 
     __shared__ double s_lnmax;
     __shared__ float s_zmax, s_zmin;
     if (threadIdx.x == 0) {
-        s_lnmax = log((double)(uint32_t)(scal->max + 1u));      // f64::from(runtime.max + 1), lib.rs:860
+        const uint32_t m1 = scal->max + 1u;                     // f64::from(runtime.max + 1), lib.rs:860
+        s_lnmax = C.host_lnmax_valid ? C.ln_max1_host : (m1 < C.lnlut_len ? C.lnlut[m1] : log((double)m1));
         s_zmax = __uint_as_float(zbits_from_key(scal->zmax_key));
         s_zmin = __uint_as_float(zbits_from_key(scal->zmin_key));
     }
@@ -533,7 +534,9 @@ colorize_kernel(const __grid_constant__ ColorParams C, const unsigned long long 
             const double g = __dsqrt_rn(__dadd_rn(__dmul_rn(C.pal[n + 1][1], t), __dmul_rn(C.pal[n][1], t1)));
             const double b = __dsqrt_rn(__dadd_rn(__dmul_rn(C.pal[n + 1][2], t), __dmul_rn(C.pal[n][2], t1)));
             const uint32_t cnt = pixel_count(fast, scal, p);
-            const double factor = __ddiv_rn(log((double)(uint32_t)(cnt + 1u)), s_lnmax);   // lib.rs:860
+            const uint32_t c1 = cnt + 1u;
+            const double lnc = c1 < C.lnlut_len ? __ldg(C.lnlut + c1) : (cnt == scal->max ? s_lnmax : log((double)c1));
+            const double factor = __ddiv_rn(lnc, s_lnmax);       // lib.rs:860
             const double vr = __dmul_rn(__dadd_rn(__dmul_rn(r, factor), C.bright_offset), C.bright_factor);
             const double vg = __dmul_rn(__dadd_rn(__dmul_rn(g, factor), C.bright_offset), C.bright_factor);
             const double vb = __dmul_rn(__dadd_rn(__dmul_rn(b, factor), C.bright_offset), C.bright_factor);

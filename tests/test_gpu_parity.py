@@ -3,7 +3,8 @@
 Bar (BASELINE.json north_star): count buffer bit-exact; colour within 1e-5 relative.  This
 build is stricter: zbuf (f32) and steps (f64) are bit-exact too, because z ties resolve to the
 earlier render() call / earlier iteration exactly as in a sequential reference run, and the u16
-image may differ from the oracle's by at most 1 LSB (CUDA's log() vs glibc's, <= 1 ulp).
+image is bit-exact as well: ln(count+1) and ln(max+1) come from a host-libm table (counts below
+2^20) or from the host directly (max), every other colour operation is exact IEEE arithmetic.
 """
 import ctypes as C
 import math
@@ -45,8 +46,12 @@ def _assert_state_equal(gpu_state, ort):
         f"steps differs in {(steps != ort.steps).sum()} pixels"
 
 
-def _assert_image_close(img, f32, oimg, of64):
+def _assert_image_close(img, f32, oimg, of64, exact=True):
+    """u16 image: bit-exact (ln comes from the host libm table); with exact=False
+    (counts beyond the table on a path that cannot read max back) at most 1 LSB in < 1e-4 of values."""
     d = np.abs(img.astype(np.int32) - oimg.astype(np.int32))
+    if exact:
+        assert d.max() == 0, f"u16 image differs in {(d > 0).sum()} values (max {d.max()} LSB)"
     assert d.max() <= 1, f"u16 image differs by {d.max()} LSB"
     assert (d > 0).mean() < 1e-4, f"{(d > 0).sum()} u16 channel values differ by 1 LSB"
     if f32 is not None:
