@@ -290,7 +290,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--lanes", type=int, default=0, help="trajectory lanes per GPU (0 = library default, SM count x 768)")
+    ap.add_argument("--lanes", type=int, default=0, help="trajectory lanes per GPU (0 = library default, SM count x 896)")
     ap.add_argument("--jobs-per-thread", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--preset", choices=["poisson-saturne", "solar-sail"], default="poisson-saturne")

@@ -102,7 +102,7 @@ typedef struct sar_renderer sar_renderer;  /* ParallelRenderer, lib.rs:908-915 *
 uint32_t    sar_abi_version(void);
 const char *sar_last_error(void);            /* thread-local, never NULL */
 int         sar_device_count(int *count);    /* SAR_ERR_CUDA when no driver/device */
-/* Default number of concurrent trajectory lanes on `device` (SM count × 768):
+/* Default number of concurrent trajectory lanes on `device` (SM count × 896):
  * the GPU's answer to available_parallelism(), lib.rs:920-922. */
 int         sar_default_threads(int device, uint32_t *threads);
 /* Tuning knobs that never change results.  "defer": depth (0..4) of the iterate

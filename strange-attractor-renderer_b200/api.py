@@ -303,7 +303,7 @@ def colorize(config, runtime: Runtime, want_f32: bool = False):
 # ---- ParallelRenderer / render_parallel (lib.rs:906-1082) -------------------------------
 class ParallelRenderer:
     """`threads` plays available_parallelism() (lib.rs:920): concurrent trajectory lanes per
-    device; 0 = library default (sar_default_threads: SM count × 768)."""
+    device; 0 = library default (sar_default_threads: SM count × 896)."""
 
     def __init__(self, devices: Optional[Sequence[int]] = None, threads: int = 0):
         self._h = C.c_void_p()

@@ -49,6 +49,8 @@ struct sar_runtime {
     int device = 0;
     uint32_t w = 0, h = 0;
     size_t npix = 0;
+    size_t nslots = 0;               // power of two >= npix: size of the scrambled `fast` array
+    SlotMap slots = {1u, 0u};
     // one device allocation: rec | fast | image | scal   (so one IPC handle exports it all)
     void *block = nullptr;
     size_t block_bytes = 0;
@@ -70,6 +72,7 @@ struct sar_runtime {
 struct sar_peer {
     int local_device = 0;
     uint32_t w = 0, h = 0;
+    SlotMap slots = {1u, 0u};
     void *block = nullptr;           // cudaIpcOpenMemHandle mapping (or a borrowed in-process pointer)
     bool ipc = false;
     ulonglong2 *rec = nullptr;
@@ -96,10 +99,26 @@ struct sar_renderer {
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+static size_t slots_for(size_t npix)
+{
+    size_t p = 1;
+    while (p < npix) p <<= 1;
+    return p;
+}
+
+// scramble the fast array only while the scrambled working set still fits the L2 comfortably
+static SlotMap slotmap_for(size_t npix)
+{
+    SlotMap m;
+    m.mask = (uint32_t)(slots_for(npix) - 1);
+    m.mult = npix <= ((size_t)1 << 23) ? SLOT_SCRAMBLE : 1u;
+    return m;
+}
+
 static void layout(size_t npix, size_t &off_fast, size_t &off_image, size_t &off_scal, size_t &total)
 {
     off_fast = align_up(npix * sizeof(ulonglong2), 256);
-    off_image = off_fast + align_up(npix * sizeof(unsigned long long), 256);
+    off_image = off_fast + align_up(slots_for(npix) * sizeof(unsigned long long), 256);
     off_scal = off_image + align_up(npix * 4 * sizeof(uint16_t), 256);
     total = off_scal + 256;
 }
@@ -180,6 +199,7 @@ static void make_iter_params(const sar_config *cfg, sar_runtime *rt, IterParams 
     p.ct_offset = cfg->ct_offset; p.ct_factor = cfg->ct_factor;
     p.fast = rt->fast; p.rec = rt->rec; p.scal = rt->scal;
     p.W = cfg->width; p.H = cfg->height; p.ct_kind = cfg->ct_kind;
+    p.slots = rt->slots;
     p.iterations = cfg->iterations;
     p.warmup = SAR_WARMUP_ITERATIONS;                                            // lib.rs:750
 }
@@ -188,6 +208,7 @@ static void make_color_params(const sar_config *cfg, const sar_runtime *rt, Colo
                               const uint32_t *host_max = nullptr)
 {
     memset(&c, 0, sizeof c);
+    c.slots = rt->slots;
     c.lnlut = g_lnlut[rt->device];
     c.lnlut_len = c.lnlut ? LNLUT_LEN : 0u;
     if (host_max) {                                              // blocking callers read max back: exact ln(max+1) from the host libm
@@ -203,9 +224,9 @@ static void make_color_params(const sar_config *cfg, const sar_runtime *rt, Colo
     c.W = cfg->width; c.H = cfg->height; c.row0 = row0; c.rows = rows;
 }
 
-// Concurrent trajectory lanes per SM: 6 warps per scheduler is where the L2 atomic-with-return
+// Concurrent trajectory lanes per SM: 7 warps per scheduler is where the L2 atomic-with-return
 // rate saturates (profiles/r1_sweep.md); more lanes only add 1000-step warm-ups (lib.rs:750).
-static const uint32_t LANES_PER_SM = 768u;
+static const uint32_t LANES_PER_SM = 896u;
 static uint32_t default_lanes(const sar_runtime *rt) { return (uint32_t)rt->sm_count * LANES_PER_SM; }
 
 // ---------------------------------------------------------------------------------------------
@@ -223,7 +244,7 @@ int sar_set_option(const char *name, int64_t value)
         return SAR_OK;
     }
     if (strcmp(name, "diagnostic_mode") == 0) {
-        if (!set_mode((int)value)) return fail(SAR_ERR_INVALID, "diagnostic_mode must be in 0..6");
+        if (!set_mode((int)value)) return fail(SAR_ERR_INVALID, "diagnostic_mode must be in 0..7");
         return SAR_OK;
     }
     return fail(SAR_ERR_INVALID, "unknown option '%s'", name);
@@ -327,6 +348,7 @@ int sar_runtime_new(uint32_t width, uint32_t height, int device, sar_runtime **o
     sar_runtime *rt = new (std::nothrow) sar_runtime();
     if (!rt) return fail(SAR_ERR_NOMEM, "host allocation failed");
     rt->device = device; rt->w = width; rt->h = height; rt->npix = (size_t)width * height;
+    rt->nslots = slots_for(rt->npix); rt->slots = slotmap_for(rt->npix);
     size_t of, oi, os, total;
     layout(rt->npix, of, oi, os, total);
     cudaError_t e = cudaMalloc(&rt->block, total);
@@ -359,7 +381,7 @@ int sar_runtime_reset_async(sar_runtime *rt, void *stream)
 {
     if (!rt) return fail(SAR_ERR_INVALID, "runtime is NULL");
     SAR_CUDA(cudaSetDevice(rt->device));
-    launch_reset(rt->fast, rt->rec, rt->scal, rt->npix, pick(rt, stream));
+    launch_reset(rt->fast, rt->rec, rt->scal, rt->npix, rt->nslots, pick(rt, stream));
     SAR_CUDA(cudaGetLastError());
     rt->job_base = 0;
     rt->host_max_valid = false;
@@ -411,7 +433,7 @@ int sar_runtime_download(const sar_runtime *crt, uint32_t *count, double *steps,
     const size_t oc = 0, os = align_up(n * 4, 256), oz = os + align_up(n * 8, 256), total = oz + align_up(n * 4, 256);
     if (int rc = ensure_scratch(rt, total)) return rc;
     char *base = (char *)rt->d_scratch;
-    launch_unpack(rt->fast, rt->rec, rt->scal, n, (uint32_t *)(base + oc), (double *)(base + os), (float *)(base + oz), rt->stream);
+    launch_unpack(rt->fast, rt->rec, rt->scal, n, rt->slots, (uint32_t *)(base + oc), (double *)(base + os), (float *)(base + oz), rt->stream);
     SAR_CUDA(cudaGetLastError());
     if (count) SAR_CUDA(cudaMemcpyAsync(count, base + oc, n * 4, cudaMemcpyDeviceToHost, rt->stream));
     if (steps) SAR_CUDA(cudaMemcpyAsync(steps, base + os, n * 8, cudaMemcpyDeviceToHost, rt->stream));
@@ -435,7 +457,7 @@ int sar_runtime_upload(sar_runtime *rt, const uint32_t *count, const double *ste
     SAR_CUDA(cudaMemcpyAsync(base + oc, count, n * 4, cudaMemcpyHostToDevice, rt->stream));
     SAR_CUDA(cudaMemcpyAsync(base + os, steps, n * 8, cudaMemcpyHostToDevice, rt->stream));
     SAR_CUDA(cudaMemcpyAsync(base + oz, zbuf, n * 4, cudaMemcpyHostToDevice, rt->stream));
-    launch_pack(rt->fast, rt->rec, rt->scal, n, (const uint32_t *)(base + oc), (const double *)(base + os), (const float *)(base + oz), rt->stream);
+    launch_pack(rt->fast, rt->rec, rt->scal, n, rt->slots, (const uint32_t *)(base + oc), (const double *)(base + os), (const float *)(base + oz), rt->stream);
     SAR_CUDA(cudaGetLastError());
     SAR_CUDA(cudaStreamSynchronize(rt->stream));
     rt->host_max_valid = false;
@@ -463,7 +485,7 @@ int sar_runtime_merge(sar_runtime *dst, const sar_runtime *src)
         sfast = (const unsigned long long *)((char *)dst->d_scratch + of);
         sscal = (const Scalars *)((char *)dst->d_scratch + os);
     }
-    launch_merge(dst->fast, dst->rec, dst->scal, sfast, srec, sscal, dst->npix, dst->stream);
+    launch_merge(dst->fast, dst->rec, dst->scal, sfast, srec, sscal, dst->npix, dst->slots, dst->stream);
     SAR_CUDA(cudaGetLastError());
     dst->host_max_valid = false;
     SAR_CUDA(cudaStreamSynchronize(dst->stream));
@@ -547,7 +569,7 @@ int sar_runtime_max_async(sar_runtime *rt, uint32_t row0, uint32_t rows, void *s
     cudaStream_t s = pick(rt, stream);
     const unsigned int init[3] = {0u, ZKEY_ZERO, ZKEY_FLT_MAX};   // max, zmax_key, zmin_key (fold seed lib.rs:882)
     SAR_CUDA(cudaMemcpyAsync(&rt->scal->max, init, sizeof init, cudaMemcpyHostToDevice, s));
-    launch_max(rt->fast, rt->rec, rt->scal, (size_t)row0 * rt->w, (size_t)rows * rt->w, s);
+    launch_max(rt->fast, rt->rec, rt->scal, (size_t)row0 * rt->w, (size_t)rows * rt->w, rt->slots, s);
     SAR_CUDA(cudaGetLastError());
     rt->host_max_valid = false;
     return SAR_OK;
@@ -661,6 +683,7 @@ static void peer_view(sar_peer *p, void *block, uint32_t w, uint32_t h)
     size_t of, oi, os, total;
     layout((size_t)w * h, of, oi, os, total);
     p->w = w; p->h = h; p->block = block;
+    p->slots = slotmap_for((size_t)w * h);
     p->rec = (ulonglong2 *)block;
     p->fast = (unsigned long long *)((char *)block + of);
     p->image = (uint16_t *)((char *)block + oi);
@@ -708,7 +731,7 @@ int sar_runtime_merge_peers_async(sar_runtime *rt, sar_peer *const *peers, int n
         pl.fast[i] = peers[i]->fast; pl.rec[i] = peers[i]->rec; pl.scal[i] = peers[i]->scal;
     }
     SAR_CUDA(cudaSetDevice(rt->device));
-    launch_merge_peers(rt->fast, rt->rec, rt->scal, pl, (size_t)row0 * rt->w, (size_t)rows * rt->w, pick(rt, stream));
+    launch_merge_peers(rt->fast, rt->rec, rt->scal, pl, (size_t)row0 * rt->w, (size_t)rows * rt->w, rt->slots, pick(rt, stream));
     SAR_CUDA(cudaGetLastError());
     rt->host_max_valid = false;
     return SAR_OK;

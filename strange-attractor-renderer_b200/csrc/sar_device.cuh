@@ -3,7 +3,14 @@
 // HBM layout of one Runtime (reference: Runtime{count,steps,zbuf,max}, lib.rs:631-646),
 // W*H pixels, row-major idx = y*W + x exactly like image::ImageBuffer:
 //
-//   fast[idx]  u64   bits 31..0  = count (u32, lib.rs:633)
+//   fast[slot(idx)]  u64   (slot = (idx * M) & (P-1), P = next power of two >= W*H.  For images up
+//                    to 2^23 pixels M = 0x9E3779B1: a bijective scramble, so that the pixels
+//                    sharing a 32-byte sector are far apart in the image and a dense region does
+//                    not serialise its atomics on a few sectors (+15 % on the atomic ceiling at
+//                    2048^2).  Larger images keep M = 1 (natural order): scrambling would spread
+//                    the ~20 % live pixels over 57 % of the sectors and push the working set out
+//                    of the 126 MB L2 (-20 % at 4096^2).  profiles/r1_sweep.md)
+//                    bits 31..0  = count (u32, lib.rs:633)
 //                    bits 63..32 = zhint: an order-preserving key of a z value that is
 //                                  <= the pixel's recorded z ("a candidate below this loses")
 //   rec[idx]   16 B  .x (low 8)  = steps as f64 bits (lib.rs:635)
@@ -24,6 +31,11 @@ namespace sar {
 // order-preserving map f32 -> u32 (a > b  <=>  zkey(a) > zkey(b) for non-NaN a,b; -0 is canonicalised first)
 __host__ __device__ inline uint32_t zkey_from_bits(uint32_t b) { return (b & 0x80000000u) ? ~b : (b | 0x80000000u); }
 __host__ __device__ inline uint32_t zbits_from_key(uint32_t k) { return (k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k; }
+
+// pixel index -> slot of the `fast` array (see the layout comment above)
+struct SlotMap { uint32_t mult, mask; };
+constexpr uint32_t SLOT_SCRAMBLE = 0x9E3779B1u;
+__host__ __device__ inline uint32_t slot_of(uint32_t idx, SlotMap m) { return (idx * m.mult) & m.mask; }
 
 constexpr uint32_t ZKEY_SENTINEL = 0x407FFFFFu;   // zkey(-1.0f): Runtime::reset fills zbuf with -1.0 (lib.rs:693)
 constexpr uint32_t ZKEY_POS_INF  = 0xFF800000u;   // zkey(+inf); +NaN keys are larger, -NaN keys are < zkey(-inf)
@@ -57,6 +69,7 @@ struct IterParams {                   // everything the iterate kernel reads; li
     unsigned int job_key0;            // order key of job 0 (Runtime job counter)
     unsigned int W, H;
     unsigned int ct_kind;
+    SlotMap slots;                    // pixel -> slot map of the fast array
     unsigned int warmup;              // unrecorded steps before the recorded ones: 1000 (lib.rs:750), or 0 when `init` holds warmed states
 };
 
@@ -66,6 +79,7 @@ struct ColorParams {
     double bright_offset, bright_factor;
     unsigned int palette_len, transparent, render_kind;
     unsigned int W, H, row0, rows;
+    SlotMap slots;
     // ln(n) for n < lnlut_len, computed on the HOST with the platform libm — the function the
     // reference's f64::ln resolves to — so that `ln(count+1)/ln(max+1)` (lib.rs:860) carries the
     // same bits as a CPU run; larger arguments fall back to the device log (<= 1 ulp).
@@ -76,25 +90,25 @@ struct ColorParams {
 };
 
 // launchers (sar_kernels.cu); every one bumps the launch counter
-void launch_reset(unsigned long long *fast, ulonglong2 *rec, Scalars *scal, size_t npix, cudaStream_t s);
+void launch_reset(unsigned long long *fast, ulonglong2 *rec, Scalars *scal, size_t npix, size_t nslots, cudaStream_t s);
 void launch_iterate(const IterParams &p, unsigned int lanes, cudaStream_t s);
 // the warm-up alone (lib.rs:748-752): start points -> states after p.warmup steps, out[3*job..]
 void launch_warm(const IterParams &p, double *out, cudaStream_t s);
-void launch_max(const unsigned long long *fast, const ulonglong2 *rec, Scalars *scal, size_t pix0, size_t npix, cudaStream_t s);
+void launch_max(const unsigned long long *fast, const ulonglong2 *rec, Scalars *scal, size_t pix0, size_t npix, SlotMap slots, cudaStream_t s);
 void launch_colorize(const ColorParams &cp, const unsigned long long *fast, const ulonglong2 *rec, const Scalars *scal,
                      uint16_t *rgba_u16, float *rgba_f32, cudaStream_t s);
-void launch_unpack(const unsigned long long *fast, const ulonglong2 *rec, const Scalars *scal, size_t npix,
+void launch_unpack(const unsigned long long *fast, const ulonglong2 *rec, const Scalars *scal, size_t npix, SlotMap slots,
                    uint32_t *count, double *steps, float *zbuf, cudaStream_t s);
-void launch_pack(unsigned long long *fast, ulonglong2 *rec, Scalars *scal, size_t npix,
+void launch_pack(unsigned long long *fast, ulonglong2 *rec, Scalars *scal, size_t npix, SlotMap slots,
                  const uint32_t *count, const double *steps, const float *zbuf, cudaStream_t s);
 // Runtime::merge (lib.rs:708-738): z-only compare, ties keep dst
 void launch_merge(unsigned long long *dfast, ulonglong2 *drec, Scalars *dscal,
                   const unsigned long long *sfast, const ulonglong2 *srec, const Scalars *sscal,
-                  size_t npix, cudaStream_t s);
+                  size_t npix, SlotMap slots, cudaStream_t s);
 // deterministic all-ranks merge of one row stripe by direct peer loads; (z, ~job) max
 struct PeerList { const unsigned long long *fast[16]; const ulonglong2 *rec[16]; const Scalars *scal[16]; int n; };
 void launch_merge_peers(unsigned long long *dfast, ulonglong2 *drec, Scalars *dscal, const PeerList &peers,
-                        size_t pix0, size_t npix, cudaStream_t s);
+                        size_t pix0, size_t npix, SlotMap slots, cudaStream_t s);
 void launch_seed_points(unsigned long long seed, unsigned long long first, unsigned long long n, double *out, cudaStream_t s);
 unsigned long long launch_count();
 bool set_mode(int mode);     // diagnostics: 0 = product path; 1..3 = roofline experiments (incomplete results)

@@ -84,16 +84,47 @@ __device__ __forceinline__ double magnitude(double x, double y, double z)
     return __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z)));
 }
 
+// ColorTransform::transform(delta, screen_space, view) for the two shipped kinds (lib.rs:511-516,
+// 520-558).  `x / 2.` is written `x * 0.5` (identical in IEEE arithmetic, one instruction).
+__device__ __forceinline__ double transform_ds(const IterParams &P, double dx, double dy, double dz,
+                                               double sx, double sy, double sz)
+{
+    const double mag = magnitude(dx, dy, dz);
+    if (P.ct_kind == 1u) return __dmul_rn(__dadd_rn(mag, P.ct_offset), P.ct_factor);   // AdjustedVelocity, lib.rs:514
+    // color_transforms::poisson_saturne, lib.rs:520-558 (COS/SIN literals lib.rs:529-536)
+    const double COS = 0.7009092642998508981833083453238941729068756103515625;
+    const double SIN = 0.7132504491541815649924274111981503665447235107421875;
+    const double x2 = __dadd_rn(__dmul_rn(__dadd_rn(sx, P.ccx), COS), __dmul_rn(__dadd_rn(sz, P.ccy), SIN));
+    const bool out = (x2 < -0.0839) ||
+                     (__dadd_rn(__dmul_rn(10.55, x2), sy) < (0.46 - 1.0941)) ||
+                     (__dadd_rn(__dmul_rn(1.0426, x2), sy) < (0.179 - 0.1576)) ||
+                     (__dsub_rn(__dmul_rn(0.5139, x2), sy) > (-0.04 - 0.04092));
+    const double part = out ? 0. : 1.;
+    const double color = __dmul_rn(__dadd_rn(part, mag), 0.5);               // `/ 2.`, lib.rs:556
+    return __ddiv_rn(__dsub_rn(color, 0.1), 0.9);                            // lib.rs:557
+}
+// Same, re-derived from the point BEFORE the step (used by the deferred-test variants): the same
+// instructions on the same inputs give the same bits as the hot loop.
+__device__ __forceinline__ double transform_value(const IterParams &P, double px, double py, double pz)
+{
+    double nx, ny, nz;
+    SAR_NEXT_POINT(P, px, py, pz, nx, ny, nz);
+    const double sx = __dadd_rn(__dadd_rn(__dmul_rn(P.m[0][0], nx), __dmul_rn(P.m[0][1], ny)), __dmul_rn(P.m[0][2], nz));
+    const double sy = __dadd_rn(__dadd_rn(__dmul_rn(P.m[1][0], nx), __dmul_rn(P.m[1][1], ny)), __dmul_rn(P.m[1][2], nz));
+    const double sz = __dadd_rn(__dadd_rn(__dmul_rn(P.m[2][0], nx), __dmul_rn(P.m[2][1], ny)), __dmul_rn(P.m[2][2], nz));
+    return transform_ds(P, __dsub_rn(nx, px), __dsub_rn(ny, py), __dsub_rn(nz, pz), sx, sy, sz);   // delta, lib.rs:822
+}
+
 // The winning branch of the depth test (lib.rs:821-833), off the hot loop.
 //   value = color_transform.transform(delta, screen_space, view)   lib.rs:826-828
 //   steps[idx] = value; zbuf[idx] = z2 as f32                       lib.rs:830-832
 // made atomic and order-independent: the record is replaced iff (zkey, ~job) is strictly
 // greater than the stored one.  The candidate is re-derived from the point BEFORE the step
 // (px,py,pz): the same instructions on the same inputs give the same bits as the hot loop.
-__device__ __noinline__ void record_win(const IterParams *Pp, unsigned int idx, uint32_t key, uint32_t job_inv,
-                                        unsigned long long old, double px, double py, double pz)
+__device__ __forceinline__ void store_win(const IterParams &P, unsigned int idx, uint32_t key, uint32_t job_inv,
+                                          unsigned long long old, bool direct, double a0, double a1, double a2,
+                                          double sx, double sy, double sz)
 {
-    const IterParams &P = *Pp;
     const unsigned long long hi = ((unsigned long long)key << 32) | job_inv;
     ulonglong2 *r = P.rec + idx;
     // Current record: known without a load if the pixel was untouched when our atomic hit it,
@@ -110,36 +141,28 @@ __device__ __noinline__ void record_win(const IterParams *Pp, unsigned int idx, 
     {
         const unsigned long long expect = old + 1ull;
         const unsigned long long want = ((unsigned long long)key << 32) | (expect & 0xFFFFFFFFull);
-        if ((uint32_t)(expect >> 32) < key) (void)atomicCAS(P.fast + idx, expect, want);
+        if ((uint32_t)(expect >> 32) < key) (void)atomicCAS(P.fast + slot_of(idx, P.slots), expect, want);
     }
-    double nx, ny, nz;
-    SAR_NEXT_POINT(P, px, py, pz, nx, ny, nz);
-    const double sx = __dadd_rn(__dadd_rn(__dmul_rn(P.m[0][0], nx), __dmul_rn(P.m[0][1], ny)), __dmul_rn(P.m[0][2], nz));
-    const double sy = __dadd_rn(__dadd_rn(__dmul_rn(P.m[1][0], nx), __dmul_rn(P.m[1][1], ny)), __dmul_rn(P.m[1][2], nz));
-    const double sz = __dadd_rn(__dadd_rn(__dmul_rn(P.m[2][0], nx), __dmul_rn(P.m[2][1], ny)), __dmul_rn(P.m[2][2], nz));
-    const double mag = magnitude(__dsub_rn(nx, px), __dsub_rn(ny, py), __dsub_rn(nz, pz));   // delta, lib.rs:822
-    double value;
-    if (P.ct_kind == 1u) {
-        value = __dmul_rn(__dadd_rn(mag, P.ct_offset), P.ct_factor);          // AdjustedVelocity, lib.rs:514
-    } else {
-        // color_transforms::poisson_saturne, lib.rs:520-558 (COS/SIN literals lib.rs:529-536)
-        const double COS = 0.7009092642998508981833083453238941729068756103515625;
-        const double SIN = 0.7132504491541815649924274111981503665447235107421875;
-        const double x2 = __dadd_rn(__dmul_rn(__dadd_rn(sx, P.ccx), COS), __dmul_rn(__dadd_rn(sz, P.ccy), SIN));
-        const bool out = (x2 < -0.0839) ||
-                         (__dadd_rn(__dmul_rn(10.55, x2), sy) < (0.46 - 1.0941)) ||
-                         (__dadd_rn(__dmul_rn(1.0426, x2), sy) < (0.179 - 0.1576)) ||
-                         (__dsub_rn(__dmul_rn(0.5139, x2), sy) > (-0.04 - 0.04092));
-        const double part = out ? 0. : 1.;
-        const double color = __ddiv_rn(__dadd_rn(part, mag), 2.);            // lib.rs:556
-        value = __ddiv_rn(__dsub_rn(color, 0.1), 0.9);                       // lib.rs:557
-    }
+    const double value = direct ? transform_ds(P, a0, a1, a2, sx, sy, sz) : transform_value(P, a0, a1, a2);
     const ulonglong2 want = make_ulonglong2((unsigned long long)__double_as_longlong(value), hi);
     while (hi > cur.y) {
         const ulonglong2 prev = cas128(r, cur, want);
         if (prev.x == cur.x && prev.y == cur.y) break;
         cur = prev;
     }
+}
+// candidate given by the point before the step (deferred-test variants)
+__device__ __noinline__ void record_win(const IterParams *Pp, unsigned int idx, uint32_t key, uint32_t job_inv,
+                                        unsigned long long old, double px, double py, double pz)
+{
+    store_win(*Pp, idx, key, job_inv, old, false, px, py, pz, 0., 0., 0.);
+}
+// candidate given by delta and screen_space straight from the hot loop's registers (lib.rs:822-828)
+__device__ __noinline__ void record_win_direct(const IterParams *Pp, unsigned int idx, uint32_t key, uint32_t job_inv,
+                                               unsigned long long old, double dx, double dy, double dz,
+                                               double sx, double sy, double sz)
+{
+    store_win(*Pp, idx, key, job_inv, old, true, dx, dy, dz, sx, sy, sz);
 }
 
 // Everything that is not a plain in-view hit: out of view, non-finite coordinates, and the
@@ -175,14 +198,15 @@ __device__ __noinline__ unsigned long long classify_rare(double fi, double fj, u
 // reduction and no depth test, 3 = reduction + separate 4-byte load of the depth hint.
 template <int MODE>
 __device__ __forceinline__ int step_point(const IterParams &P, double &x, double &y, double &z,
-                                          unsigned int &idx, uint32_t &key, unsigned long long &old)
+                                          unsigned int &idx, uint32_t &key, unsigned long long &old,
+                                          double &sx, double &sy, double &sz)
 {
     double nx, ny, nz;
     SAR_NEXT_POINT(P, x, y, z, nx, ny, nz);                                   // lib.rs:770
     // screen_space = rotation_matrix.mul_right(current_point), lib.rs:773 / 208-215
-    const double sx = __dadd_rn(__dadd_rn(__dmul_rn(P.m[0][0], nx), __dmul_rn(P.m[0][1], ny)), __dmul_rn(P.m[0][2], nz));
-    const double sy = __dadd_rn(__dadd_rn(__dmul_rn(P.m[1][0], nx), __dmul_rn(P.m[1][1], ny)), __dmul_rn(P.m[1][2], nz));
-    const double sz = __dadd_rn(__dadd_rn(__dmul_rn(P.m[2][0], nx), __dmul_rn(P.m[2][1], ny)), __dmul_rn(P.m[2][2], nz));
+    sx = __dadd_rn(__dadd_rn(__dmul_rn(P.m[0][0], nx), __dmul_rn(P.m[0][1], ny)), __dmul_rn(P.m[0][2], nz));
+    sy = __dadd_rn(__dadd_rn(__dmul_rn(P.m[1][0], nx), __dmul_rn(P.m[1][1], ny)), __dmul_rn(P.m[1][2], nz));
+    sz = __dadd_rn(__dadd_rn(__dmul_rn(P.m[2][0], nx), __dmul_rn(P.m[2][1], ny)), __dmul_rn(P.m[2][2], nz));
     // rotate around center_camera, lib.rs:776-779 (center_camera.y pairs with screen_space.z)
     const double a = __dadd_rn(sx, P.ccx);
     const double b = __dadd_rn(sz, P.ccy);
@@ -206,8 +230,9 @@ __device__ __forceinline__ int step_point(const IterParams &P, double &x, double
     key = 0u;
     old = ~0ull;
     if (act == 1) {
+        const unsigned int slot = slot_of(idx, P.slots);
         if (MODE == 0) {
-            old = atomicAdd(P.fast + idx, 1ull);      // count += 1 (lib.rs:811) + fetch the depth hint, one L2 atomic
+            old = atomicAdd(P.fast + slot, 1ull);     // count += 1 (lib.rs:811) + fetch the depth hint, one L2 atomic
         } else if (MODE == 1) {
             old = ~0ull ^ (unsigned long long)(idx == 0xFFFFFFFFu);
         } else if (MODE == 2) {
@@ -215,8 +240,10 @@ __device__ __forceinline__ int step_point(const IterParams &P, double &x, double
         } else if (MODE == 3) {
             asm volatile("red.global.add.u64 [%0], 1;" ::"l"(P.fast + idx) : "memory");
             old = (unsigned long long)__ldcg(reinterpret_cast<const unsigned int *>(P.fast + idx) + 1) << 32;
-        } else if (MODE == 4) {
+        } else if (MODE == 7) {                     // natural (unscrambled) pixel -> address map, for comparison
             old = atomicAdd(P.fast + idx, 1ull);
+        } else if (MODE == 4) {
+            old = atomicAdd(P.fast + slot, 1ull);
         } else if (MODE == 5) {
             asm volatile("red.global.add.u64 [%0], 1;" ::"l"(P.fast + idx) : "memory");
         } else if (MODE == 6) {
@@ -233,7 +260,7 @@ __device__ __forceinline__ int step_point(const IterParams &P, double &x, double
             asm volatile("red.global.max.u64 [%0], %1;" ::"l"(&P.rec[idx].y), "l"(packed) : "memory");
             key = 0u;
         }
-        if (MODE == 4) {                              // keep the returned value live, never take the slow path
+        if (MODE == 4 || MODE == 7) {                 // keep the returned value live, never take the slow path
             if (key >= (uint32_t)(old >> 32) && key != 0u && idx == 0xFFFFFFF0u) P.scal->pad = key;
             key = 0u;
         }
@@ -271,7 +298,8 @@ __device__ __forceinline__ bool group_steps(const IterParams &P, Queue<NQ> &q, d
     if constexpr (J < NQ) {
         const double px = x, py = y, pz = z;
         unsigned int idx; uint32_t key; unsigned long long old;
-        const int act = step_point<MODE>(P, x, y, z, idx, key, old);
+        double sx, sy, sz;
+        const int act = step_point<MODE>(P, x, y, z, idx, key, old, sx, sy, sz);
         if (act == 2) {
             atomicAdd(&P.scal->nan_sink, P.iterations - (it + J));            // pay the whole debt at once
             retire_range<J, NQ, NQ>(P, q, job_inv);
@@ -333,9 +361,11 @@ iterate_kernel(const __grid_constant__ IterParams P)
         for (; it < P.iterations && !dead; ++it) {                            // DEFER == 0, or the < NQ tail
             const double px = x, py = y, pz = z;
             unsigned int idx; uint32_t key; unsigned long long old;
-            const int act = step_point<MODE>(P, x, y, z, idx, key, old);
+            double sx, sy, sz;
+            const int act = step_point<MODE>(P, x, y, z, idx, key, old, sx, sy, sz);
             if (act == 2) { atomicAdd(&P.scal->nan_sink, P.iterations - it); break; }
-            if (key >= (uint32_t)(old >> 32) && key != 0u) record_win(&P, idx, key, job_inv, old, px, py, pz);
+            if (key >= (uint32_t)(old >> 32) && key != 0u)                    // may beat zbuf (lib.rs:821)
+                record_win_direct(&P, idx, key, job_inv, old, __dsub_rn(x, px), __dsub_rn(y, py), __dsub_rn(z, pz), sx, sy, sz);
         }
     }
 }
@@ -370,9 +400,10 @@ void launch_warm(const IterParams &p, double *out, cudaStream_t s)
 
 static std::atomic<int> g_defer{-1};
 static std::atomic<int> g_mode{0};
+
 bool set_mode(int m)
 {
-    if (m < 0 || m > 6) return false;
+    if (m < 0 || m > 7) return false;
     g_mode = m;
     return true;
 }
@@ -399,9 +430,10 @@ void launch_iterate(const IterParams &p, unsigned int lanes, cudaStream_t s)
         case 1: iterate_kernel<1, 1><<<grid, block, 0, s>>>(p); break;
         case 2: iterate_kernel<1, 2><<<grid, block, 0, s>>>(p); break;
         case 3: iterate_kernel<1, 3><<<grid, block, 0, s>>>(p); break;
-        case 4: iterate_kernel<1, 4><<<grid, block, 0, s>>>(p); break;
+        case 4: iterate_kernel<0, 4><<<grid, block, 0, s>>>(p); break;
         case 5: iterate_kernel<1, 5><<<grid, block, 0, s>>>(p); break;
-        default: iterate_kernel<1, 6><<<grid, block, 0, s>>>(p); break;
+        case 6: iterate_kernel<1, 6><<<grid, block, 0, s>>>(p); break;
+        default: iterate_kernel<0, 7><<<grid, block, 0, s>>>(p); break;
         }
         ++g_launches;
         return;
@@ -419,24 +451,24 @@ void launch_iterate(const IterParams &p, unsigned int lanes, cudaStream_t s)
 // ---------------------------------------------------------------------------------------------
 // Runtime::reset (lib.rs:682-699)
 // ---------------------------------------------------------------------------------------------
-__global__ void reset_kernel(unsigned long long *fast, ulonglong2 *rec, Scalars *scal, size_t npix)
+__global__ void reset_kernel(unsigned long long *fast, ulonglong2 *rec, Scalars *scal, size_t npix, size_t nslots)
 {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += stride) {
-        fast[i] = FAST_RESET;                                   // count 0 (lib.rs:687)
-        rec[i] = make_ulonglong2(0ull, REC_HI_RESET);           // steps 0.0 (lib.rs:690), zbuf -1.0 (lib.rs:693)
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nslots; i += stride) {
+        fast[i] = FAST_RESET;                                   // count 0 (lib.rs:687); every slot, whatever pixel it belongs to
+        if (i < npix) rec[i] = make_ulonglong2(0ull, REC_HI_RESET);   // steps 0.0 (lib.rs:690), zbuf -1.0 (lib.rs:693)
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         scal->nan_sink = 0ull; scal->max = 0u;                  // lib.rs:694
         scal->zmax_key = ZKEY_ZERO; scal->zmin_key = ZKEY_FLT_MAX; scal->pad = 0u;
     }
 }
-void launch_reset(unsigned long long *fast, ulonglong2 *rec, Scalars *scal, size_t npix, cudaStream_t s)
+void launch_reset(unsigned long long *fast, ulonglong2 *rec, Scalars *scal, size_t npix, size_t nslots, cudaStream_t s)
 {
     const unsigned int block = 256;
-    size_t g = (npix + block - 1) / block;
+    size_t g = (nslots + block - 1) / block;
     const unsigned int grid = (unsigned int)(g > 148u * 16u ? 148u * 16u : (g ? g : 1));
-    reset_kernel<<<grid, block, 0, s>>>(fast, rec, scal, npix);
+    reset_kernel<<<grid, block, 0, s>>>(fast, rec, scal, npix, nslots);
     ++g_launches;
 }
 
@@ -445,19 +477,19 @@ void launch_reset(unsigned long long *fast, ulonglong2 *rec, Scalars *scal, size
 // reference tracks equals the max over the final counts.  Also folds the Depth min/max
 // (lib.rs:877-882).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t pixel_count(const unsigned long long *fast, const Scalars *scal, size_t i)
+__device__ __forceinline__ uint32_t pixel_count(const unsigned long long *fast, const Scalars *scal, size_t i, SlotMap slots)
 {
-    uint32_t c = (uint32_t)fast[i];
+    uint32_t c = (uint32_t)fast[slot_of((uint32_t)i, slots)];
     if (i == 0) c += (uint32_t)scal->nan_sink;                  // wrapping u32, like lib.rs:811 in release
     return c;
 }
-__global__ void max_kernel(const unsigned long long *fast, const ulonglong2 *rec, Scalars *scal, size_t pix0, size_t npix)
+__global__ void max_kernel(const unsigned long long *fast, const ulonglong2 *rec, Scalars *scal, size_t pix0, size_t npix, SlotMap slots)
 {
     uint32_t m = 0, zmx = ZKEY_ZERO, zmn = ZKEY_FLT_MAX;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += stride) {
         const size_t p = pix0 + i;
-        const uint32_t c = pixel_count(fast, scal, p);
+        const uint32_t c = pixel_count(fast, scal, p, slots);
         m = c > m ? c : m;
         const uint32_t k = (uint32_t)(rec[p].y >> 32);
         if (k != ZKEY_SENTINEL) { zmx = k > zmx ? k : zmx; zmn = k < zmn ? k : zmn; }
@@ -474,13 +506,13 @@ __global__ void max_kernel(const unsigned long long *fast, const ulonglong2 *rec
         atomicMin(&scal->zmin_key, zmn);
     }
 }
-void launch_max(const unsigned long long *fast, const ulonglong2 *rec, Scalars *scal, size_t pix0, size_t npix, cudaStream_t s)
+void launch_max(const unsigned long long *fast, const ulonglong2 *rec, Scalars *scal, size_t pix0, size_t npix, SlotMap slots, cudaStream_t s)
 {
     if (npix == 0) return;
     const unsigned int block = 256;
     size_t g = (npix + block - 1) / block;
     const unsigned int grid = (unsigned int)(g > 148u * 8u ? 148u * 8u : g);
-    max_kernel<<<grid, block, 0, s>>>(fast, rec, scal, pix0, npix);
+    max_kernel<<<grid, block, 0, s>>>(fast, rec, scal, pix0, npix, slots);
     ++g_launches;
 }
 
@@ -533,7 +565,7 @@ colorize_kernel(const __grid_constant__ ColorParams C, const unsigned long long 
             const double r = __dsqrt_rn(__dadd_rn(__dmul_rn(C.pal[n + 1][0], t), __dmul_rn(C.pal[n][0], t1)));
             const double g = __dsqrt_rn(__dadd_rn(__dmul_rn(C.pal[n + 1][1], t), __dmul_rn(C.pal[n][1], t1)));
             const double b = __dsqrt_rn(__dadd_rn(__dmul_rn(C.pal[n + 1][2], t), __dmul_rn(C.pal[n][2], t1)));
-            const uint32_t cnt = pixel_count(fast, scal, p);
+            const uint32_t cnt = pixel_count(fast, scal, p, C.slots);
             const uint32_t c1 = cnt + 1u;
             const double lnc = c1 < C.lnlut_len ? __ldg(C.lnlut + c1) : (cnt == scal->max ? s_lnmax : log((double)c1));
             const double factor = __ddiv_rn(lnc, s_lnmax);       // lib.rs:860
@@ -573,28 +605,28 @@ void launch_colorize(const ColorParams &cp, const unsigned long long *fast, cons
 // ---------------------------------------------------------------------------------------------
 // layout conversion to / from the reference's three textures (lib.rs:633-639)
 // ---------------------------------------------------------------------------------------------
-__global__ void unpack_kernel(const unsigned long long *fast, const ulonglong2 *rec, const Scalars *scal, size_t npix,
+__global__ void unpack_kernel(const unsigned long long *fast, const ulonglong2 *rec, const Scalars *scal, size_t npix, SlotMap slots,
                               uint32_t *count, double *steps, float *zbuf)
 {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += stride) {
-        if (count) count[i] = pixel_count(fast, scal, i);
+        if (count) count[i] = pixel_count(fast, scal, i, slots);
         const ulonglong2 r = rec[i];
         if (steps) steps[i] = __longlong_as_double((long long)r.x);
         if (zbuf) zbuf[i] = __uint_as_float(zbits_from_key((uint32_t)(r.y >> 32)));
     }
 }
-void launch_unpack(const unsigned long long *fast, const ulonglong2 *rec, const Scalars *scal, size_t npix,
+void launch_unpack(const unsigned long long *fast, const ulonglong2 *rec, const Scalars *scal, size_t npix, SlotMap slots,
                    uint32_t *count, double *steps, float *zbuf, cudaStream_t s)
 {
     if (npix == 0) return;
     const unsigned int block = 256;
     size_t g = (npix + block - 1) / block;
-    unpack_kernel<<<(unsigned int)(g > 148u * 16u ? 148u * 16u : g), block, 0, s>>>(fast, rec, scal, npix, count, steps, zbuf);
+    unpack_kernel<<<(unsigned int)(g > 148u * 16u ? 148u * 16u : g), block, 0, s>>>(fast, rec, scal, npix, slots, count, steps, zbuf);
     ++g_launches;
 }
 
-__global__ void pack_kernel(unsigned long long *fast, ulonglong2 *rec, Scalars *scal, size_t npix,
+__global__ void pack_kernel(unsigned long long *fast, ulonglong2 *rec, Scalars *scal, size_t npix, SlotMap slots,
                             const uint32_t *count, const double *steps, const float *zbuf)
 {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -603,7 +635,7 @@ __global__ void pack_kernel(unsigned long long *fast, ulonglong2 *rec, Scalars *
         uint32_t k = zkey_of(z);
         if (!(z > -1.0f)) k = ZKEY_SENTINEL;                    // untouched (or invalid) pixels
         const uint32_t hint = k == ZKEY_SENTINEL ? ZKEY_SENTINEL + 1u : k;
-        fast[i] = ((unsigned long long)hint << 32) | count[i];
+        fast[slot_of((uint32_t)i, slots)] = ((unsigned long long)hint << 32) | count[i];
         // uploaded records predate every future job: they keep all z ties (job key 0)
         rec[i] = make_ulonglong2((unsigned long long)__double_as_longlong(steps[i]), ((unsigned long long)k << 32) | 0xFFFFFFFFull);
     }
@@ -611,12 +643,12 @@ __global__ void pack_kernel(unsigned long long *fast, ulonglong2 *rec, Scalars *
         scal->nan_sink = 0ull; scal->max = 0u; scal->zmax_key = ZKEY_ZERO; scal->zmin_key = ZKEY_FLT_MAX; scal->pad = 0u;
     }
 }
-void launch_pack(unsigned long long *fast, ulonglong2 *rec, Scalars *scal, size_t npix,
+void launch_pack(unsigned long long *fast, ulonglong2 *rec, Scalars *scal, size_t npix, SlotMap slots,
                  const uint32_t *count, const double *steps, const float *zbuf, cudaStream_t s)
 {
     const unsigned int block = 256;
     size_t g = (npix + block - 1) / block;
-    pack_kernel<<<(unsigned int)(g > 148u * 16u ? 148u * 16u : (g ? g : 1)), block, 0, s>>>(fast, rec, scal, npix, count, steps, zbuf);
+    pack_kernel<<<(unsigned int)(g > 148u * 16u ? 148u * 16u : (g ? g : 1)), block, 0, s>>>(fast, rec, scal, npix, slots, count, steps, zbuf);
     ++g_launches;
 }
 
@@ -624,27 +656,28 @@ void launch_pack(unsigned long long *fast, ulonglong2 *rec, Scalars *scal, size_
 // Runtime::merge (lib.rs:708-738): count +=, `other` wins iff its z is strictly greater.
 // ---------------------------------------------------------------------------------------------
 __global__ void merge_kernel(unsigned long long *dfast, ulonglong2 *drec, Scalars *dscal,
-                             const unsigned long long *sfast, const ulonglong2 *srec, const Scalars *sscal, size_t npix)
+                             const unsigned long long *sfast, const ulonglong2 *srec, const Scalars *sscal, size_t npix, SlotMap slots)
 {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += stride) {
-        const uint32_t c = (uint32_t)dfast[i] + (uint32_t)sfast[i];                 // lib.rs:719
+        const uint32_t sl = slot_of((uint32_t)i, slots);
+        const uint32_t c = (uint32_t)dfast[sl] + (uint32_t)sfast[sl];               // lib.rs:719
         ulonglong2 d = drec[i];
         const ulonglong2 o = srec[i];
         if ((uint32_t)(o.y >> 32) > (uint32_t)(d.y >> 32)) { d = o; drec[i] = d; }  // lib.rs:728-735
         const uint32_t k = (uint32_t)(d.y >> 32);
         const uint32_t hint = k == ZKEY_SENTINEL ? ZKEY_SENTINEL + 1u : k;
-        dfast[i] = ((unsigned long long)hint << 32) | c;
+        dfast[sl] = ((unsigned long long)hint << 32) | c;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) dscal->nan_sink += sscal->nan_sink;
 }
 void launch_merge(unsigned long long *dfast, ulonglong2 *drec, Scalars *dscal,
                   const unsigned long long *sfast, const ulonglong2 *srec, const Scalars *sscal,
-                  size_t npix, cudaStream_t s)
+                  size_t npix, SlotMap slots, cudaStream_t s)
 {
     const unsigned int block = 256;
     size_t g = (npix + block - 1) / block;
-    merge_kernel<<<(unsigned int)(g > 148u * 16u ? 148u * 16u : (g ? g : 1)), block, 0, s>>>(dfast, drec, dscal, sfast, srec, sscal, npix);
+    merge_kernel<<<(unsigned int)(g > 148u * 16u ? 148u * 16u : (g ? g : 1)), block, 0, s>>>(dfast, drec, dscal, sfast, srec, sscal, npix, slots);
     ++g_launches;
 }
 
@@ -655,22 +688,23 @@ void launch_merge(unsigned long long *dfast, ulonglong2 *drec, Scalars *dscal,
 // Runtime, whatever the number of ranks.
 // ---------------------------------------------------------------------------------------------
 __global__ void merge_peers_kernel(unsigned long long *dfast, ulonglong2 *drec, Scalars *dscal,
-                                   const __grid_constant__ PeerList peers, size_t pix0, size_t npix)
+                                   const __grid_constant__ PeerList peers, size_t pix0, size_t npix, SlotMap slots)
 {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += stride) {
         const size_t p = pix0 + i;
-        uint32_t c = (uint32_t)dfast[p];
+        const uint32_t sl = slot_of((uint32_t)p, slots);
+        uint32_t c = (uint32_t)dfast[sl];
         ulonglong2 d = drec[p];
         for (int r = 0; r < peers.n; ++r) {
-            c += (uint32_t)__ldcv(peers.fast[r] + p);
+            c += (uint32_t)__ldcv(peers.fast[r] + sl);
             const unsigned long long oy = __ldcv(&peers.rec[r][p].y);
             if (oy > d.y) { d.y = oy; d.x = __ldcv(&peers.rec[r][p].x); }
         }
         const uint32_t k = (uint32_t)(d.y >> 32);
         const uint32_t hint = k == ZKEY_SENTINEL ? ZKEY_SENTINEL + 1u : k;
         drec[p] = d;
-        dfast[p] = ((unsigned long long)hint << 32) | c;
+        dfast[sl] = ((unsigned long long)hint << 32) | c;
     }
     if (pix0 == 0 && blockIdx.x == 0 && threadIdx.x == 0) {
         unsigned long long s = dscal->nan_sink;
@@ -679,12 +713,12 @@ __global__ void merge_peers_kernel(unsigned long long *dfast, ulonglong2 *drec, 
     }
 }
 void launch_merge_peers(unsigned long long *dfast, ulonglong2 *drec, Scalars *dscal, const PeerList &peers,
-                        size_t pix0, size_t npix, cudaStream_t s)
+                        size_t pix0, size_t npix, SlotMap slots, cudaStream_t s)
 {
     if (npix == 0) return;
     const unsigned int block = 256;
     size_t g = (npix + block - 1) / block;
-    merge_peers_kernel<<<(unsigned int)(g > 148u * 16u ? 148u * 16u : g), block, 0, s>>>(dfast, drec, dscal, peers, pix0, npix);
+    merge_peers_kernel<<<(unsigned int)(g > 148u * 16u ? 148u * 16u : g), block, 0, s>>>(dfast, drec, dscal, peers, pix0, npix, slots);
     ++g_launches;
 }
 

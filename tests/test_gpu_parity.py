@@ -256,7 +256,7 @@ def test_palette_and_transparency_variants(S, oracle):
 
 def test_lane_count_does_not_change_the_result(S):
     """Size-independent property: the trajectory -> lane mapping is invisible.  Same job list on
-    64 lanes and on the default (SM count x 768) lanes gives identical buffers."""
+    64 lanes and on the default (SM count x 896) lanes gives identical buffers."""
     cfg = _small(S.Config.solar_sail(), 450, 500, 3_000)
     states = []
     for lanes in (64, 0):

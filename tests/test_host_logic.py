@@ -13,11 +13,11 @@ def D():
 
 def test_iterations_per_job_is_two_integer_divisions(D):
     # lib.rs:1058: iterations / num_threads / jobs_per_thread
-    assert D.iterations_per_job(1_000_000_000, 113_664, 1) == 8_797
+    assert D.iterations_per_job(1_000_000_000, 132_608, 1) == 7_541
     assert D.iterations_per_job(10_000_123, 96, 3) == 10_000_123 // 96 // 3 == 34_722
     assert D.iterations_per_job(100, 7, 3) == 4            # (100//7)//3, not 100//21 rounded differently
     for world in (1, 2, 4, 8):                              # weak scaling keeps the per-job length
-        assert D.iterations_per_job(world * 10**9, world * 113_664, 1) == 8_797
+        assert D.iterations_per_job(world * 10**9, world * 132_608, 1) == 7_541
 
 
 def test_job_slices_partition_the_job_list(D):
