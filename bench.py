@@ -268,7 +268,13 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel": "iterate_kernel", "kernel_ms": it_ms, "algorithmic_bytes_per_iteration": ALGO_BYTES_PER_ITER,
                          "peak_source": peak_src,
-                         "note": "f64 issue binds before HBM here: ~91 non-fusable DP instructions per iteration (DESIGN.md §5)"},
+                         "note": "the working set is L2-resident, so HBM is not what binds: the ceiling of this kernel is the rate of "
+                                 "scattered L2 atomics with return (one per recorded iteration), measured 128e9/s raw on this GPU "
+                                 "(profiles/r1_micro_atomics.md); see l2_atomic",
+                         "l2_atomic": {"bound": "l2 atomic with return, 1 per recorded iteration", "peak": 127.9e9, "unit": "ops/s",
+                                       "achieved": frame.recorded_iterations_local() / (it_ms * 1e-3),
+                                       "frac": frame.recorded_iterations_local() / (it_ms * 1e-3) / 127.9e9,
+                                       "peak_source": "tools/micro_atomics.cu, ATOM.ADD.64 uniform random over 32 MB, 1x B200"}},
         }
     frame.close()
     if rank == 0 and world == 1 and not args.no_cpu_baseline and not (args.size or args.iterations_per_gpu or args.preset != "poisson-saturne"):
