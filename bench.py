@@ -157,8 +157,11 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("no CUDA device: the render path has no CPU fallback")
     torch.cuda.set_device(local)
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"       # keep stdout to the one JSON line (NCCL prints its version banner there)
+    # stdout carries exactly one JSON line: native libraries (NCCL prints its version banner on stdout)
+    # get stderr for the duration of the run
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     group = D.init_process_group(world, rank, local) if world > 1 else None
 
     global WIDTH, HEIGHT, ITERATIONS, WORKLOAD
@@ -283,10 +286,13 @@ def run_ours(args):
         v, dt = cpu_render_parallel(iters, threads)
         out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                                "sample": f"{iters:.3g} of 1e9 iterations ({dt:.1f} s), render_parallel semantics: {threads} threads x 12 jobs"}
-    if rank == 0:
-        print(json.dumps(out))
     if group is not None:
         D.shutdown(group)
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
+    os.close(real_stdout)
+    if rank == 0:
+        print(json.dumps(out), flush=True)
     return 0
 
 
