@@ -268,6 +268,24 @@ int  sar_peer_open(const uint8_t handle[SAR_IPC_HANDLE_BYTES], uint32_t width, u
 void sar_peer_close(sar_peer *p);
 int  sar_runtime_merge_peers_async(sar_runtime *rt, sar_peer *const *peers, int n_peers,
                                    uint32_t row0, uint32_t rows, void *stream);
+/* Device-side synchronisation between the ranks of a frame, with no host round
+ * trip: every Runtime holds one flag per (kind, source rank) in its exported
+ * allocation.  signal: a 1-block kernel that stores `epoch` into flag[kind]
+ * [my_rank] of every target (peers, and this runtime if include_self) — remote
+ * stores over NVLink, ordered after all earlier work on `stream`.  wait: a
+ * 1-block kernel that polls this runtime's own flags [kind][0..n_ranks) until
+ * all are >= epoch (gives up after ~10 s and records an error instead of
+ * hanging the GPU; see sar_runtime_sync_error).  exchange_max: the all-reduce
+ * (max) of Runtime.max over the ranks' stripes (lib.rs:860's log base is
+ * global): publish this rank's value to everyone, wait for all, take the max. */
+enum { SAR_SYNC_RENDER_DONE = 0, SAR_SYNC_MERGE_DONE = 1, SAR_SYNC_MAX_READY = 2,
+       SAR_SYNC_IMAGE_DONE = 3, SAR_SYNC_IMAGE_FREE = 4 };
+int  sar_runtime_signal_async(sar_runtime *rt, sar_peer *const *peers, int n_peers, int include_self,
+                              int kind, int my_rank, uint32_t epoch, void *stream);
+int  sar_runtime_wait_async(sar_runtime *rt, int kind, int n_ranks, uint32_t epoch, void *stream);
+int  sar_runtime_exchange_max_async(sar_runtime *rt, sar_peer *const *peers, int n_peers, int my_rank,
+                                    uint32_t epoch, void *stream);
+int  sar_runtime_sync_error(sar_runtime *rt, uint32_t *error);
 
 #ifdef __cplusplus
 }

@@ -120,7 +120,7 @@ static void layout(size_t npix, size_t &off_fast, size_t &off_image, size_t &off
     off_fast = align_up(npix * sizeof(ulonglong2), 256);
     off_image = off_fast + align_up(slots_for(npix) * sizeof(unsigned long long), 256);
     off_scal = off_image + align_up(npix * 4 * sizeof(uint16_t), 256);
-    total = off_scal + 256;
+    total = off_scal + 1024;
 }
 
 static cudaStream_t pick(const sar_runtime *rt, void *stream) { return stream ? (cudaStream_t)stream : rt->stream; }
@@ -358,6 +358,7 @@ int sar_runtime_new(uint32_t width, uint32_t height, int device, sar_runtime **o
     rt->fast = (unsigned long long *)((char *)rt->block + of);
     rt->image = (uint16_t *)((char *)rt->block + oi);
     rt->scal = (Scalars *)((char *)rt->block + os);
+    cudaMemset(rt->scal, 0, 1024);                          // flags/epochs start at 0; reset never touches them
     e = cudaStreamCreateWithFlags(&rt->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { cudaFree(rt->block); delete rt; return fail(SAR_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
     cudaDeviceGetAttribute(&rt->sm_count, cudaDevAttrMultiProcessorCount, device);
@@ -734,6 +735,68 @@ int sar_runtime_merge_peers_async(sar_runtime *rt, sar_peer *const *peers, int n
     launch_merge_peers(rt->fast, rt->rec, rt->scal, pl, (size_t)row0 * rt->w, (size_t)rows * rt->w, rt->slots, pick(rt, stream));
     SAR_CUDA(cudaGetLastError());
     rt->host_max_valid = false;
+    return SAR_OK;
+}
+
+// ---- device-side cross-GPU synchronisation ---------------------------------------
+static int make_scal_list(sar_runtime *rt, sar_peer *const *peers, int n_peers, bool include_self, ScalList &out)
+{
+    if (n_peers < 0 || n_peers + (include_self ? 1 : 0) > SYNC_MAX_RANKS) return fail(SAR_ERR_INVALID, "too many ranks");
+    memset(&out, 0, sizeof out);
+    int k = 0;
+    if (include_self) out.scal[k++] = rt->scal;
+    for (int i = 0; i < n_peers; ++i) {
+        if (!peers || !peers[i]) return fail(SAR_ERR_INVALID, "peer %d is NULL", i);
+        out.scal[k++] = peers[i]->scal;
+    }
+    out.n = k;
+    return SAR_OK;
+}
+
+int sar_runtime_signal_async(sar_runtime *rt, sar_peer *const *peers, int n_peers, int include_self, int kind,
+                             int my_rank, uint32_t epoch, void *stream)
+{
+    if (!rt) return fail(SAR_ERR_INVALID, "runtime is NULL");
+    if (kind < 0 || kind >= SYNC_KINDS || my_rank < 0 || my_rank >= SYNC_MAX_RANKS) return fail(SAR_ERR_INVALID, "bad kind/rank");
+    ScalList t;
+    if (int rc = make_scal_list(rt, peers, n_peers, include_self != 0, t)) return rc;
+    SAR_CUDA(cudaSetDevice(rt->device));
+    launch_signal(t, kind, my_rank, epoch, pick(rt, stream));
+    SAR_CUDA(cudaGetLastError());
+    return SAR_OK;
+}
+
+int sar_runtime_wait_async(sar_runtime *rt, int kind, int n_ranks, uint32_t epoch, void *stream)
+{
+    if (!rt) return fail(SAR_ERR_INVALID, "runtime is NULL");
+    if (kind < 0 || kind >= SYNC_KINDS || n_ranks < 0 || n_ranks > SYNC_MAX_RANKS) return fail(SAR_ERR_INVALID, "bad kind/n_ranks");
+    SAR_CUDA(cudaSetDevice(rt->device));
+    launch_wait(rt->scal, kind, n_ranks, epoch, pick(rt, stream));
+    SAR_CUDA(cudaGetLastError());
+    return SAR_OK;
+}
+
+int sar_runtime_exchange_max_async(sar_runtime *rt, sar_peer *const *peers, int n_peers, int my_rank, uint32_t epoch, void *stream)
+{
+    if (!rt) return fail(SAR_ERR_INVALID, "runtime is NULL");
+    if (my_rank < 0 || my_rank >= SYNC_MAX_RANKS) return fail(SAR_ERR_INVALID, "bad rank");
+    ScalList t;
+    if (int rc = make_scal_list(rt, peers, n_peers, true, t)) return rc;
+    SAR_CUDA(cudaSetDevice(rt->device));
+    cudaStream_t s = pick(rt, stream);
+    launch_publish_max(rt->scal, t, my_rank, epoch, s);
+    launch_wait(rt->scal, SYNC_MAX_READY, t.n, epoch, s);
+    launch_gather_max(rt->scal, t.n, s);
+    SAR_CUDA(cudaGetLastError());
+    rt->host_max_valid = false;
+    return SAR_OK;
+}
+
+int sar_runtime_sync_error(sar_runtime *rt, uint32_t *error)
+{
+    if (!rt || !error) return fail(SAR_ERR_INVALID, "NULL argument");
+    SAR_CUDA(cudaSetDevice(rt->device));
+    SAR_CUDA(cudaMemcpy(error, &rt->scal->sync_error, sizeof(uint32_t), cudaMemcpyDeviceToHost));
     return SAR_OK;
 }
 

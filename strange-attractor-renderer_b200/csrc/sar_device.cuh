@@ -44,12 +44,30 @@ constexpr uint32_t ZKEY_FLT_MAX  = 0xFF7FFFFFu;   // zkey(f32::MAX)
 constexpr unsigned long long FAST_RESET = (unsigned long long)(ZKEY_SENTINEL + 1u) << 32;  // count 0, hint just above the sentinel
 constexpr unsigned long long REC_HI_RESET = ((unsigned long long)ZKEY_SENTINEL << 32) | 0xFFFFFFFFull;
 
+constexpr int SYNC_MAX_RANKS = 16;
+enum SyncKind {                       // what a flag announces (see sar_runtime_signal_async)
+    SYNC_RENDER_DONE = 0,             // rank r's trajectories of this frame are all in its accumulators
+    SYNC_MERGE_DONE = 1,              // rank r has finished reading every peer's accumulators
+    SYNC_MAX_READY = 2,               // stripe_max[r] holds rank r's stripe maximum
+    SYNC_IMAGE_DONE = 3,              // rank r has stored its colourised stripe into this rank's image
+    SYNC_IMAGE_FREE = 4,              // rank r (the image owner) is done with the image of the frame
+    SYNC_KINDS = 5
+};
+
 struct Scalars {                      // device-resident scalar state of a Runtime
     unsigned long long nan_sink;      // iterations of NaN trajectories, owed to count[(0,0)]
     unsigned int max;                 // Runtime.max (lib.rs:643), valid after launch_max()
     unsigned int zmax_key, zmin_key;  // Depth colourise fold (lib.rs:877-882)
     unsigned int pad;
+    // Cross-GPU synchronisation over peer memory (one process per GPU).  flag[k][r] is
+    // written ONLY by rank r (remotely, over NVLink) and polled locally; values are frame epochs
+    // and only grow.  Never touched by reset.
+    unsigned int sync_error;          // a wait timed out
+    unsigned int pad2[3];
+    unsigned int flag[SYNC_KINDS][SYNC_MAX_RANKS];
+    unsigned int stripe_max[SYNC_MAX_RANKS];   // rank r's share of Runtime.max for the current frame
 };
+static_assert(sizeof(Scalars) <= 1024, "Scalars must fit its slot of the runtime allocation");
 
 struct IterParams {                   // everything the iterate kernel reads; lives in the constant bank
     double c[3][10];                  // attractor coefficients; c[k][0] pre-reduced to 0.0 + 1.0*c0 (lib.rs:589-596)
@@ -110,6 +128,12 @@ struct PeerList { const unsigned long long *fast[16]; const ulonglong2 *rec[16];
 void launch_merge_peers(unsigned long long *dfast, ulonglong2 *drec, Scalars *dscal, const PeerList &peers,
                         size_t pix0, size_t npix, SlotMap slots, cudaStream_t s);
 void launch_seed_points(unsigned long long seed, unsigned long long first, unsigned long long n, double *out, cudaStream_t s);
+// device-side cross-GPU synchronisation: remote flag stores and local polling
+struct ScalList { Scalars *scal[SYNC_MAX_RANKS]; int n; };
+void launch_signal(const ScalList &targets, int kind, int my_rank, unsigned int epoch, cudaStream_t s);
+void launch_wait(Scalars *mine, int kind, int n_ranks, unsigned int epoch, cudaStream_t s);
+void launch_publish_max(Scalars *mine, const ScalList &targets, int my_rank, unsigned int epoch, cudaStream_t s);
+void launch_gather_max(Scalars *mine, int n_ranks, cudaStream_t s);
 unsigned long long launch_count();
 bool set_mode(int mode);     // diagnostics: 0 = product path; 1..3 = roofline experiments (incomplete results)
 bool set_defer(int depth);   // tuning: depth of the deferred depth-test queue (0..4)

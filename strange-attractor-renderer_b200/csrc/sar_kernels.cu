@@ -722,6 +722,87 @@ void launch_merge_peers(unsigned long long *dfast, ulonglong2 *drec, Scalars *ds
     ++g_launches;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Cross-GPU synchronisation without the host: every rank keeps, inside its exported allocation,
+// one flag per (kind, source rank).  A source rank announces an event by storing the frame epoch
+// into that flag on every target (a remote store over NVLink, release at system scope); a target
+// polls its OWN memory.  Kernel boundaries order the announced work before the flag store.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys(unsigned int *p, unsigned int v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int *p)
+{
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void signal_kernel(const __grid_constant__ ScalList T, int kind, int my_rank, unsigned int epoch)
+{
+    __threadfence_system();
+    if ((int)threadIdx.x < T.n) st_release_sys(&T.scal[threadIdx.x]->flag[kind][my_rank], epoch);
+}
+void launch_signal(const ScalList &targets, int kind, int my_rank, unsigned int epoch, cudaStream_t s)
+{
+    signal_kernel<<<1, 32, 0, s>>>(targets, kind, my_rank, epoch);
+    ++g_launches;
+}
+
+__global__ void wait_kernel(Scalars *mine, int kind, int n_ranks, unsigned int epoch)
+{
+    if ((int)threadIdx.x < n_ranks) {
+        const unsigned int *f = &mine->flag[kind][threadIdx.x];
+        const long long t0 = clock64();
+        while ((int)(ld_acquire_sys(f) - epoch) < 0) {           // epochs only grow; wrap-safe compare
+            __nanosleep(100);
+            if (clock64() - t0 > 20000000000ll) {                // ~10 s: a peer is gone; do not hang the GPU
+                mine->sync_error = 1u + (unsigned int)kind;
+                break;
+            }
+        }
+    }
+    __syncthreads();
+    __threadfence_system();
+}
+void launch_wait(Scalars *mine, int kind, int n_ranks, unsigned int epoch, cudaStream_t s)
+{
+    wait_kernel<<<1, 32, 0, s>>>(mine, kind, n_ranks, epoch);
+    ++g_launches;
+}
+
+// rank r's stripe maximum (already in mine->max) to every rank, then the MAX_READY flag
+__global__ void publish_max_kernel(Scalars *mine, const __grid_constant__ ScalList T, int my_rank, unsigned int epoch)
+{
+    if ((int)threadIdx.x < T.n) {
+        const unsigned int m = mine->max;
+        *((volatile unsigned int *)&T.scal[threadIdx.x]->stripe_max[my_rank]) = m;
+        __threadfence_system();
+        st_release_sys(&T.scal[threadIdx.x]->flag[SYNC_MAX_READY][my_rank], epoch);
+    }
+}
+void launch_publish_max(Scalars *mine, const ScalList &targets, int my_rank, unsigned int epoch, cudaStream_t s)
+{
+    publish_max_kernel<<<1, 32, 0, s>>>(mine, targets, my_rank, epoch);
+    ++g_launches;
+}
+// Runtime.max = max over the stripes (the log base of lib.rs:860 is global)
+__global__ void gather_max_kernel(Scalars *mine, int n_ranks)
+{
+    unsigned int m = (int)threadIdx.x < n_ranks ? *((volatile unsigned int *)&mine->stripe_max[threadIdx.x]) : 0u;
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned int m2 = __shfl_xor_sync(0xffffffffu, m, o);
+        m = m2 > m ? m2 : m;
+    }
+    if (threadIdx.x == 0) mine->max = m;
+}
+void launch_gather_max(Scalars *mine, int n_ranks, cudaStream_t s)
+{
+    gather_max_kernel<<<1, 32, 0, s>>>(mine, n_ranks);
+    ++g_launches;
+}
+
 __global__ void seed_points_kernel(unsigned long long seed, unsigned long long first, unsigned long long n, double *out)
 {
     const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -6,17 +6,22 @@ Here a worker is a GPU (a rank), its private Runtime lives in its HBM, and the m
 stripe-wise by the GPUs themselves:
 
     rank r renders jobs [r*J, (r+1)*J)                      (no communication)
-    barrier
+    flag RENDER_DONE to every rank, wait for everyone's
     rank r reduces ROW STRIPE r over all ranks by loading the peers' accumulators directly
         over NVLink (CUDA IPC mappings; csrc merge_peers_kernel): counts add, the Δp record
         with the greatest (z, earlier job) wins — Runtime::merge (lib.rs:708-738) made
         order-independent, so the frame is bit-identical for 1, 2, 4, 8 ranks
-    all-reduce(max) of one u32 (Runtime.max is the global log base, lib.rs:860)
+    flag MERGE_DONE (peers may reset once everyone has read them)
+    max over the stripe, published into every rank's memory; each rank takes the max of all
+        (Runtime.max is the global log base, lib.rs:860)
     rank r colourises stripe r and stores it straight into rank 0's image over NVLink
-    barrier
+    flag IMAGE_DONE to rank 0; rank 0 flags IMAGE_FREE when it is done with the frame's image
 
-torch.distributed is plumbing only: rendezvous, the 64-byte IPC-handle all-gather, barriers and
-the one-scalar max all-reduce.  Pure functions at the top (job_slice, stripe_rows,
+All of that synchronisation is device-side: flags in the ranks' exported allocations, written by
+remote stores and polled locally by one-block kernels (sar_runtime_signal_async / _wait_async /
+_exchange_max_async) — the host only enqueues.  torch.distributed is plumbing for set-up: the
+rendezvous and the all-gather of the 64-byte IPC handles (plus max-over-ranks of timings in
+bench.py).  SAR_HOST_SYNC=1 selects the older host-driven variant (barriers + NCCL all-reduce).  Pure functions at the top (job_slice, stripe_rows,
 iterations_per_job) are the host logic; they are covered by CPU tests (gloo, world_size 2).
 """
 from __future__ import annotations
@@ -162,6 +167,10 @@ class Frame:
                 self.peers[r] = p
             others = [p for p in self.peers if p is not None]
             self.peer_arr = (C.c_void_p * len(others))(*[p.value for p in others])
+            self.owner_arr = (C.c_void_p * 1)(self.peers[0].value) if rank != 0 else None
+            barrier(group)                       # every rank has mapped every peer before the first remote store
+        self.device_sync = os.environ.get("SAR_HOST_SYNC", "0") != "1"
+        self.epoch = 0
         self._renderer = None
 
     # -- bookkeeping
@@ -190,6 +199,31 @@ class Frame:
             N.check(L.sar_runtime_max_async(self.rt, 0, 0, sp))
             N.check(L.sar_colorize_rows_async(C.byref(self.pod), self.rt, 0, 0, None, sp))
             return
+        if not self.device_sync:
+            return self._finish_host_sync(sp)
+        e, n, r, others = self.epoch, self.world, self.rank, self.world - 1
+        N.check(L.sar_runtime_signal_async(self.rt, self.peer_arr, others, 1, N.SYNC_RENDER_DONE, r, e, sp))
+        N.check(L.sar_runtime_wait_async(self.rt, N.SYNC_RENDER_DONE, n, e, sp))          # every rank's trajectories are in its HBM
+        N.check(L.sar_runtime_merge_peers_async(self.rt, self.peer_arr, others, self.row0, self.rows, sp))
+        N.check(L.sar_runtime_signal_async(self.rt, self.peer_arr, others, 1, N.SYNC_MERGE_DONE, r, e, sp))
+        N.check(L.sar_runtime_max_async(self.rt, self.row0, self.rows, sp))
+        N.check(L.sar_runtime_exchange_max_async(self.rt, self.peer_arr, others, r, e, sp))
+        N.check(L.sar_runtime_wait_async(self.rt, N.SYNC_IMAGE_FREE, 1, e - 1, sp))       # owner is done with the previous image
+        N.check(L.sar_colorize_rows_async(C.byref(self.pod), self.rt, self.row0, self.rows, self.peers[0], sp))
+        if r == 0:
+            N.check(L.sar_runtime_signal_async(self.rt, None, 0, 1, N.SYNC_IMAGE_DONE, r, e, sp))
+            N.check(L.sar_runtime_wait_async(self.rt, N.SYNC_IMAGE_DONE, n, e, sp))       # rank 0's image is complete
+        else:
+            N.check(L.sar_runtime_signal_async(self.rt, self.owner_arr, 1, 0, N.SYNC_IMAGE_DONE, r, e, sp))
+
+    def release_image(self, sp) -> None:
+        """Rank 0 is done with the frame's image (copied out, or not needed): peers may overwrite it."""
+        if self.world > 1 and self.device_sync and self.rank == 0:
+            self.N.check(self.L.sar_runtime_signal_async(self.rt, self.peer_arr, self.world - 1, 1,
+                                                         self.N.SYNC_IMAGE_FREE, 0, self.epoch, sp))
+
+    def _finish_host_sync(self, sp) -> None:
+        N, L = self.N, self.L
         N.check(L.sar_stream_synchronize(self.rt, sp))
         barrier(self.group)                       # every rank's trajectories are in its HBM
         N.check(L.sar_runtime_merge_peers_async(self.rt, self.peer_arr, self.world - 1, self.row0, self.rows, sp))
@@ -202,10 +236,25 @@ class Frame:
         N.check(L.sar_stream_synchronize(self.rt, sp))
         barrier(self.group)                       # rank 0's image is complete; peers may reset
 
+    def begin_frame(self, sp) -> None:
+        """New frame epoch; with device-side sync, wait until every peer has finished reading this
+        rank's accumulators of the previous frame before they are reset."""
+        self.epoch += 1
+        if self.world > 1 and self.device_sync:
+            self.N.check(self.L.sar_runtime_wait_async(self.rt, self.N.SYNC_MERGE_DONE, self.world, self.epoch - 1, sp))
+
     def step_device(self, sp) -> None:
+        self.begin_frame(sp)
         self.reset_async(sp)
         self.render_async(sp)
         self.finish_async(sp)
+        self.release_image(sp)
+
+    def check_sync(self) -> None:
+        err = C.c_uint32()
+        self.N.check(self.L.sar_runtime_sync_error(self.rt, C.byref(err)))
+        if err.value:
+            raise RuntimeError(f"cross-GPU wait timed out (kind {err.value - 1}) on rank {self.rank}")
 
     # -- end to end with host buffers
     def make_e2e(self):
@@ -259,8 +308,10 @@ class _E2E:
         sp = C.c_void_p(self.stream.cuda_stream)
         with torch.cuda.stream(self.stream):
             self.d_pts.copy_(self.h_pts, non_blocking=True)
+        f.begin_frame(sp)
         f.reset_async(sp)
         f.render_async(sp, C.c_void_p(self.d_pts.data_ptr()))
         f.finish_async(sp)
         if f.rank == 0:
             N.check(L.sar_runtime_image_download(f.rt, 0, 0, C.c_void_p(self.h_img.data_ptr()), sp))
+        f.release_image(sp)

@@ -30,6 +30,8 @@ sp = C.c_void_p(stream.cuda_stream)
 for rep in range(2):                                      # twice: reset/re-merge must be clean
     frame.step_device(sp)
 torch.cuda.synchronize()
+frame.check_sync()
+D.barrier(group)
 
 # every rank downloads its merged stripe; rank 0 assembles the full state
 count = np.empty((frame.h, frame.w), np.uint32); steps = np.empty((frame.h, frame.w), np.float64); zbuf = np.empty((frame.h, frame.w), np.float32)
