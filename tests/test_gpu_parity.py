@@ -335,3 +335,42 @@ def test_render_sequence_frames_equal_render_parallel(S, oracle):
     oracle.render_jobs(ocfg, ort, oracle.seed_points(5, 0, jobs))
     _assert_image_close(shared[2], None, oracle.colorize(ocfg, ort), None)
     r.shutdown()
+
+
+def test_randomised_configs_bit_exact(S, oracle):
+    """Seeded random sweep over what a caller can vary: image shape (odd sizes, non powers of two),
+    scale (incl. zoomed-in views that put most points out of view), camera centre, view angle,
+    rotation, transform parameters, palette, iterations, job count — and perturbed coefficients,
+    some of which make trajectories diverge.  State and RGBA16 image must equal the oracle's."""
+    rng = np.random.default_rng(20261017)
+    for case in range(12):
+        base = S.Config.poisson_saturne() if case % 2 == 0 else S.Config.solar_sail()
+        w, h = int(rng.integers(1, 400)), int(rng.integers(1, 400))
+        cfg = _small(base, w, h, int(rng.integers(0, 4000)))
+        cfg.angle = float(rng.uniform(-7.0, 7.0))
+        cfg.view.scale = float(rng.choice([0.3, 1.0, 1.7, 4.0, 9.0]))
+        cfg.view.center_camera.x += float(rng.normal(0, 0.05))
+        cfg.view.center_camera.z += float(rng.normal(0, 0.05))
+        cfg.view.rotation.rotation = float(rng.uniform(0, 6.3))
+        cfg.transparent = bool(rng.integers(0, 2))
+        cfg.colors.brighness = S.BrighnessConstants(offset=float(rng.uniform(-0.3, 0.1)), factor=float(rng.uniform(0.5, 2.5)))
+        if case % 3 == 0:
+            cfg.color_transform = S.color_transforms.AdjustedVelocity(offset=float(rng.uniform(-0.2, 0.5)), factor=float(rng.uniform(0.5, 3.0)))
+        if case % 4 == 1:
+            n = int(rng.integers(1, 9))
+            cfg.colors.palette = S.Palette([tuple(rng.uniform(0, 1, 3)) for _ in range(n)])
+        if case >= 6:   # nudge the map: some of these escape to infinity / NaN
+            for lst in (cfg.attractor.x, cfg.attractor.y, cfg.attractor.z):
+                k = int(rng.integers(0, 10))
+                lst[k] += float(rng.normal(0, 0.02))
+        if case == 11:
+            cfg.render = S.RenderKind.Depth
+        pts = S.seed_points(1000 + case, 0, int(rng.integers(1, 300)))
+        rt = S.Runtime.new(cfg)
+        S.render(cfg, rt, initial_points=pts)
+        ort, st = _oracle_state(oracle, cfg, pts)
+        _assert_state_equal(rt.download(), ort)
+        img, f32 = S.colorize(cfg, rt, want_f32=True)
+        oimg, of64 = oracle.colorize(cfg.to_pod(), ort, want_f64=True)
+        _assert_image_close(img, f32, oimg, of64)
+        rt.close()
