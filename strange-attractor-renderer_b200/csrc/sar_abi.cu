@@ -66,7 +66,6 @@ struct sar_runtime {
     // lazily allocated scratch
     double *d_init = nullptr; size_t d_init_cap = 0;
     void *d_scratch = nullptr; size_t d_scratch_cap = 0;
-    void *h_pinned = nullptr;
 };
 
 struct sar_peer {
@@ -358,9 +357,9 @@ int sar_runtime_new(uint32_t width, uint32_t height, int device, sar_runtime **o
     rt->fast = (unsigned long long *)((char *)rt->block + of);
     rt->image = (uint16_t *)((char *)rt->block + oi);
     rt->scal = (Scalars *)((char *)rt->block + os);
-    cudaMemset(rt->scal, 0, 1024);                          // flags/epochs start at 0; reset never touches them
     e = cudaStreamCreateWithFlags(&rt->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { cudaFree(rt->block); delete rt; return fail(SAR_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+    cudaMemsetAsync(rt->scal, 0, 1024, rt->stream);         // flags/epochs start at 0; reset never touches them
     cudaDeviceGetAttribute(&rt->sm_count, cudaDevAttrMultiProcessorCount, device);
     *out = rt;
     int rc = sar_runtime_reset(rt);
@@ -374,7 +373,6 @@ void sar_runtime_free(sar_runtime *rt)
     cudaSetDevice(rt->device);
     if (rt->stream) { cudaStreamSynchronize(rt->stream); cudaStreamDestroy(rt->stream); }
     cudaFree(rt->block); cudaFree(rt->d_init); cudaFree(rt->d_scratch);
-    if (rt->h_pinned) cudaFreeHost(rt->h_pinned);
     delete rt;
 }
 
