@@ -18,12 +18,13 @@ def _gpu_count():
         return 0
 
 
-@pytest.mark.parametrize("preset", ["solar", "poisson"])
-def test_two_rank_frame_equals_single_gpu(preset):
-    if _gpu_count() < 2:
-        pytest.skip("needs 2 GPUs")
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-           "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tools", "dist_check.py"), preset]
+@pytest.mark.parametrize("preset,world", [("solar", 2), ("poisson", 2), ("solar", 4), ("poisson", 8)])
+def test_n_rank_frame_equals_single_gpu(preset, world):
+    """Verified on an 8xB200 box at world = 2, 4 and 8 (profiles/r1_scaling.md)."""
+    if _gpu_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+           "--master-addr", "127.0.0.1", "--master-port", str(29533 + world), os.path.join(ROOT, "tools", "dist_check.py"), preset]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0 and "DIST_CHECK_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
 
