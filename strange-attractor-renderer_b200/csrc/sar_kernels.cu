@@ -119,8 +119,9 @@ __device__ __forceinline__ double transform_value(const IterParams &P, double px
 //   value = color_transform.transform(delta, screen_space, view)   lib.rs:826-828
 //   steps[idx] = value; zbuf[idx] = z2 as f32                       lib.rs:830-832
 // made atomic and order-independent: the record is replaced iff (zkey, ~job) is strictly
-// greater than the stored one.  The candidate is re-derived from the point BEFORE the step
-// (px,py,pz): the same instructions on the same inputs give the same bits as the hot loop.
+// greater than the stored one.  The candidate comes either straight from the hot loop's registers
+// (direct: delta in a0..a2, screen_space in sx..sz) or as the point before the step (a0..a2),
+// from which it is re-derived.
 __device__ __forceinline__ void store_win(const IterParams &P, unsigned int idx, uint32_t key, uint32_t job_inv,
                                           unsigned long long old, bool direct, double a0, double a1, double a2,
                                           double sx, double sy, double sz)
@@ -185,17 +186,21 @@ __device__ __noinline__ unsigned long long classify_rare(double fi, double fj, u
 // Lane L runs jobs L, L+lanes, L+2*lanes, ...; each job is one reference render() call:
 // start point, 1000 warm-up steps (lib.rs:750-752), `iterations` recorded steps.
 //
-// DEFER: the depth test needs the value the L2 atomic returns (~1000 cycles under load).
-// Instead of stalling, the test for iteration n is made DEFER iterations later, from a small
-// register queue {point before the step, pixel, z key, atomic result}; entries retire in order,
-// so within a job the earlier iteration still wins exact z ties.
+// DEFER (tuning knob, default 0): the depth test needs the value the L2 atomic returns (~1000
+// cycles under load).  With DEFER > 0 the test for iteration n is made DEFER iterations later,
+// from a small register queue {point before the step, pixel, z key, atomic result}; entries
+// retire in order, so within a job the earlier iteration still wins exact z ties.  Measured: no
+// gain — the limit is the rate of atomics with return, not their latency (profiles/r1_sweep.md).
 // ---------------------------------------------------------------------------------------------
 // One recorded iteration up to (and including) the count atomic.  In: the current point.
 // Out: the next point in (x,y,z); act 0 = out of view, 1 = recorded at idx with the atomic's
 // return value in `old` and the candidate depth key in `key` (0 = cannot win), 2 = NaN state.
-// MODE is a diagnostic switch for roofline experiments (tools/sweep_iterate.py); only MODE 0
-// is the product: 1 = arithmetic only (no memory traffic), 2 = count with a fire-and-forget
-// reduction and no depth test, 3 = reduction + separate 4-byte load of the depth hint.
+// MODE is a diagnostic switch for roofline experiments (tools/sweep_iterate.py, sweep_lanes.py);
+// only MODE 0 is the product.  1 = arithmetic only (no memory traffic); 2 = count with a
+// fire-and-forget reduction, no depth test; 3 / 6 = reduction + 4-byte load of the hint (ld.cg /
+// ld.ca); 4 = the product's atomic with the win path removed; 5 = two reductions (count add +
+// packed z max); 7 = like 4 on the unscrambled pixel -> slot map.  Modes != 0 leave the Runtime
+// in a state that is only good for timing.
 template <int MODE>
 __device__ __forceinline__ int step_point(const IterParams &P, double &x, double &y, double &z,
                                           unsigned int &idx, uint32_t &key, unsigned long long &old,
