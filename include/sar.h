@@ -107,9 +107,9 @@ int         sar_device_count(int *count);    /* SAR_ERR_CUDA when no driver/devi
 int         sar_default_threads(int device, uint32_t *threads);
 /* Tuning knobs that never change results.  "defer": depth (0..4) of the iterate
  * kernel's deferred depth-test queue (default 0, env SAR_DEFER).
- * "diagnostic_mode": 0 = product path (default); 1..3 run the iterate kernel
- * with parts of the scatter removed, for roofline experiments only — their
- * results are incomplete by design (tools/sweep_iterate.py). */
+ * "diagnostic_mode": 0 = product path (default); 1..7 run the iterate kernel
+ * with parts of the scatter removed or replaced, for roofline experiments only
+ * — their results are incomplete by design (tools/sweep_iterate.py). */
 int         sar_set_option(const char *name, int64_t value);
 
 /* ---- Config presets --------------------------------------------------- */
