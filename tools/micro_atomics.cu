@@ -31,6 +31,46 @@ __global__ void k(unsigned long long *tab, unsigned int mask, int iters, unsigne
     if (acc == 0x1234567887654321ull) *sink = acc;
 }
 
+// shared-memory counterpart: scattered atomics on a 32 K-entry table private to the block
+template <int MODE>
+__global__ void ks(int iters, unsigned long long *sink)
+{
+    extern __shared__ unsigned int tab[];
+    const unsigned int n = 32768;
+    for (unsigned int i = threadIdx.x; i < n; i += blockDim.x) tab[i] = 0;
+    __syncthreads();
+    unsigned int s = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
+    unsigned long long acc = 0;
+#pragma unroll 4
+    for (int i = 0; i < iters; ++i) {
+        s = s * 1664525u + 1013904223u;
+        const unsigned int idx = (s >> 7) & (n - 1);
+        if (MODE == 0) atomicAdd(tab + idx, 1u);
+        if (MODE == 1) { atomicAdd(tab + idx, 1u); atomicMax(tab + ((idx + 16384u) & (n - 1)), s); }
+        if (MODE == 2) acc += atomicAdd(tab + idx, 1u);
+    }
+    __syncthreads();
+    if (acc == 0x1234567887654321ull || tab[threadIdx.x] == 0xdeadbeefu) *sink = acc;
+}
+template <int MODE>
+static void run_smem(const char *name, unsigned long long *sink)
+{
+    const int iters = 4096, block = 1024, grid = 148;
+    cudaFuncSetAttribute(ks<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    ks<MODE><<<grid, block, 131072>>>(64, sink);
+    cudaDeviceSynchronize();
+    cudaEventRecord(e0);
+    ks<MODE><<<grid, block, 131072>>>(iters, sink);
+    cudaEventRecord(e1);
+    cudaDeviceSynchronize();
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    const double ops = (double)grid * block * iters;
+    printf("%-38s table  128 KB smem/SM, threads/SM 1024 : %8.2f G iterations/s  (%.3f lane-iterations/cycle/SM @1.965 GHz)\n", name,
+           ops / ms / 1e6, ops / ms / 1e6 / 148 / 1.965);
+}
+
 template <int MODE>
 static void run(const char *name, unsigned long long *tab, unsigned int mask, unsigned long long *sink, int threads_per_sm)
 {
@@ -70,5 +110,8 @@ int main()
             run<11>("RED.ADD.32 + RED.MAX.32 2 arrays", tab, mask, sink, tps);
         }
     }
+    run_smem<0>("ATOMS.ADD.32 (no return)", sink);
+    run_smem<2>("ATOMS.ADD.32 (return)", sink);
+    run_smem<1>("ATOMS.ADD.32 + ATOMS.MAX.32", sink);
     return 0;
 }
