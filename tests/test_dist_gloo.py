@@ -55,7 +55,7 @@ def test_two_rank_frame_on_gloo(tmp_path, oracle):
 
     from strange_attractor_renderer_b200 import dist as D
 
-    world, port = 2, 29541
+    world, port = 2, 29551
     mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     lanes, jpt, total = 6, 2, 2 * 6 * 2 * 3000 + 5
     cfg = oracle.solar_sail()
