@@ -1,0 +1,231 @@
+// PROTOTYPE (not part of the product): cost of the "bin-then-tile" scatter of DESIGN.md §10 item 0.
+//   producer : the real trajectory arithmetic (poisson-saturne, 2048x2048), no atomic in the loop;
+//              every 32 iterations a 128-lane block multisplits its 4096 hit records by image tile
+//              (256 tiles of 128x128) in shared memory and appends them to per-tile global queues.
+//   consumer : blocks take (tile, segment) work items, accumulate count and a 64-bit (zkey, order)
+//              max per pixel in shared memory, then flush the touched pixels with reductions.
+// It answers two questions before the design is built for real: does the producer stay
+// arithmetic-bound with the multisplit in it, and how long does the consumer take.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -fmad=false -o tools/proto_binning.bin tools/proto_binning.cu
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include <cuda_runtime.h>
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA %s at %d: %s\n", #x, __LINE__, cudaGetErrorString(e_)); exit(1); } } while (0)
+
+struct Params {
+    double c[3][10], m[3][3], ccx, ccy, ccz, cv, sv, sam, ws, half_h;
+    unsigned int W, H;
+};
+
+constexpr int LANES = 128, WIN = 32, TILE = 128, TSHIFT = 7;
+constexpr int NT = 256;                       // 16 x 16 tiles of 128 x 128 at 2048^2
+constexpr unsigned long long SEG = 1u << 20;  // consumer work item: up to 1 Mi records of one tile
+
+__device__ __forceinline__ double sum10(const double (&c)[10], double x, double y, double z, double xx, double xy, double xz, double yy, double yz, double zz)
+{
+    double s = c[0];
+    s = __dadd_rn(s, __dmul_rn(x, c[1])); s = __dadd_rn(s, __dmul_rn(xx, c[2])); s = __dadd_rn(s, __dmul_rn(xy, c[3]));
+    s = __dadd_rn(s, __dmul_rn(xz, c[4])); s = __dadd_rn(s, __dmul_rn(y, c[5])); s = __dadd_rn(s, __dmul_rn(yy, c[6]));
+    s = __dadd_rn(s, __dmul_rn(yz, c[7])); s = __dadd_rn(s, __dmul_rn(z, c[8])); s = __dadd_rn(s, __dmul_rn(zz, c[9]));
+    return s;
+}
+__device__ __forceinline__ void next_point(const Params &P, double &x, double &y, double &z)
+{
+    const double xx = __dmul_rn(x, x), xy = __dmul_rn(x, y), xz = __dmul_rn(x, z), yy = __dmul_rn(y, y), yz = __dmul_rn(y, z), zz = __dmul_rn(z, z);
+    const double nx = sum10(P.c[0], x, y, z, xx, xy, xz, yy, yz, zz), ny = sum10(P.c[1], x, y, z, xx, xy, xz, yy, yz, zz),
+                 nz = sum10(P.c[2], x, y, z, xx, xy, xz, yy, yz, zz);
+    x = nx; y = ny; z = nz;
+}
+__device__ __forceinline__ unsigned long long splitmix(unsigned long long seed, unsigned long long n)
+{
+    unsigned long long z = seed + (n + 1ull) * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+// record: [63:32] zkey | [31:18] pixel in tile (14 b) | [17:11] lane (7 b) | [10:5] iteration in window (6 b); tile kept beside it while staging
+__global__ void __launch_bounds__(LANES)
+producer(const __grid_constant__ Params P, unsigned long long **queues, unsigned long long *cursors, const unsigned long long *qcap,
+         double *ckpt, unsigned int iterations, int mode)
+{
+    extern __shared__ unsigned long long sm[];
+    unsigned long long *recs = sm;                               // WIN * LANES records
+    unsigned char *tiles = (unsigned char *)(recs + WIN * LANES);   // their tile ids
+    unsigned int *hist = (unsigned int *)(tiles + WIN * LANES);     // NT counts, then NT running offsets
+    unsigned long long *base = (unsigned long long *)(hist + 2 * NT);   // NT global bases
+    const unsigned int lane = threadIdx.x;
+    const unsigned long long job = (unsigned long long)blockIdx.x * LANES + lane;
+    double x = __dmul_rn(__dmul_rn((double)(splitmix(1234, 3 * job) >> 11), 0x1.0p-53), 0.1);
+    double y = __dmul_rn(__dmul_rn((double)(splitmix(1234, 3 * job + 1) >> 11), 0x1.0p-53), 0.1);
+    double z = __dmul_rn(__dmul_rn((double)(splitmix(1234, 3 * job + 2) >> 11), 0x1.0p-53), 0.1);
+    for (int w = 0; w < 1000; ++w) next_point(P, x, y, z);
+    const unsigned int nwin = iterations / WIN;
+    for (unsigned int win = 0; win < nwin; ++win) {
+        if (ckpt) { double *c = ckpt + ((size_t)win * gridDim.x * LANES + job) * 3; c[0] = x; c[1] = y; c[2] = z; }   // replay checkpoint
+        for (int i = 0; i < WIN; ++i) {
+            next_point(P, x, y, z);
+            const double sx = __dadd_rn(__dadd_rn(__dmul_rn(P.m[0][0], x), __dmul_rn(P.m[0][1], y)), __dmul_rn(P.m[0][2], z));
+            const double sy = __dadd_rn(__dadd_rn(__dmul_rn(P.m[1][0], x), __dmul_rn(P.m[1][1], y)), __dmul_rn(P.m[1][2], z));
+            const double sz = __dadd_rn(__dadd_rn(__dmul_rn(P.m[2][0], x), __dmul_rn(P.m[2][1], y)), __dmul_rn(P.m[2][2], z));
+            const double a = __dadd_rn(sx, P.ccx), b = __dadd_rn(sz, P.ccy);
+            const double x2 = __dadd_rn(__dmul_rn(a, P.cv), __dmul_rn(b, P.sv));
+            const double z2 = __dsub_rn(__dmul_rn(a, P.sv), __dmul_rn(b, P.cv));
+            const double fi = __dmul_rn(__dsub_rn(P.sam, x2), P.ws);
+            const double fj = __dsub_rn(P.half_h, __dmul_rn(__dadd_rn(sy, P.ccz), P.ws));
+            const unsigned int ii = (unsigned int)__double2int_rd(fi), jj = (unsigned int)__double2int_rd(fj);
+            unsigned long long rec = 0ull;
+            unsigned int tile = 255u;
+            if (ii < P.W && jj < P.H) {
+                const unsigned int bits = __float_as_uint(__double2float_rn(z2) + 0.0f);
+                const unsigned int key = (bits & 0x80000000u) ? ~bits : (bits | 0x80000000u);
+                tile = (jj >> TSHIFT) * (P.W >> TSHIFT) + (ii >> TSHIFT);
+                const unsigned int pix = ((jj & (TILE - 1)) << TSHIFT) | (ii & (TILE - 1));
+                rec = ((unsigned long long)key << 32) | ((unsigned long long)pix << 18) | (lane << 11) | ((unsigned int)i << 5) | 1u;
+            }
+            recs[i * LANES + lane] = rec;
+            tiles[i * LANES + lane] = (unsigned char)tile;
+        }
+        if (mode == 0) continue;                                  // arithmetic + staging only
+        __syncthreads();
+        for (int t = lane; t < 2 * NT; t += LANES) hist[t] = 0;
+        __syncthreads();
+        for (int i = 0; i < WIN; ++i) if (recs[i * LANES + lane]) atomicAdd(&hist[tiles[i * LANES + lane]], 1u);
+        __syncthreads();
+        for (int t = lane; t < NT; t += LANES) base[t] = hist[t] ? atomicAdd(&cursors[t], (unsigned long long)hist[t]) : 0ull;
+        __syncthreads();
+        if (mode == 2) { __syncthreads(); continue; }              // dry run: per-tile totals only
+        for (int i = 0; i < WIN; ++i) {
+            const unsigned long long rec = recs[i * LANES + lane];
+            if (rec) {
+                const unsigned int t = tiles[i * LANES + lane];
+                const unsigned long long pos = base[t] + atomicAdd(&hist[NT + t], 1u);
+                if (pos < qcap[t]) queues[t][pos] = rec;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// consumer: one block per (tile, segment); count u32 + best u64 per pixel in shared memory
+__global__ void __launch_bounds__(512)
+consumer(unsigned long long *const *queues, const unsigned long long *cursors, const unsigned int *work_tile, const unsigned long long *work_first,
+         unsigned long long *gfast, unsigned long long *gbest, unsigned int W)
+{
+    extern __shared__ unsigned long long csm[];
+    unsigned long long *best = csm;                               // TILE*TILE
+    unsigned int *cnt = (unsigned int *)(best + TILE * TILE);     // TILE*TILE
+    const unsigned int t = work_tile[blockIdx.x];
+    const unsigned long long first = work_first[blockIdx.x];
+    unsigned long long last = first + SEG;
+    if (last > cursors[t]) last = cursors[t];
+    for (int p = threadIdx.x; p < TILE * TILE; p += blockDim.x) { best[p] = 0ull; cnt[p] = 0u; }
+    __syncthreads();
+    const unsigned long long *q = queues[t];
+    for (unsigned long long r = first + threadIdx.x; r < last; r += blockDim.x) {
+        const unsigned long long rec = __ldcs(q + r);
+        const unsigned int pix = (unsigned int)(rec >> 18) & 0x3FFFu;
+        atomicAdd(&cnt[pix], 1u);
+        // (zkey, ~order): the order bits of the real design come from the run header; here the low word stands in
+        atomicMax(&best[pix], rec);
+    }
+    __syncthreads();
+    const unsigned int tx = t % (W >> TSHIFT), ty = t / (W >> TSHIFT);
+    for (int p = threadIdx.x; p < TILE * TILE; p += blockDim.x) {
+        if (cnt[p]) {
+            const size_t g = (size_t)((ty << TSHIFT) + (p >> TSHIFT)) * W + (tx << TSHIFT) + (p & (TILE - 1));
+            atomicAdd(&gfast[g], (unsigned long long)cnt[p]);
+            atomicMax(&gbest[g], best[p]);
+        }
+    }
+}
+
+int main(int argc, char **argv)
+{
+    const unsigned int W = 2048, H = 2048;
+    const int lanes_per_sm = argc > 1 ? atoi(argv[1]) : 640;
+    const int grid = 148 * lanes_per_sm / LANES;
+    const unsigned long long njobs = (unsigned long long)grid * LANES;
+    const unsigned int iters = (unsigned int)(1000000000ull / njobs) / WIN * WIN;
+    Params P;
+    const double cx[10] = {0.021, 1.182, -1.183, 0.128, -1.12, -0.641, -1.152, -0.834, -0.97, 0.722};
+    const double cy[10] = {0.243038, -0.825, -1.2, -0.835443, -0.835443, -0.364557, 0.458, 0.622785, -0.394937, -1.032911};
+    const double cz[10] = {-0.455696, 0.673, 0.915, -0.258228, -0.495, -0.264, -0.432, -0.416, -0.877, -0.3};
+    for (int i = 0; i < 10; ++i) { P.c[0][i] = cx[i]; P.c[1][i] = cy[i]; P.c[2][i] = cz[i]; }
+    const double ax = 0.304289493528802, ay = 0.760492682863655, az = 0.573636455813981, rot = 1.78268191887446;
+    const double c = cos(rot), c1 = 1. - c, s = sin(rot);
+    P.m[0][0] = c + ax * ax * c1; P.m[0][1] = ax * ay * c1 - az * s; P.m[0][2] = ax * az * c1 + ay * s;
+    P.m[1][0] = ay * ax * c1 + az * s; P.m[1][1] = c + ay * ay * c1; P.m[1][2] = ay * az * c1 - ax * s;
+    P.m[2][0] = az * ax * c1 - ay * s; P.m[2][1] = az * ay * c1 + ax * s; P.m[2][2] = c + az * az * c1;
+    P.ccx = -0.005; P.ccy = 0.262; P.ccz = -0.366 + 0.12; P.cv = 1.0; P.sv = 0.0; P.sam = 0.5; P.ws = 2048.0; P.half_h = 1024.0;
+    P.W = W; P.H = H;
+
+    const unsigned long long total = njobs * iters;
+    unsigned long long **dq, *cursors, *gfast, *gbest, *dcap;
+    CK(cudaMalloc(&dq, NT * sizeof(void *)));
+    CK(cudaMalloc(&cursors, NT * 8)); CK(cudaMalloc(&dcap, NT * 8));
+    CK(cudaMalloc(&gfast, (size_t)W * H * 8)); CK(cudaMalloc(&gbest, (size_t)W * H * 8));
+    double *ckpt; CK(cudaMalloc(&ckpt, (size_t)(iters / WIN) * njobs * 24));
+    const size_t psm = (size_t)WIN * LANES * 8 + WIN * LANES + 2 * NT * 4 + NT * 8;
+    CK(cudaFuncSetAttribute(producer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
+    const size_t csmb = (size_t)TILE * TILE * 12;
+    CK(cudaFuncSetAttribute(consumer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmb));
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float ms;
+    // dry run: exact per-tile record counts -> queue sizes (the real design would size queues from the previous frame / a sample)
+    CK(cudaMemset(cursors, 0, NT * 8)); CK(cudaMemset(dcap, 0, NT * 8));
+    producer<<<grid, LANES, psm>>>(P, dq, cursors, dcap, nullptr, iters, 2);
+    CK(cudaDeviceSynchronize());
+    std::vector<unsigned long long> cap(NT);
+    CK(cudaMemcpy(cap.data(), cursors, NT * 8, cudaMemcpyDeviceToHost));
+    std::vector<unsigned long long *> hq(NT);
+    size_t qbytes_total = 0;
+    for (int t = 0; t < NT; ++t) { CK(cudaMalloc(&hq[t], (cap[t] + 1) * 8)); qbytes_total += cap[t] * 8; }
+    CK(cudaMemcpy(dq, hq.data(), NT * sizeof(void *), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dcap, cap.data(), NT * 8, cudaMemcpyHostToDevice));
+    printf("lanes/SM %d, jobs %llu, iterations/job %u, iterations %.4g, queue memory %.2f GB, checkpoints %.2f GB, producer smem %zu B/block\n", lanes_per_sm, njobs, iters,
+           (double)total, qbytes_total / 1e9, (double)(iters / WIN) * njobs * 24 / 1e9, psm);
+    for (int mode = 0; mode < 2; ++mode) {
+        for (int rep = 0; rep < 2; ++rep) {
+            CK(cudaMemset(cursors, 0, NT * 8));
+            cudaEventRecord(e0);
+            producer<<<grid, LANES, psm>>>(P, dq, cursors, dcap, mode ? ckpt : nullptr, iters, mode);
+            cudaEventRecord(e1);
+            CK(cudaDeviceSynchronize());
+            cudaEventElapsedTime(&ms, e0, e1);
+        }
+        printf("producer mode %d (%s): %.3f ms  %.2f G recorded it/s\n", mode, mode ? "arithmetic + multisplit + queue append + checkpoints" : "arithmetic + staging in shared memory only",
+               ms, (double)total / ms / 1e6);
+    }
+    std::vector<unsigned long long> hc(NT);
+    CK(cudaMemcpy(hc.data(), cursors, NT * 8, cudaMemcpyDeviceToHost));
+    unsigned long long sum = 0, mx = 0, dropped = 0;
+    std::vector<unsigned int> wt; std::vector<unsigned long long> wf;
+    for (int t = 0; t < NT; ++t) {
+        sum += hc[t]; if (hc[t] > mx) mx = hc[t];
+        unsigned long long have = hc[t] < cap[t] ? hc[t] : cap[t];
+        dropped += hc[t] - have;
+        hc[t] = have;
+        for (unsigned long long f = 0; f < have; f += SEG) { wt.push_back(t); wf.push_back(f); }
+    }
+    CK(cudaMemcpy(cursors, hc.data(), NT * 8, cudaMemcpyHostToDevice));
+    printf("records %llu (%.4f of iterations), densest tile %.4f of them, dropped by the prototype's fixed capacity %.4f, consumer work items %zu\n",
+           sum, (double)sum / total, (double)mx / sum, (double)dropped / sum, wt.size());
+    unsigned int *dwt; unsigned long long *dwf;
+    CK(cudaMalloc(&dwt, wt.size() * 4)); CK(cudaMalloc(&dwf, wf.size() * 8));
+    CK(cudaMemcpy(dwt, wt.data(), wt.size() * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dwf, wf.data(), wf.size() * 8, cudaMemcpyHostToDevice));
+    for (int rep = 0; rep < 2; ++rep) {
+        CK(cudaMemset(gfast, 0, (size_t)W * H * 8)); CK(cudaMemset(gbest, 0, (size_t)W * H * 8));
+        cudaEventRecord(e0);
+        consumer<<<(unsigned int)wt.size(), 512, csmb>>>(dq, cursors, dwt, dwf, gfast, gbest, W);
+        cudaEventRecord(e1);
+        CK(cudaDeviceSynchronize());
+        cudaEventElapsedTime(&ms, e0, e1);
+    }
+    printf("consumer: %.3f ms for %llu records  (%.2f G records/s, %.1f GB/s of queue reads)\n", ms, sum - dropped, (double)(sum - dropped) / ms / 1e6,
+           (double)(sum - dropped) * 8 / ms / 1e6);
+    return 0;
+}
