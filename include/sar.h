@@ -185,6 +185,14 @@ void sar_renderer_shutdown(sar_renderer *r);
  * steps run, exactly as lib.rs:1058-1062 prescribes for that num_threads. */
 int  sar_renderer_num_threads(const sar_renderer *r, uint64_t *num_threads);   /* jobs_per_thread = 1 */
 int  sar_renderer_num_threads_for(const sar_renderer *r, uint64_t jobs_per_thread, uint64_t *num_threads);
+/* The decomposition sar_render_parallel will use for a frame of `iterations`:
+ * num_threads and iterations/num_threads/jobs_per_thread (lib.rs:1058).  In
+ * auto mode num_threads is additionally capped so that every job gets at least
+ * 64 recorded steps (multiple of 32, >= 32): a GPU has ~10^5 lanes where the
+ * reference has ~10 threads, and a small render — the reference's default is
+ * 1e7 iterations — must not round to 0 steps per job.  Either output may be NULL. */
+int  sar_renderer_plan(const sar_renderer *r, uint64_t iterations, uint64_t jobs_per_thread,
+                       uint64_t *num_threads, uint64_t *iterations_per_job);
 /* render_parallel, lib.rs:1051: iterations/num_threads/jobs_per_thread per job
  * (integer division, lib.rs:1058), num_threads*jobs_per_thread jobs
  * (lib.rs:1062), merge (lib.rs:1072-1076), colorize (lib.rs:1080).

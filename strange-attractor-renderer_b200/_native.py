@@ -81,6 +81,7 @@ SYMBOLS = {
     "sar_renderer_shutdown": (None, [_vp]),
     "sar_renderer_num_threads": (C.c_int, [_vp, _P(C.c_uint64)]),
     "sar_renderer_num_threads_for": (C.c_int, [_vp, C.c_uint64, _P(C.c_uint64)]),
+    "sar_renderer_plan": (C.c_int, [_vp, C.c_uint64, C.c_uint64, _P(C.c_uint64), _P(C.c_uint64)]),
     "sar_render_parallel": (C.c_int, [_vp, _cfgp, C.c_uint64, C.c_uint64, _f64p, _u16p]),
     "sar_renderer_runtime": (C.c_int, [_vp, _P(_vp)]),
     "sar_render_sequence": (C.c_int, [_vp, _cfgp, _f64p, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32, _u16p, _vp, _vp]),

@@ -326,6 +326,13 @@ class ParallelRenderer:
         N.check(N.lib().sar_renderer_num_threads_for(self._h, jobs_per_thread, C.byref(n)))
         return int(n.value)
 
+    def plan(self, iterations: int, jobs_per_thread: int = 1):
+        """(num_threads, iterations_per_job) render_parallel will use for a frame of `iterations`
+        (include/sar.h: sar_renderer_plan; lib.rs:1058-1062)."""
+        n, ipj = C.c_uint64(), C.c_uint64()
+        N.check(N.lib().sar_renderer_plan(self._h, int(iterations), jobs_per_thread, C.byref(n), C.byref(ipj)))
+        return int(n.value), int(ipj.value)
+
     def shutdown(self) -> None:
         if getattr(self, "_h", None):
             N.lib().sar_renderer_shutdown(self._h)
@@ -358,7 +365,7 @@ def render_parallel(renderer: ParallelRenderer, config, jobs_per_thread: int, se
     pts_p = None
     if initial_points is not None:
         pts = np.ascontiguousarray(initial_points, dtype=np.float64).reshape(-1, 3)
-        if pts.shape[0] < renderer.num_threads(jobs_per_thread) * jobs_per_thread:
+        if pts.shape[0] < renderer.plan(c.iterations, jobs_per_thread)[0] * jobs_per_thread:
             raise SarError(N.SAR_ERR_INVALID, "initial_points must hold num_threads*jobs_per_thread points")
         pts_p = pts.ctypes.data_as(N._f64p)
     N.check(N.lib().sar_render_parallel(renderer._h, C.byref(c), jobs_per_thread, seed & (2**64 - 1), pts_p,

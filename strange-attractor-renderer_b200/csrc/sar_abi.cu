@@ -858,23 +858,39 @@ static uint32_t renderer_lanes(const sar_renderer *r, size_t d)
 // worker, lib.rs:956-988).  In auto mode the GPU needs no over-decomposition for load balance —
 // every job has the same length and gets its own lane — so the job count is kept at the
 // device's lane count: threads = lanes / jobs_per_thread (multiple of 32, at least 32), which
-// keeps the 1000-step warm-up per job (lib.rs:750) from swamping short frames.
-static uint32_t renderer_threads_for(const sar_renderer *r, size_t d, uint64_t jobs_per_thread)
+// keeps the 1000-step warm-up per job (lib.rs:750) from swamping short frames.  A GPU has ~10^5
+// lanes where the reference has ~10 threads, so auto mode also never uses more threads than give
+// every job at least MIN_JOB_ITERATIONS recorded steps: a small render (the reference's default is
+// 1e7 iterations, and `iterations / threads / jobs` rounds to 0 below threads*jobs) must not come
+// out empty.  `iterations` = the whole frame's (UINT64_MAX: no cap).
+static const uint64_t MIN_JOB_ITERATIONS = 64;
+static uint32_t renderer_threads_for(const sar_renderer *r, size_t d, uint64_t jobs_per_thread, uint64_t iterations = ~0ull)
 {
     const uint32_t lanes = renderer_lanes(r, d);
-    if (r->threads_per_device || jobs_per_thread <= 1) return lanes;
-    uint64_t t = (lanes / jobs_per_thread) & ~31ull;
+    if (r->threads_per_device) return lanes;
+    uint64_t t = lanes / jobs_per_thread;
+    const uint64_t share = iterations / r->devices.size() / jobs_per_thread / MIN_JOB_ITERATIONS;   // per device
+    if (share < t) t = share;
+    t &= ~31ull;
     return (uint32_t)(t < 32 ? 32 : t);
+}
+
+int sar_renderer_plan(const sar_renderer *r, uint64_t iterations, uint64_t jobs_per_thread, uint64_t *num_threads,
+                      uint64_t *iterations_per_job)
+{
+    if (!r) return fail(SAR_ERR_INVALID, "renderer is NULL");
+    if (jobs_per_thread == 0) return fail(SAR_ERR_INVALID, "jobs_per_thread must be non-zero");
+    uint64_t n = 0;
+    for (size_t d = 0; d < r->devices.size(); ++d) n += renderer_threads_for(r, d, jobs_per_thread, iterations);
+    if (num_threads) *num_threads = n;
+    if (iterations_per_job) *iterations_per_job = iterations / n / jobs_per_thread;     // lib.rs:1058
+    return SAR_OK;
 }
 
 int sar_renderer_num_threads_for(const sar_renderer *r, uint64_t jobs_per_thread, uint64_t *num_threads)
 {
-    if (!r || !num_threads) return fail(SAR_ERR_INVALID, "NULL argument");
-    if (jobs_per_thread == 0) return fail(SAR_ERR_INVALID, "jobs_per_thread must be non-zero");
-    uint64_t n = 0;
-    for (size_t d = 0; d < r->devices.size(); ++d) n += renderer_threads_for(r, d, jobs_per_thread);
-    *num_threads = n;
-    return SAR_OK;
+    if (!num_threads) return fail(SAR_ERR_INVALID, "NULL argument");
+    return sar_renderer_plan(r, ~0ull, jobs_per_thread, num_threads, nullptr);
 }
 
 int sar_renderer_num_threads(const sar_renderer *r, uint64_t *num_threads)
@@ -899,7 +915,7 @@ int sar_render_parallel(sar_renderer *r, const sar_config *cfg_in, uint64_t jobs
     if (int rc = check_dims(cfg_in->width, cfg_in->height)) return rc;
     const size_t nd = r->devices.size();
     uint64_t num_threads = 0;
-    sar_renderer_num_threads_for(r, jobs_per_thread, &num_threads);
+    sar_renderer_plan(r, cfg_in->iterations, jobs_per_thread, &num_threads, nullptr);
     sar_config cfg = *cfg_in;
     cfg.iterations = cfg_in->iterations / num_threads / jobs_per_thread;        // lib.rs:1058
     const uint64_t total_jobs = jobs_per_thread * num_threads;                  // lib.rs:1062
@@ -914,7 +930,7 @@ int sar_render_parallel(sar_renderer *r, const sar_config *cfg_in, uint64_t jobs
     uint64_t first = 0;
     for (size_t d = 0; d < nd; ++d) {
         sar_runtime *rt = r->rts[d];
-        const uint32_t threads = renderer_threads_for(r, d, jobs_per_thread);
+        const uint32_t threads = renderer_threads_for(r, d, jobs_per_thread, cfg_in->iterations);
         const uint64_t n = (uint64_t)threads * jobs_per_thread;
         // explicit thread count: that many lanes, jobs_per_thread jobs each; auto: one lane per job
         const uint32_t lanes = r->threads_per_device ? threads : (uint32_t)(n < renderer_lanes(r, d) ? n : renderer_lanes(r, d));
@@ -996,7 +1012,7 @@ int sar_render_sequence(sar_renderer *r, const sar_config *cfg_in, const double 
     std::vector<uint64_t> jobs(nd);
     std::vector<sar_config> cfgs(nd, *cfg_in);
     for (size_t d = 0; d < nd; ++d) {
-        threads[d] = renderer_threads_for(r, d, jobs_per_thread);
+        threads[d] = renderer_threads_for(r, d, jobs_per_thread, cfg_in->iterations * nd);   // a whole frame per device
         jobs[d] = (uint64_t)threads[d] * jobs_per_thread;
         lanes[d] = r->threads_per_device ? threads[d] : (uint32_t)(jobs[d] < renderer_lanes(r, d) ? jobs[d] : renderer_lanes(r, d));
         cfgs[d].iterations = cfg_in->iterations / threads[d] / jobs_per_thread;

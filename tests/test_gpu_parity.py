@@ -374,3 +374,25 @@ def test_randomised_configs_bit_exact(S, oracle):
         oimg, of64 = oracle.colorize(cfg.to_pod(), ort, want_f64=True)
         _assert_image_close(img, f32, oimg, of64)
         rt.close()
+
+
+def test_small_renders_are_not_empty_in_auto_mode(S, oracle):
+    """A GPU has ~1e5 lanes; `iterations / num_threads / jobs_per_thread` (lib.rs:1058) must not
+    round a small frame to nothing.  Auto mode caps num_threads so each job keeps >= 64 steps."""
+    r = S.ParallelRenderer.new()
+    lanes = r.num_threads()
+    for iterations, jpt in ((100_000, 1), (1_000_000, 12), (2_000, 3)):
+        n, per_job = r.plan(iterations, jpt)
+        assert n % 32 == 0 and 32 <= n <= lanes and per_job == iterations // n // jpt
+        assert per_job >= 64 or n == 32
+        cfg = _small(S.Config.poisson_saturne(), 160, 120, iterations)
+        img = S.render_parallel(r, cfg, jpt, seed=3)
+        ocfg = cfg.to_pod()
+        ocfg.iterations = per_job
+        ort = oracle.Runtime(160, 120)
+        oracle.render_jobs(ocfg, ort, oracle.seed_points(3, 0, n * jpt))
+        assert int(ort.count.sum()) == per_job * n * jpt > 0
+        _assert_state_equal(r.runtime().download(), ort)
+        _assert_image_close(img, None, oracle.colorize(ocfg, ort), None)
+    assert r.plan(10**9, 1) == (lanes, 10**9 // lanes)          # large frames are unaffected
+    r.shutdown()
