@@ -78,3 +78,18 @@ def test_oracle_render_parallel_counts_match_sequential(oracle):
     assert np.array_equal(merged.zbuf, seq.zbuf)
     assert (merged.steps != seq.steps).mean() < 1e-3
     assert img.shape == (200, 180, 4)
+
+
+def test_angle_iter_follows_the_reference_cli():
+    """AngleIter (src/bin/main.rs:107-176): while curr + step/2 < end yield curr in RADIANS
+    (main.rs:166), curr += step; if nothing was yielded, the start value as is (main.rs:169-171)."""
+    import math
+
+    import strange_attractor_renderer_b200 as S
+
+    sweep = S.angle_iter(0.0, 360.0, 1.0)                      # BASELINE configs[4]: 360 frames
+    assert len(sweep) == 360 and sweep[0] == 0.0
+    assert all(sweep[k] == float(k) * math.pi / 180.0 for k in range(360))
+    assert S.angle_iter(10.0, 20.0, 4.0) == [a * math.pi / 180.0 for a in (10.0, 14.0)]   # 18 + 2 >= 20 stops
+    assert S.angle_iter(220.0, 220.0, 1.0) == [220.0]          # single image: passed through unconverted
+    assert S.angle_iter(5.0, 5.4, 1.0) == [5.0]
