@@ -158,8 +158,9 @@ __device__ __noinline__ void record_win(const IterParams *Pp, unsigned int idx, 
 {
     store_win(*Pp, idx, key, job_inv, old, false, px, py, pz, 0., 0., 0.);
 }
-// candidate given by delta and screen_space straight from the hot loop's registers (lib.rs:822-828)
-__device__ __noinline__ void record_win_direct(const IterParams *Pp, unsigned int idx, uint32_t key, uint32_t job_inv,
+// candidate given by delta and screen_space straight from the hot loop's registers (lib.rs:822-828).
+// Inlined into the loop: costs 2 registers and is 4-7 % faster than a call (profiles/r1_sweep.md).
+__device__ __forceinline__ void record_win_direct(const IterParams *Pp, unsigned int idx, uint32_t key, uint32_t job_inv,
                                                unsigned long long old, double dx, double dy, double dz,
                                                double sx, double sy, double sz)
 {
