@@ -13,9 +13,9 @@ for preset, W, H in (("poisson", 2048, 2048), ("solar", 1800, 2000), ("poisson",
     cfg.width, cfg.height = W, H
     if preset == "solar": cfg.angle = 3.839724354387525
     rt = C.c_void_p(); N.check(L.sar_runtime_new(W, H, 0, C.byref(rt)))
-    for mode in (0, 4):
+    for mode in [int(m) for m in os.environ.get("SWEEP_MODES", "0,4").split(",")]:
         N.check(L.sar_set_option(b"diagnostic_mode", mode))
-        for lanes_per_sm in (640, 768, 896, 1024, 1152):
+        for lanes_per_sm in [int(v) for v in os.environ.get("SWEEP_LANES", "640,768,896,1024,1152").split(",")]:
             lanes = 148 * lanes_per_sm
             pod = cfg.to_pod(); pod.iterations = ITERS // lanes
             ts = []
