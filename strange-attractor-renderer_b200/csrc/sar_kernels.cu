@@ -364,6 +364,7 @@ iterate_kernel(const __grid_constant__ IterParams P)
             }
             if (!dead) retire_range<0, NQ, NQ>(P, q, job_inv);
         }
+#pragma unroll 2
         for (; it < P.iterations && !dead; ++it) {                            // DEFER == 0, or the < NQ tail
             const double px = x, py = y, pz = z;
             unsigned int idx; uint32_t key; unsigned long long old;
