@@ -140,7 +140,6 @@ def run_reference(args):
 # GPU arm
 # --------------------------------------------------------------------------------------------
 def run_ours(args):
-    import numpy as np
     import torch
 
     import strange_attractor_renderer_b200 as S
