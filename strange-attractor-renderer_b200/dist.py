@@ -130,8 +130,6 @@ class Frame:
 
     def __init__(self, cfg, device: int, world: int, rank: int, group, lanes: int, jobs_per_thread: int,
                  iterations_per_gpu: int, seed: int):
-        import torch
-
         from . import _native as N
 
         self.N, self.L = N, N.lib()
