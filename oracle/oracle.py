@@ -101,6 +101,8 @@ def lib() -> C.CDLL:
         L.orc_runtime_merge.argtypes = [P(_OrcRuntime), P(_OrcRuntime)]
         L.orc_render.argtypes = [P(SarConfig), P(_OrcRuntime), dp, P(OrcStats)]
         L.orc_render_jobs.argtypes = [P(SarConfig), P(_OrcRuntime), dp, C.c_uint64, P(OrcStats)]
+        L.orc_render_jobs_mt.argtypes = [P(SarConfig), P(_OrcRuntime), dp, C.c_uint64, C.c_uint32, P(OrcStats)]
+        L.orc_render_jobs_mt.restype = C.c_int
         L.orc_colorize.argtypes = [P(SarConfig), P(_OrcRuntime), P(C.c_uint16), dp]
         L.orc_render_parallel.argtypes = [P(SarConfig), C.c_uint32, C.c_uint64, dp, P(C.c_uint16), P(P(_OrcRuntime))]
         L.orc_screen_bbox.argtypes = [P(SarConfig), dp, C.c_uint64, dp]
@@ -238,6 +240,17 @@ def render_jobs(cfg, rt: Runtime, init_xyz, stats: OrcStats | None = None) -> No
     pts = np.ascontiguousarray(init_xyz, dtype=np.float64).reshape(-1, 3)
     lib().orc_render_jobs(C.byref(cfg), rt._p, _dp(pts), pts.shape[0],
                           C.byref(stats) if stats is not None else None)
+
+
+def render_jobs_mt(cfg, rt: Runtime, init_xyz, n_threads: int = 0, stats: OrcStats | None = None) -> None:
+    """render_jobs on n_threads OS threads (0 = all cores); bit-identical to render_jobs (sar_oracle.c)."""
+    cfg = as_oracle_config(cfg)
+    pts = np.ascontiguousarray(init_xyz, dtype=np.float64).reshape(-1, 3)
+    if n_threads <= 0:
+        n_threads = os.cpu_count() or 8
+    if lib().orc_render_jobs_mt(C.byref(cfg), rt._p, _dp(pts), pts.shape[0], n_threads,
+                                C.byref(stats) if stats is not None else None) != 0:
+        raise RuntimeError("orc_render_jobs_mt failed")
 
 
 def colorize(cfg, rt: Runtime, want_f64: bool = False):

@@ -211,6 +211,103 @@ void orc_render_jobs(const sar_config *cfg, orc_runtime *rt, const double *init_
     for (uint64_t k = 0; k < n_jobs; ++k) orc_render(cfg, rt, init_xyz + 3 * k, st);
 }
 
+/* ---- the same n_jobs render() calls on n_threads OS threads, result identical to the serial loop ----
+ * Thread t renders the CONTIGUOUS job slice [t*n/T, (t+1)*n/T) in list order — thread 0 straight into
+ * `rt` (which may already hold earlier renders), the others into private reset Runtimes (as the
+ * reference's workers do, lib.rs:938-951) — and the caller merges them IN THREAD ORDER with
+ * Runtime::merge (lib.rs:708-738).  Counts add (commutative).  For z: each private Runtime holds, per
+ * pixel, the greatest z of its slice and, among equal z, the earliest iteration of the earliest job
+ * (strict `>`, lib.rs:821); merge's strict `>` (lib.rs:728) keeps the earlier slice on ties.  So the
+ * merged (zbuf, steps) are those of the serial run, bit for bit, whatever T is.  max: counts only
+ * grow, merge re-derives the running max from the summed counts (lib.rs:721-723).
+ * Stats: recorded / nan_iters are order-independent; z_wins / z_ties count the private passes. */
+typedef struct mt_worker {
+    const sar_config *cfg;
+    orc_runtime *rt;
+    const double *init_xyz;
+    uint64_t first, n;
+    orc_stats st;
+    pthread_t tid;
+} mt_worker;
+static void *mt_worker_main(void *arg)
+{
+    mt_worker *w = (mt_worker *)arg;
+    for (uint64_t k = 0; k < w->n; ++k) orc_render(w->cfg, w->rt, w->init_xyz + 3 * (w->first + k), &w->st);
+    return NULL;
+}
+typedef struct mt_merge {
+    orc_runtime *dst;
+    orc_runtime *const *src;      /* src[1..n_src) merged into dst, in order, over pixels [p0,p1) */
+    uint32_t n_src;
+    size_t p0, p1;
+    uint32_t max;
+    pthread_t tid;
+} mt_merge;
+static void *mt_merge_main(void *arg)  /* lib.rs:708-738 restricted to a pixel range; per-pixel independent */
+{
+    mt_merge *m = (mt_merge *)arg;
+    orc_runtime *a = m->dst;
+    uint32_t mx = 0;
+    for (uint32_t s = 1; s < m->n_src; ++s) {
+        const orc_runtime *b = m->src[s];
+        for (size_t i = m->p0; i < m->p1; ++i) {
+            a->count[i] += b->count[i];                        /* lib.rs:719 */
+            if (b->zbuf[i] > a->zbuf[i]) { a->steps[i] = b->steps[i]; a->zbuf[i] = b->zbuf[i]; }  /* lib.rs:728-735 */
+        }
+    }
+    for (size_t i = m->p0; i < m->p1; ++i) if (a->count[i] > mx) mx = a->count[i];   /* lib.rs:721-723 */
+    m->max = mx;
+    return NULL;
+}
+int orc_render_jobs_mt(const sar_config *cfg, orc_runtime *rt, const double *init_xyz, uint64_t n_jobs,
+                       uint32_t n_threads, orc_stats *st)
+{
+    if (n_threads == 0) return -1;
+    if ((uint64_t)n_threads > n_jobs) n_threads = (uint32_t)(n_jobs ? n_jobs : 1);
+    if (n_threads == 1) { orc_render_jobs(cfg, rt, init_xyz, n_jobs, st); return 0; }
+    mt_worker *ws = (mt_worker *)calloc(n_threads, sizeof *ws);
+    orc_runtime **rts = (orc_runtime **)calloc(n_threads, sizeof *rts);
+    mt_merge *ms = (mt_merge *)calloc(n_threads, sizeof *ms);
+    if (!ws || !rts || !ms) { free(ws); free(rts); free(ms); return -1; }
+    int rc = 0;
+    rts[0] = rt;
+    for (uint32_t t = 1; t < n_threads && rc == 0; ++t)
+        if (orc_runtime_new(rt->w, rt->h, &rts[t]) != 0) rc = -1;
+    uint32_t started = 0;
+    for (uint32_t t = 0; t < n_threads && rc == 0; ++t) {
+        ws[t].cfg = cfg; ws[t].rt = rts[t]; ws[t].init_xyz = init_xyz;
+        ws[t].first = n_jobs * t / n_threads;
+        ws[t].n = n_jobs * (t + 1) / n_threads - ws[t].first;
+        if (pthread_create(&ws[t].tid, NULL, mt_worker_main, &ws[t]) != 0) { rc = -1; break; }
+        ++started;
+    }
+    for (uint32_t t = 0; t < started; ++t) pthread_join(ws[t].tid, NULL);
+    if (rc == 0) {
+        /* merge in thread order; pixels are independent, so the pixel range is split over the threads */
+        const size_t npix = (size_t)rt->w * rt->h;
+        uint32_t m_started = 0;
+        for (uint32_t t = 0; t < n_threads; ++t) {
+            ms[t].dst = rt; ms[t].src = rts; ms[t].n_src = n_threads;
+            ms[t].p0 = npix * t / n_threads; ms[t].p1 = npix * (t + 1) / n_threads;
+            if (pthread_create(&ms[t].tid, NULL, mt_merge_main, &ms[t]) != 0) { rc = -1; break; }
+            ++m_started;
+        }
+        for (uint32_t t = 0; t < m_started; ++t) pthread_join(ms[t].tid, NULL);
+        if (rc == 0) {
+            uint32_t mx = rt->max;
+            for (uint32_t t = 0; t < n_threads; ++t) if (ms[t].max > mx) mx = ms[t].max;
+            rt->max = mx;
+            if (st) for (uint32_t t = 0; t < n_threads; ++t) {
+                st->recorded += ws[t].st.recorded; st->z_wins += ws[t].st.z_wins;
+                st->nan_iters += ws[t].st.nan_iters; st->z_ties += ws[t].st.z_ties;
+            }
+        }
+    }
+    for (uint32_t t = 1; t < n_threads; ++t) orc_runtime_free(rts[t]);
+    free(ws); free(rts); free(ms);
+    return rc;
+}
+
 /* ---- colorize(), lib.rs:841-904 ------------------------------------------- */
 void orc_colorize(const sar_config *cfg, const orc_runtime *rt, uint16_t *out, double *out_f64)
 {

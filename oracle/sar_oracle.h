@@ -81,6 +81,13 @@ void orc_render(const sar_config *cfg, orc_runtime *rt, const double init[3], or
  * of the image", lib.rs:742-743) — the sequential semantics the GPU matches. */
 void orc_render_jobs(const sar_config *cfg, orc_runtime *rt, const double *init_xyz,
                      uint64_t n_jobs, orc_stats *stats);
+/* The same n_jobs render() calls, computed on n_threads OS threads (contiguous job slices into
+ * private Runtimes, merged in thread order with Runtime::merge): bit-identical to orc_render_jobs
+ * for count, zbuf, steps and max, whatever n_threads is — see the proof sketch in sar_oracle.c.
+ * It exists so that the BASELINE configurations (1e9 iterations) can be checked at full size.
+ * Returns 0, or -1 on allocation / thread failure. */
+int orc_render_jobs_mt(const sar_config *cfg, orc_runtime *rt, const double *init_xyz,
+                       uint64_t n_jobs, uint32_t n_threads, orc_stats *stats);
 /* colorize(), lib.rs:841-904.  rgba_f64 (optional) gets the pre-cast values. */
 void orc_colorize(const sar_config *cfg, const orc_runtime *rt, uint16_t *rgba_u16,
                   double *rgba_f64);
