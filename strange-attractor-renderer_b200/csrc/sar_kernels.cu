@@ -103,28 +103,17 @@ __device__ __forceinline__ double transform_ds(const IterParams &P, double dx, d
     const double color = __dmul_rn(__dadd_rn(part, mag), 0.5);               // `/ 2.`, lib.rs:556
     return __ddiv_rn(__dsub_rn(color, 0.1), 0.9);                            // lib.rs:557
 }
-// Same, re-derived from the point BEFORE the step (used by the deferred-test variants): the same
-// instructions on the same inputs give the same bits as the hot loop.
-__device__ __forceinline__ double transform_value(const IterParams &P, double px, double py, double pz)
-{
-    double nx, ny, nz;
-    SAR_NEXT_POINT(P, px, py, pz, nx, ny, nz);
-    const double sx = __dadd_rn(__dadd_rn(__dmul_rn(P.m[0][0], nx), __dmul_rn(P.m[0][1], ny)), __dmul_rn(P.m[0][2], nz));
-    const double sy = __dadd_rn(__dadd_rn(__dmul_rn(P.m[1][0], nx), __dmul_rn(P.m[1][1], ny)), __dmul_rn(P.m[1][2], nz));
-    const double sz = __dadd_rn(__dadd_rn(__dmul_rn(P.m[2][0], nx), __dmul_rn(P.m[2][1], ny)), __dmul_rn(P.m[2][2], nz));
-    return transform_ds(P, __dsub_rn(nx, px), __dsub_rn(ny, py), __dsub_rn(nz, pz), sx, sy, sz);   // delta, lib.rs:822
-}
-
 // The winning branch of the depth test (lib.rs:821-833), off the hot loop.
 //   value = color_transform.transform(delta, screen_space, view)   lib.rs:826-828
 //   steps[idx] = value; zbuf[idx] = z2 as f32                       lib.rs:830-832
 // made atomic and order-independent: the record is replaced iff (zkey, ~job) is strictly
-// greater than the stored one.  The candidate comes either straight from the hot loop's registers
-// (direct: delta in a0..a2, screen_space in sx..sz) or as the point before the step (a0..a2),
-// from which it is re-derived.
-__device__ __forceinline__ void store_win(const IterParams &P, unsigned int idx, uint32_t key, uint32_t job_inv,
-                                          unsigned long long old, bool direct, double a0, double a1, double a2,
-                                          double sx, double sy, double sz)
+// greater than the stored one.  The candidate comes straight from the hot loop's registers
+// (delta = current - previous point, lib.rs:822; screen_space, lib.rs:773).  `key` is the
+// canonical key (-0.0 compares equal to +0.0, as f32 `>` does); the record keeps the sign of a
+// zero z in REC_NEG_ZERO so that zbuf reads back -0.0 exactly where the reference stores it.
+__device__ __forceinline__ void record_win(const IterParams &P, unsigned int idx, uint32_t key, bool neg_zero, uint32_t job_inv,
+                                           unsigned long long old, double dx, double dy, double dz,
+                                           double sx, double sy, double sz)
 {
     const unsigned long long hi = ((unsigned long long)key << 32) | job_inv;
     ulonglong2 *r = P.rec + idx;
@@ -144,27 +133,15 @@ __device__ __forceinline__ void store_win(const IterParams &P, unsigned int idx,
         const unsigned long long want = ((unsigned long long)key << 32) | (expect & 0xFFFFFFFFull);
         if ((uint32_t)(expect >> 32) < key) (void)atomicCAS(P.fast + slot_of(idx, P.slots), expect, want);
     }
-    const double value = direct ? transform_ds(P, a0, a1, a2, sx, sy, sz) : transform_value(P, a0, a1, a2);
-    const ulonglong2 want = make_ulonglong2((unsigned long long)__double_as_longlong(value), hi);
-    while (hi > cur.y) {
+    const double value = transform_ds(P, dx, dy, dz, sx, sy, sz);
+    // steps of a record is an f64 and zbuf an f32: the sign of a zero z rides in the record's low word
+    // (bit 0 of .x is part of `value`, so it goes to .y: the job key keeps 31 bits + this flag — see rec_order)
+    const ulonglong2 want = make_ulonglong2((unsigned long long)__double_as_longlong(value), neg_zero ? rec_with_neg_zero(hi) : hi);
+    while (rec_order(want.y) > rec_order(cur.y)) {
         const ulonglong2 prev = cas128(r, cur, want);
         if (prev.x == cur.x && prev.y == cur.y) break;
         cur = prev;
     }
-}
-// candidate given by the point before the step (deferred-test variants)
-__device__ __noinline__ void record_win(const IterParams *Pp, unsigned int idx, uint32_t key, uint32_t job_inv,
-                                        unsigned long long old, double px, double py, double pz)
-{
-    store_win(*Pp, idx, key, job_inv, old, false, px, py, pz, 0., 0., 0.);
-}
-// candidate given by delta and screen_space straight from the hot loop's registers (lib.rs:822-828).
-// Inlined into the loop: costs 2 registers and is 4-7 % faster than a call (profiles/r1_sweep.md).
-__device__ __forceinline__ void record_win_direct(const IterParams *Pp, unsigned int idx, uint32_t key, uint32_t job_inv,
-                                               unsigned long long old, double dx, double dy, double dz,
-                                               double sx, double sy, double sz)
-{
-    store_win(*Pp, idx, key, job_inv, old, true, dx, dy, dz, sx, sy, sz);
 }
 
 // Everything that is not a plain in-view hit: out of view, non-finite coordinates, and the

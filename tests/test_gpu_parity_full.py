@@ -89,4 +89,5 @@ def test_more_than_2_pow_23_pixels_layout(S, oracle):
     cfg.width, cfg.height, cfg.iterations, cfg.transparent = 4096, 2049, 200_000_000, True
     assert cfg.width * cfg.height > (1 << 23)
     n, per_job, st, count, mx = _check_frame(S, oracle, cfg, seed=99)
-    assert st.recorded == n * per_job
+    # the frame is wider than tall, so part of the attractor falls outside it (lib.rs:789)
+    assert 0.5 * n * per_job < st.recorded == int(count.sum(dtype=np.uint64)) < n * per_job
