@@ -105,11 +105,12 @@ int         sar_device_count(int *count);    /* SAR_ERR_CUDA when no driver/devi
 /* Default number of concurrent trajectory lanes on `device` (SM count × 896):
  * the GPU's answer to available_parallelism(), lib.rs:920-922. */
 int         sar_default_threads(int device, uint32_t *threads);
-/* Tuning knobs that never change results.  "defer": depth (0..4) of the iterate
- * kernel's deferred depth-test queue (default 0, env SAR_DEFER).
- * "diagnostic_mode": 0 = product path (default); 1..7 run the iterate kernel
- * with parts of the scatter removed or replaced, for roofline experiments only
- * — their results are incomplete by design (tools/sweep_iterate.py). */
+/* Options.  "traj_per_thread" (1, 2 or 4): how many trajectories one GPU thread
+ * carries side by side in the iterate kernel — a tuning knob that never changes
+ * results.  "diagnostic_mode": the product library accepts only 0;
+ * the roofline-experiment variants of the iterate kernel (incomplete results by
+ * design) exist only in the separately built libsar_b200_diag.so
+ * (-DSAR_DIAGNOSTICS, tools/sweep_iterate.py) — SAR_ERR_UNSUPPORTED here. */
 int         sar_set_option(const char *name, int64_t value);
 
 /* ---- Config presets --------------------------------------------------- */
@@ -228,8 +229,11 @@ int  sar_renderer_runtime(sar_renderer *r, sar_runtime **rt);
  * (NULL = the runtime's own stream); *_async calls do not synchronise.
  * `threads` = concurrent trajectory lanes (0 = default, sar_default_threads);
  * lane L runs jobs L, L+threads, ... one after the other.
- * Order key of job k of a call = job_base + first_job + k (see
- * sar_runtime_set_job_base); earlier keys keep exact z ties. */
+ * `first_job` positions the call in the seed stream only.  Order key of job k
+ * of a call = job_base + k, and the call advances job_base by n_jobs
+ * (sar_runtime_set_job_base; reset() zeroes it); earlier keys keep exact z
+ * ties.  Keys are 32-bit: a call that would pass 2^32 jobs since the last reset
+ * fails with SAR_ERR_INVALID instead of letting late jobs share a key. */
 int sar_render_seeded_async(const sar_config *cfg, sar_runtime *rt, uint64_t seed,
                             uint64_t first_job, uint64_t n_jobs, uint32_t threads,
                             void *stream);
@@ -252,7 +256,8 @@ int sar_colorize_rows_async(const sar_config *cfg, sar_runtime *rt, uint32_t row
 int sar_runtime_image_download(sar_runtime *rt, uint32_t row0, uint32_t rows, uint16_t *rgba_u16,
                                void *stream);
 int sar_stream_synchronize(sar_runtime *rt, void *stream);
-/* job order counter of the runtime (reset() zeroes it) */
+/* job order counter of the runtime (reset() zeroes it).  A multi-rank frame sets it to the
+ * rank's first global job index before rendering, so that keys are global over the ranks. */
 int sar_runtime_get_job_base(const sar_runtime *rt, uint64_t *job_base);
 int sar_runtime_set_job_base(sar_runtime *rt, uint64_t job_base);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */

@@ -8,6 +8,8 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 OUT = os.path.join(_HERE, "libsar_b200.so")
+# the same sources with -DSAR_DIAGNOSTICS: roofline-experiment variants of the iterate kernel, for tools/ only
+OUT_DIAG = os.path.join(_HERE, "libsar_b200_diag.so")
 SOURCES = ["sar_kernels.cu", "sar_abi.cu"]
 HEADERS = ["sar_device.cuh", os.path.join("..", "..", "include", "sar.h")]
 
@@ -35,10 +37,14 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
-        return OUT
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES]
+def build(force: bool = False, verbose: bool = False, diagnostics: bool = False, defines=()) -> str:
+    out = OUT_DIAG if diagnostics else OUT
+    if not force and not diagnostics and not needs_build():
+        return out
+    cmd = [_nvcc(), *NVCC_FLAGS, "-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
+    if diagnostics:
+        cmd += ["-DSAR_DIAGNOSTICS"]
+    cmd += [f"-D{d}" for d in defines]
     if verbose:
         cmd += ["-Xptxas", "-v"]
     r = subprocess.run(cmd, capture_output=True, text=True)
@@ -46,7 +52,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
     if verbose:
         print(r.stderr)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":

@@ -238,13 +238,18 @@ uint64_t sar_launch_count(void) { return launch_count(); }
 int sar_set_option(const char *name, int64_t value)
 {
     if (!name) return fail(SAR_ERR_INVALID, "name is NULL");
-    if (strcmp(name, "defer") == 0) {
-        if (!set_defer((int)value)) return fail(SAR_ERR_INVALID, "defer must be in 0..4");
+    if (strcmp(name, "traj_per_thread") == 0) {
+        if (!set_traj_per_thread((int)value)) return fail(SAR_ERR_INVALID, "traj_per_thread must be 1, 2 or 4");
         return SAR_OK;
     }
     if (strcmp(name, "diagnostic_mode") == 0) {
-        if (!set_mode((int)value)) return fail(SAR_ERR_INVALID, "diagnostic_mode must be in 0..7");
+#ifdef SAR_DIAGNOSTICS
+        if (!set_mode((int)value)) return fail(SAR_ERR_INVALID, "diagnostic_mode must be 0, 1, 2 or 4");
         return SAR_OK;
+#else
+        if (value == 0) return SAR_OK;
+        return fail(SAR_ERR_UNSUPPORTED, "this build has no diagnostic kernels (build with -DSAR_DIAGNOSTICS: libsar_b200_diag.so)");
+#endif
     }
     return fail(SAR_ERR_INVALID, "unknown option '%s'", name);
 }
@@ -503,12 +508,17 @@ static int render_launch(const sar_config *cfg, sar_runtime *rt, const double *d
     make_iter_params(cfg, rt, p);
     p.init = d_init; p.seed = seed; p.first_job = first_job; p.n_jobs = n_jobs;
     if (init_is_warm) p.warmup = 0;
-    const uint64_t key0 = rt->job_base + first_job;
-    p.job_key0 = key0 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (unsigned int)key0;
+    // Order keys (who keeps an exact z tie): this call's job k gets key job_base + k — independent of
+    // first_job, which only positions the call in the seed stream.  32-bit keys: refuse rather than
+    // let late jobs share a key (ties between them would then resolve by scheduling order).
+    if (rt->job_base + n_jobs > (1ull << 32))
+        return fail(SAR_ERR_INVALID, "job order keys exhausted (%llu jobs since the last reset, 2^32 at most): reset or "
+                    "download/upload the Runtime", (unsigned long long)rt->job_base);
+    p.job_key0 = (unsigned int)rt->job_base;
     launch_iterate(p, threads ? threads : default_lanes(rt), s);
     SAR_CUDA(cudaGetLastError());
     rt->host_max_valid = false;
-    rt->job_base = key0 + n_jobs;
+    rt->job_base += n_jobs;
     return SAR_OK;
 }
 
@@ -934,7 +944,7 @@ int sar_render_parallel(sar_renderer *r, const sar_config *cfg_in, uint64_t jobs
         const uint64_t n = (uint64_t)threads * jobs_per_thread;
         // explicit thread count: that many lanes, jobs_per_thread jobs each; auto: one lane per job
         const uint32_t lanes = r->threads_per_device ? threads : (uint32_t)(n < renderer_lanes(r, d) ? n : renderer_lanes(r, d));
-        rt->job_base = 0;
+        rt->job_base = first;                      // global order keys: device d's jobs follow device d-1's
         if (init_xyz) {
             SAR_CUDA(cudaSetDevice(rt->device));
             if (int rc = upload_init(rt, init_xyz + 3 * first, n, rt->stream)) return rc;

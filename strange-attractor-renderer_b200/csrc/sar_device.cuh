@@ -32,6 +32,15 @@ namespace sar {
 __host__ __device__ inline uint32_t zkey_from_bits(uint32_t b) { return (b & 0x80000000u) ? ~b : (b | 0x80000000u); }
 __host__ __device__ inline uint32_t zbits_from_key(uint32_t k) { return (k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k; }
 
+// f32 compare of two keys: -0.0 == +0.0.  canon_key folds zkey(-0.0) onto zkey(+0.0); rec_order does
+// the same on a record's high word (zkey << 32 | ~job), so records compare as (z, earlier job) with
+// the reference's notion of "z strictly greater" (lib.rs:728, 821).  Hints always hold canonical keys.
+__host__ __device__ inline uint32_t canon_key(uint32_t k) { return k == 0x7FFFFFFFu ? 0x80000000u : k; }
+__host__ __device__ inline unsigned long long rec_order(unsigned long long y)
+{
+    return (uint32_t)(y >> 32) == 0x7FFFFFFFu ? y + (1ull << 32) : y;
+}
+
 // pixel index -> slot of the `fast` array (see the layout comment above)
 struct SlotMap { uint32_t mult, mask; };
 constexpr uint32_t SLOT_SCRAMBLE = 0x9E3779B1u;
@@ -40,6 +49,7 @@ __host__ __device__ inline uint32_t slot_of(uint32_t idx, SlotMap m) { return (i
 constexpr uint32_t ZKEY_SENTINEL = 0x407FFFFFu;   // zkey(-1.0f): Runtime::reset fills zbuf with -1.0 (lib.rs:693)
 constexpr uint32_t ZKEY_POS_INF  = 0xFF800000u;   // zkey(+inf); +NaN keys are larger, -NaN keys are < zkey(-inf)
 constexpr uint32_t ZKEY_ZERO     = 0x80000000u;   // zkey(+0.0f)
+constexpr uint32_t ZKEY_NEG_ZERO = 0x7FFFFFFFu;   // zkey(-0.0f): directly below ZKEY_ZERO, but f32 `>` sees the two zeros equal
 constexpr uint32_t ZKEY_FLT_MAX  = 0xFF7FFFFFu;   // zkey(f32::MAX)
 constexpr unsigned long long FAST_RESET = (unsigned long long)(ZKEY_SENTINEL + 1u) << 32;  // count 0, hint just above the sentinel
 constexpr unsigned long long REC_HI_RESET = ((unsigned long long)ZKEY_SENTINEL << 32) | 0xFFFFFFFFull;
@@ -135,7 +145,7 @@ void launch_wait(Scalars *mine, int kind, int n_ranks, unsigned int epoch, cudaS
 void launch_publish_max(Scalars *mine, const ScalList &targets, int my_rank, unsigned int epoch, cudaStream_t s);
 void launch_gather_max(Scalars *mine, int n_ranks, cudaStream_t s);
 unsigned long long launch_count();
-bool set_mode(int mode);     // diagnostics: 0 = product path; 1..3 = roofline experiments (incomplete results)
-bool set_defer(int depth);   // tuning: depth of the deferred depth-test queue (0..4)
+bool set_mode(int mode);     // SAR_DIAGNOSTICS builds only: 0 = product path; 1, 2, 4 = roofline experiments (incomplete results)
+bool set_traj_per_thread(int nt);   // tuning: trajectories carried per thread (1, 2 or 4); never changes results
 
 }  // namespace sar

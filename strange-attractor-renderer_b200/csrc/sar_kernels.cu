@@ -8,7 +8,10 @@
 #include "sar_device.cuh"
 
 #include <atomic>
-#include <cstdlib>
+
+#ifndef SAR_DEFAULT_NT
+#define SAR_DEFAULT_NT 2
+#endif
 
 namespace sar {
 
@@ -109,13 +112,19 @@ __device__ __forceinline__ double transform_ds(const IterParams &P, double dx, d
 // made atomic and order-independent: the record is replaced iff (zkey, ~job) is strictly
 // greater than the stored one.  The candidate comes straight from the hot loop's registers
 // (delta = current - previous point, lib.rs:822; screen_space, lib.rs:773).  `key` is the
-// canonical key (-0.0 compares equal to +0.0, as f32 `>` does); the record keeps the sign of a
-// zero z in REC_NEG_ZERO so that zbuf reads back -0.0 exactly where the reference stores it.
-__device__ __forceinline__ void record_win(const IterParams &P, unsigned int idx, uint32_t key, bool neg_zero, uint32_t job_inv,
+// canonical key (-0.0 already folded onto +0.0, which is how f32 `>` sees them); the record itself
+// keeps zkey(-0.0) so that zbuf reads back -0.0 exactly where the reference stores it, and records
+// are ordered with rec_order(), which folds the two zeros again.
+__device__ __forceinline__ void record_win(const IterParams &P, unsigned int idx, uint32_t key, uint32_t job_inv,
                                            unsigned long long old, double dx, double dy, double dz,
                                            double sx, double sy, double sz)
 {
-    const unsigned long long hi = ((unsigned long long)key << 32) | job_inv;
+    unsigned long long hi = ((unsigned long long)key << 32) | job_inv;
+    if (key == ZKEY_ZERO) {
+        // z2 as f32 is +0.0 or -0.0; which one is not kept by the hot loop: redo lib.rs:778-779 from screen_space
+        const double z2 = __dsub_rn(__dmul_rn(__dadd_rn(sx, P.ccx), P.sv), __dmul_rn(__dadd_rn(sz, P.ccy), P.cv));
+        if (__float_as_uint(__double2float_rn(z2)) == 0x80000000u) hi = ((unsigned long long)ZKEY_NEG_ZERO << 32) | job_inv;
+    }
     ulonglong2 *r = P.rec + idx;
     // Current record: known without a load if the pixel was untouched when our atomic hit it,
     // otherwise loaded now (may be stale or torn — the CAS validates it) so that the round trip
@@ -134,9 +143,7 @@ __device__ __forceinline__ void record_win(const IterParams &P, unsigned int idx
         if ((uint32_t)(expect >> 32) < key) (void)atomicCAS(P.fast + slot_of(idx, P.slots), expect, want);
     }
     const double value = transform_ds(P, dx, dy, dz, sx, sy, sz);
-    // steps of a record is an f64 and zbuf an f32: the sign of a zero z rides in the record's low word
-    // (bit 0 of .x is part of `value`, so it goes to .y: the job key keeps 31 bits + this flag — see rec_order)
-    const ulonglong2 want = make_ulonglong2((unsigned long long)__double_as_longlong(value), neg_zero ? rec_with_neg_zero(hi) : hi);
+    const ulonglong2 want = make_ulonglong2((unsigned long long)__double_as_longlong(value), hi);
     while (rec_order(want.y) > rec_order(cur.y)) {
         const ulonglong2 prev = cas128(r, cur, want);
         if (prev.x == cur.x && prev.y == cur.y) break;
@@ -160,196 +167,125 @@ __device__ __noinline__ unsigned long long classify_rare(double fi, double fj, u
 }
 
 // ---------------------------------------------------------------------------------------------
-// iterate → project → scatter: render() (lib.rs:747-838), one lane per trajectory.
-// Lane L runs jobs L, L+lanes, L+2*lanes, ...; each job is one reference render() call:
-// start point, 1000 warm-up steps (lib.rs:750-752), `iterations` recorded steps.
+// iterate → project → scatter: render() (lib.rs:747-838).
+// One LANE = one trajectory = one reference render() call (a job): start point, 1000 warm-up steps
+// (lib.rs:750-752), `iterations` recorded steps.  A THREAD carries NT lanes at once (jobs tid,
+// tid + nthreads, ...): their arithmetic is written branch-free and side by side so that the
+// compiler interleaves the NT dependency chains and every constant fetched from the parameter
+// bank (47 f64: coefficients, rotation matrix, projection scalars — they do not fit the uniform
+// register file, so each iteration re-fetches them) feeds NT multiplications instead of one.
 //
-// DEFER (tuning knob, default 0): the depth test needs the value the L2 atomic returns (~1000
-// cycles under load).  With DEFER > 0 the test for iteration n is made DEFER iterations later,
-// from a small register queue {point before the step, pixel, z key, atomic result}; entries
-// retire in order, so within a job the earlier iteration still wins exact z ties.  Measured: no
-// gain — the limit is the rate of atomics with return, not their latency (profiles/r1_sweep.md).
+// MODE (only in SAR_DIAGNOSTICS builds; the product library holds MODE 0 alone): 1 = arithmetic
+// only (no memory traffic); 2 = count with a fire-and-forget reduction, no depth test; 4 = the
+// product's atomic with the win path removed.  Modes != 0 leave the Runtime in a state that is
+// only good for timing (tools/sweep_iterate.py).
 // ---------------------------------------------------------------------------------------------
-// One recorded iteration up to (and including) the count atomic.  In: the current point.
-// Out: the next point in (x,y,z); act 0 = out of view, 1 = recorded at idx with the atomic's
-// return value in `old` and the candidate depth key in `key` (0 = cannot win), 2 = NaN state.
-// MODE is a diagnostic switch for roofline experiments (tools/sweep_iterate.py, sweep_lanes.py);
-// only MODE 0 is the product.  1 = arithmetic only (no memory traffic); 2 = count with a
-// fire-and-forget reduction, no depth test; 3 / 6 = reduction + 4-byte load of the hint (ld.cg /
-// ld.ca); 4 = the product's atomic with the win path removed; 5 = two reductions (count add +
-// packed z max); 7 = like 4 on the unscrambled pixel -> slot map.  Modes != 0 leave the Runtime
-// in a state that is only good for timing.
-template <int MODE>
-__device__ __forceinline__ int step_point(const IterParams &P, double &x, double &y, double &z,
-                                          unsigned int &idx, uint32_t &key, unsigned long long &old,
-                                          double &sx, double &sy, double &sz)
-{
-    double nx, ny, nz;
-    SAR_NEXT_POINT(P, x, y, z, nx, ny, nz);                                   // lib.rs:770
-    // screen_space = rotation_matrix.mul_right(current_point), lib.rs:773 / 208-215
-    sx = __dadd_rn(__dadd_rn(__dmul_rn(P.m[0][0], nx), __dmul_rn(P.m[0][1], ny)), __dmul_rn(P.m[0][2], nz));
-    sy = __dadd_rn(__dadd_rn(__dmul_rn(P.m[1][0], nx), __dmul_rn(P.m[1][1], ny)), __dmul_rn(P.m[1][2], nz));
-    sz = __dadd_rn(__dadd_rn(__dmul_rn(P.m[2][0], nx), __dmul_rn(P.m[2][1], ny)), __dmul_rn(P.m[2][2], nz));
-    // rotate around center_camera, lib.rs:776-779 (center_camera.y pairs with screen_space.z)
-    const double a = __dadd_rn(sx, P.ccx);
-    const double b = __dadd_rn(sz, P.ccy);
-    const double x2 = __dadd_rn(__dmul_rn(a, P.cv), __dmul_rn(b, P.sv));
-    const double z2 = __dsub_rn(__dmul_rn(a, P.sv), __dmul_rn(b, P.cv));
-    const double fi = __dmul_rn(__dsub_rn(P.sam, x2), P.ws);                       // lib.rs:783
-    const double fj = __dsub_rn(P.half_h, __dmul_rn(__dadd_rn(sy, P.ccz), P.ws));  // lib.rs:786
-    // Bounds test + `as u32` (lib.rs:789-802) for the common case in one step: floor-convert
-    // (saturating) and compare unsigned.  i in [0,W) <=> 0 <= floor(i) < W, and floor == trunc
-    // there.  Anything else — out of view, NaN, pixel 0 — takes classify_rare(), which applies
-    // the reference's comparisons literally.
-    const unsigned int ii = (unsigned int)__double2int_rd(fi);
-    const unsigned int jj = (unsigned int)__double2int_rd(fj);
-    idx = jj * P.W + ii;
-    int act = 1;
-    if (!(ii < P.W && jj < P.H) || idx == 0u) {
-        const unsigned long long r = classify_rare(fi, fj, P.W, P.H, nx, ny, nz);
-        act = (int)(r >> 32);
-        idx = (unsigned int)r;
-    }
-    key = 0u;
-    old = ~0ull;
-    if (act == 1) {
-        const unsigned int slot = slot_of(idx, P.slots);
-        if (MODE == 0) {
-            old = atomicAdd(P.fast + slot, 1ull);     // count += 1 (lib.rs:811) + fetch the depth hint, one L2 atomic
-        } else if (MODE == 1) {
-            old = ~0ull ^ (unsigned long long)(idx == 0xFFFFFFFFu);
-        } else if (MODE == 2) {
-            asm volatile("red.global.add.u64 [%0], 1;" ::"l"(P.fast + idx) : "memory");
-        } else if (MODE == 3) {
-            asm volatile("red.global.add.u64 [%0], 1;" ::"l"(P.fast + idx) : "memory");
-            old = (unsigned long long)__ldcg(reinterpret_cast<const unsigned int *>(P.fast + idx) + 1) << 32;
-        } else if (MODE == 7) {                     // natural (unscrambled) pixel -> address map, for comparison
-            old = atomicAdd(P.fast + idx, 1ull);
-        } else if (MODE == 4) {
-            old = atomicAdd(P.fast + slot, 1ull);
-        } else if (MODE == 5) {
-            asm volatile("red.global.add.u64 [%0], 1;" ::"l"(P.fast + idx) : "memory");
-        } else if (MODE == 6) {
-            asm volatile("red.global.add.u64 [%0], 1;" ::"l"(P.fast + idx) : "memory");
-            unsigned int h;
-            asm volatile("ld.global.ca.u32 %0, [%1];" : "=r"(h) : "l"(reinterpret_cast<const unsigned int *>(P.fast + idx) + 1));
-            old = (unsigned long long)h << 32;
-        }
-        const float zf = __double2float_rn(z2) + 0.0f;                        // `z2 as f32`; -0 -> +0
-        key = zkey_of(zf);
-        if (key > ZKEY_POS_INF) key = 0u;                                     // NaN never passes `>` (lib.rs:821)
-        if (MODE == 5) {
-            const unsigned long long packed = ((unsigned long long)key << 32) | idx;
-            asm volatile("red.global.max.u64 [%0], %1;" ::"l"(&P.rec[idx].y), "l"(packed) : "memory");
-            key = 0u;
-        }
-        if (MODE == 4 || MODE == 7) {                 // keep the returned value live, never take the slow path
-            if (key >= (uint32_t)(old >> 32) && key != 0u && idx == 0xFFFFFFF0u) P.scal->pad = key;
-            key = 0u;
-        }
-    }
-    x = nx; y = ny; z = nz;                           // previous_point = current_point, lib.rs:793/836
-    return act;
-}
-
-// Register queue of pending depth tests (struct of arrays; every index is a template constant,
-// so the whole queue stays in registers).
-template <int NQ>
-struct Queue {
-    double x[NQ], y[NQ], z[NQ];       // the point BEFORE the step (previous_point, lib.rs:766/836)
-    unsigned long long old[NQ];       // what the atomic returned: zhint << 32 | count
-    unsigned int idx[NQ];
-    uint32_t key[NQ];                 // 0 = nothing to test (the hint is never 0)
-};
-
-template <int K, int END, int NQ>
-__device__ __forceinline__ void retire_range(const IterParams &P, const Queue<NQ> &q, uint32_t job_inv)
-{
-    if constexpr (K < END) {
-        if (q.key[K] >= (uint32_t)(q.old[K] >> 32) && q.key[K] != 0u)        // may beat zbuf, lib.rs:821
-            record_win(&P, q.idx[K], q.key[K], job_inv, q.old[K], q.x[K], q.y[K], q.z[K]);
-        retire_range<K + 1, END, NQ>(P, q, job_inv);
-    }
-}
-
-// NQ consecutive iterations; slot J holds the entry of NQ iterations ago.  Returns true when the
-// trajectory went NaN (queue drained oldest-first, debt paid): the job is over.
-template <int J, int NQ, int MODE>
-__device__ __forceinline__ bool group_steps(const IterParams &P, Queue<NQ> &q, double &x, double &y, double &z,
-                                            unsigned long long it, uint32_t job_inv)
-{
-    if constexpr (J < NQ) {
-        const double px = x, py = y, pz = z;
-        unsigned int idx; uint32_t key; unsigned long long old;
-        double sx, sy, sz;
-        const int act = step_point<MODE>(P, x, y, z, idx, key, old, sx, sy, sz);
-        if (act == 2) {
-            atomicAdd(&P.scal->nan_sink, P.iterations - (it + J));            // pay the whole debt at once
-            retire_range<J, NQ, NQ>(P, q, job_inv);
-            retire_range<0, J, NQ>(P, q, job_inv);
-            return true;
-        }
-        retire_range<J, J + 1, NQ>(P, q, job_inv);                            // the test of NQ iterations ago
-        q.x[J] = px; q.y[J] = py; q.z[J] = pz; q.old[J] = old; q.idx[J] = idx; q.key[J] = key;
-        return group_steps<J + 1, NQ, MODE>(P, q, x, y, z, it, job_inv);
-    } else {
-        return false;
-    }
-}
-
-template <int K, int NQ>
-__device__ __forceinline__ void clear_queue(Queue<NQ> &q)
-{
-    if constexpr (K < NQ) {
-        q.key[K] = 0u; q.old[K] = ~0ull; q.idx[K] = 0u; q.x[K] = q.y[K] = q.z[K] = 0.;
-        clear_queue<K + 1, NQ>(q);
-    }
-}
-
-template <int DEFER, int MODE>
+template <int NT, int MODE>
 __global__ void __launch_bounds__(128)
 iterate_kernel(const __grid_constant__ IterParams P)
 {
-    constexpr int NQ = DEFER > 0 ? DEFER : 1;
-    const unsigned long long lanes = (unsigned long long)gridDim.x * blockDim.x;
-    for (unsigned long long job = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; job < P.n_jobs; job += lanes) {
-        double x, y, z;
-        if (P.init != nullptr) {
-            x = P.init[3 * job + 0]; y = P.init[3 * job + 1]; z = P.init[3 * job + 2];
-        } else {
-            const unsigned long long g = 3ull * (P.first_job + job);
-            x = seed_coord(P.seed, g); y = seed_coord(P.seed, g + 1); z = seed_coord(P.seed, g + 2);
+    const unsigned long long nthreads = (unsigned long long)gridDim.x * blockDim.x;
+    const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (unsigned long long job0 = tid; job0 < P.n_jobs; job0 += nthreads * NT) {
+        double x[NT], y[NT], z[NT];
+        uint32_t job_inv[NT];
+        bool live[NT];
+#pragma unroll
+        for (int k = 0; k < NT; ++k) {
+            const unsigned long long job = job0 + (unsigned long long)k * nthreads;
+            live[k] = job < P.n_jobs;
+            x[k] = y[k] = z[k] = 0.;
+            if (live[k]) {
+                if (P.init != nullptr) {
+                    x[k] = P.init[3 * job + 0]; y[k] = P.init[3 * job + 1]; z[k] = P.init[3 * job + 2];
+                } else {
+                    const unsigned long long g = 3ull * (P.first_job + job);
+                    x[k] = seed_coord(P.seed, g); y[k] = seed_coord(P.seed, g + 1); z[k] = seed_coord(P.seed, g + 2);
+                }
+            }
+            // order key of this job: earlier jobs win z ties (see sar_device.cuh); the host
+            // guarantees job_key0 + n_jobs <= 2^32
+            job_inv[k] = 0xFFFFFFFFu - (P.job_key0 + (uint32_t)job);
         }
         for (unsigned int w = 0; w < P.warmup; ++w) {                         // lib.rs:750-752
-            double nx, ny, nz;
-            SAR_NEXT_POINT(P, x, y, z, nx, ny, nz);
-            x = nx; y = ny; z = nz;
-        }
-        // order key of this job: earlier jobs win z ties (see sar_device.cuh)
-        const unsigned long long jk = (unsigned long long)P.job_key0 + job;
-        const uint32_t job_inv = 0xFFFFFFFFu - (uint32_t)(jk > 0xFFFFFFFFull ? 0xFFFFFFFFull : jk);
-
-        unsigned long long it = 0;
-        bool dead = false;
-        if (DEFER > 0) {
-            Queue<NQ> q;
-            clear_queue<0, NQ>(q);
-            const unsigned long long n_main = P.iterations - P.iterations % (unsigned long long)NQ;
-            for (; it < n_main; it += NQ) {                                   // lib.rs:769, NQ at a time
-                dead = group_steps<0, NQ, MODE>(P, q, x, y, z, it, job_inv);
-                if (dead) break;
+#pragma unroll
+            for (int k = 0; k < NT; ++k) {
+                double nx, ny, nz;
+                SAR_NEXT_POINT(P, x[k], y[k], z[k], nx, ny, nz);
+                x[k] = nx; y[k] = ny; z[k] = nz;
             }
-            if (!dead) retire_range<0, NQ, NQ>(P, q, job_inv);
         }
-#pragma unroll 2
-        for (; it < P.iterations && !dead; ++it) {                            // DEFER == 0, or the < NQ tail
-            const double px = x, py = y, pz = z;
-            unsigned int idx; uint32_t key; unsigned long long old;
-            double sx, sy, sz;
-            const int act = step_point<MODE>(P, x, y, z, idx, key, old, sx, sy, sz);
-            if (act == 2) { atomicAdd(&P.scal->nan_sink, P.iterations - it); break; }
-            if (key >= (uint32_t)(old >> 32) && key != 0u)                    // may beat zbuf (lib.rs:821)
-                record_win_direct(&P, idx, key, job_inv, old, __dsub_rn(x, px), __dsub_rn(y, py), __dsub_rn(z, pz), sx, sy, sz);
+
+        for (unsigned long long it = 0; it < P.iterations; ++it) {            // lib.rs:769
+            double dx[NT], dy[NT], dz[NT], sx[NT], sy[NT], sz[NT], fi[NT], fj[NT];
+            unsigned int idx[NT];
+            uint32_t key[NT];
+            bool plain[NT];
+            // ---- arithmetic of the NT lanes, branch-free ----
+#pragma unroll
+            for (int k = 0; k < NT; ++k) {
+                double nx, ny, nz;
+                SAR_NEXT_POINT(P, x[k], y[k], z[k], nx, ny, nz);              // lib.rs:770
+                // screen_space = rotation_matrix.mul_right(current_point), lib.rs:773 / 208-215
+                sx[k] = __dadd_rn(__dadd_rn(__dmul_rn(P.m[0][0], nx), __dmul_rn(P.m[0][1], ny)), __dmul_rn(P.m[0][2], nz));
+                sy[k] = __dadd_rn(__dadd_rn(__dmul_rn(P.m[1][0], nx), __dmul_rn(P.m[1][1], ny)), __dmul_rn(P.m[1][2], nz));
+                sz[k] = __dadd_rn(__dadd_rn(__dmul_rn(P.m[2][0], nx), __dmul_rn(P.m[2][1], ny)), __dmul_rn(P.m[2][2], nz));
+                // rotate around center_camera, lib.rs:776-779 (center_camera.y pairs with screen_space.z)
+                const double a = __dadd_rn(sx[k], P.ccx);
+                const double b = __dadd_rn(sz[k], P.ccy);
+                const double x2 = __dadd_rn(__dmul_rn(a, P.cv), __dmul_rn(b, P.sv));
+                const double z2 = __dsub_rn(__dmul_rn(a, P.sv), __dmul_rn(b, P.cv));
+                fi[k] = __dmul_rn(__dsub_rn(P.sam, x2), P.ws);                       // lib.rs:783
+                fj[k] = __dsub_rn(P.half_h, __dmul_rn(__dadd_rn(sy[k], P.ccz), P.ws));  // lib.rs:786
+                // Bounds test + `as u32` (lib.rs:789-802) for the common case in one step: floor-convert
+                // (saturating) and compare unsigned.  i in [0,W) <=> 0 <= floor(i) < W, and floor == trunc
+                // there.  Anything else — out of view, NaN, pixel 0 — takes classify_rare(), which applies
+                // the reference's comparisons literally.
+                const unsigned int ii = (unsigned int)__double2int_rd(fi[k]);
+                const unsigned int jj = (unsigned int)__double2int_rd(fj[k]);
+                idx[k] = jj * P.W + ii;
+                plain[k] = (ii < P.W && jj < P.H) && idx[k] != 0u;
+                const float zf = __double2float_rn(z2) + 0.0f;                // `z2 as f32`; -0 folded onto +0 (f32 `>` sees them equal)
+                key[k] = zkey_of(zf);
+                if (key[k] > ZKEY_POS_INF) key[k] = 0u;                       // NaN never passes `>` (lib.rs:821)
+                dx[k] = __dsub_rn(nx, x[k]); dy[k] = __dsub_rn(ny, y[k]); dz[k] = __dsub_rn(nz, z[k]);   // delta, lib.rs:822
+                x[k] = nx; y[k] = ny; z[k] = nz;                              // previous_point = current_point, lib.rs:793/836
+            }
+            // ---- scatter: count += 1 (lib.rs:811) + fetch of the depth hint, one L2 atomic per lane ----
+            unsigned long long old[NT];
+            bool hit[NT];
+#pragma unroll
+            for (int k = 0; k < NT; ++k) {
+                hit[k] = live[k];
+                if (live[k] && !plain[k]) {
+                    const unsigned long long r = classify_rare(fi[k], fj[k], P.W, P.H, x[k], y[k], z[k]);
+                    const unsigned int act = (unsigned int)(r >> 32);
+                    idx[k] = (unsigned int)r;
+                    hit[k] = act == 1u;
+                    if (act == 2u) {                                          // NaN state: pay the whole debt at once, the job is over
+                        atomicAdd(&P.scal->nan_sink, P.iterations - it);
+                        live[k] = false;
+                    }
+                }
+                old[k] = ~0ull;
+                if (hit[k]) {
+                    unsigned long long *slot = P.fast + slot_of(idx[k], P.slots);
+                    if (MODE == 0 || MODE == 4) old[k] = atomicAdd(slot, 1ull);
+                    else if (MODE == 2) asm volatile("red.global.add.u64 [%0], 1;" ::"l"(slot) : "memory");
+                    else old[k] = ~0ull ^ (unsigned long long)(idx[k] == 0xFFFFFFFFu);
+                }
+            }
+            // ---- depth test (lib.rs:821) on the returned hints ----
+            bool any = false;
+#pragma unroll
+            for (int k = 0; k < NT; ++k) {
+                if (key[k] >= (uint32_t)(old[k] >> 32) && key[k] != 0u) {      // may beat zbuf
+                    if (MODE == 0) record_win(P, idx[k], key[k], job_inv[k], old[k], dx[k], dy[k], dz[k], sx[k], sy[k], sz[k]);
+                    else if (idx[k] == 0xFFFFFFF0u) P.scal->pad = key[k];     // diagnostics: keep the returned value live
+                }
+                any |= live[k];
+            }
+            if (!any) break;
         }
     }
 }
@@ -382,53 +318,56 @@ void launch_warm(const IterParams &p, double *out, cudaStream_t s)
     ++g_launches;
 }
 
-static std::atomic<int> g_defer{-1};
+// Lanes per thread (NT): a tuning knob that never changes results.
+static std::atomic<int> g_nt{SAR_DEFAULT_NT};
+bool set_traj_per_thread(int nt)
+{
+    if (nt != 1 && nt != 2 && nt != 4) return false;
+    g_nt = nt;
+    return true;
+}
+#ifdef SAR_DIAGNOSTICS
 static std::atomic<int> g_mode{0};
-
 bool set_mode(int m)
 {
-    if (m < 0 || m > 7) return false;
+    if (m != 0 && m != 1 && m != 2 && m != 4) return false;
     g_mode = m;
     return true;
 }
-bool set_defer(int d)
+#else
+bool set_mode(int m) { return m == 0; }
+#endif
+
+template <int MODE>
+static void launch_iterate_mode(const IterParams &p, unsigned long long want, cudaStream_t s)
 {
-    if (d < 0 || d > 4) return false;
-    g_defer = d;
-    return true;
+    // `want` lanes; NT lanes per thread; narrow blocks so that the grid stays a multiple of the SM
+    // count at the default 896 lanes per SM (7 blocks per SM) and small launches spread over the SMs
+    const int nt = g_nt.load();
+    const unsigned long long threads = (want + nt - 1) / nt;
+    const unsigned int block = threads >= 148ull * 128ull ? 128u / (unsigned int)nt : 32u;
+    const unsigned int grid = (unsigned int)((threads + block - 1) / block);
+    switch (nt) {
+    case 1: iterate_kernel<1, MODE><<<grid, block, 0, s>>>(p); break;
+    case 2: iterate_kernel<2, MODE><<<grid, block, 0, s>>>(p); break;
+    default: iterate_kernel<4, MODE><<<grid, block, 0, s>>>(p); break;
+    }
 }
+
 void launch_iterate(const IterParams &p, unsigned int lanes, cudaStream_t s)
 {
     if (p.n_jobs == 0) return;
-    if (g_defer < 0) {                       // tuning knob; the default is what the sweep measured best
-        const char *e = getenv("SAR_DEFER");
-        int d = e ? atoi(e) : 0;
-        g_defer = (d < 0 || d > 4) ? 0 : d;
+    const unsigned long long want = p.n_jobs < lanes ? p.n_jobs : lanes;
+#ifdef SAR_DIAGNOSTICS
+    switch (g_mode.load()) {
+    case 1: launch_iterate_mode<1>(p, want, s); break;
+    case 2: launch_iterate_mode<2>(p, want, s); break;
+    case 4: launch_iterate_mode<4>(p, want, s); break;
+    default: launch_iterate_mode<0>(p, want, s); break;
     }
-    unsigned long long want = p.n_jobs < lanes ? p.n_jobs : lanes;
-    // small launches: narrow blocks so the jobs spread over the SMs
-    const unsigned int block = want >= 148ull * 128ull ? 128u : 32u;
-    const unsigned int grid = (unsigned int)((want + block - 1) / block);
-    if (g_mode != 0) {                       // diagnostics only (incomplete results by design)
-        switch (g_mode.load()) {
-        case 1: iterate_kernel<1, 1><<<grid, block, 0, s>>>(p); break;
-        case 2: iterate_kernel<1, 2><<<grid, block, 0, s>>>(p); break;
-        case 3: iterate_kernel<1, 3><<<grid, block, 0, s>>>(p); break;
-        case 4: iterate_kernel<0, 4><<<grid, block, 0, s>>>(p); break;
-        case 5: iterate_kernel<1, 5><<<grid, block, 0, s>>>(p); break;
-        case 6: iterate_kernel<1, 6><<<grid, block, 0, s>>>(p); break;
-        default: iterate_kernel<0, 7><<<grid, block, 0, s>>>(p); break;
-        }
-        ++g_launches;
-        return;
-    }
-    switch (g_defer.load()) {
-    case 0: iterate_kernel<0, 0><<<grid, block, 0, s>>>(p); break;
-    case 1: iterate_kernel<1, 0><<<grid, block, 0, s>>>(p); break;
-    case 2: iterate_kernel<2, 0><<<grid, block, 0, s>>>(p); break;
-    case 3: iterate_kernel<3, 0><<<grid, block, 0, s>>>(p); break;
-    default: iterate_kernel<4, 0><<<grid, block, 0, s>>>(p); break;
-    }
+#else
+    launch_iterate_mode<0>(p, want, s);
+#endif
     ++g_launches;
 }
 
@@ -475,7 +414,7 @@ __global__ void max_kernel(const unsigned long long *fast, const ulonglong2 *rec
         const size_t p = pix0 + i;
         const uint32_t c = pixel_count(fast, scal, p, slots);
         m = c > m ? c : m;
-        const uint32_t k = (uint32_t)(rec[p].y >> 32);
+        const uint32_t k = canon_key((uint32_t)(rec[p].y >> 32));
         if (k != ZKEY_SENTINEL) { zmx = k > zmx ? k : zmx; zmn = k < zmn ? k : zmn; }
     }
     for (int o = 16; o > 0; o >>= 1) {
@@ -615,10 +554,10 @@ __global__ void pack_kernel(unsigned long long *fast, ulonglong2 *rec, Scalars *
 {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += stride) {
-        const float z = zbuf[i] + 0.0f;
-        uint32_t k = zkey_of(z);
+        const float z = zbuf[i];
+        uint32_t k = zkey_of(z);                                // keeps the sign of a zero
         if (!(z > -1.0f)) k = ZKEY_SENTINEL;                    // untouched (or invalid) pixels
-        const uint32_t hint = k == ZKEY_SENTINEL ? ZKEY_SENTINEL + 1u : k;
+        const uint32_t hint = k == ZKEY_SENTINEL ? ZKEY_SENTINEL + 1u : canon_key(k);
         fast[slot_of((uint32_t)i, slots)] = ((unsigned long long)hint << 32) | count[i];
         // uploaded records predate every future job: they keep all z ties (job key 0)
         rec[i] = make_ulonglong2((unsigned long long)__double_as_longlong(steps[i]), ((unsigned long long)k << 32) | 0xFFFFFFFFull);
@@ -648,8 +587,8 @@ __global__ void merge_kernel(unsigned long long *dfast, ulonglong2 *drec, Scalar
         const uint32_t c = (uint32_t)dfast[sl] + (uint32_t)sfast[sl];               // lib.rs:719
         ulonglong2 d = drec[i];
         const ulonglong2 o = srec[i];
-        if ((uint32_t)(o.y >> 32) > (uint32_t)(d.y >> 32)) { d = o; drec[i] = d; }  // lib.rs:728-735
-        const uint32_t k = (uint32_t)(d.y >> 32);
+        if (canon_key((uint32_t)(o.y >> 32)) > canon_key((uint32_t)(d.y >> 32))) { d = o; drec[i] = d; }  // lib.rs:728-735
+        const uint32_t k = canon_key((uint32_t)(d.y >> 32));
         const uint32_t hint = k == ZKEY_SENTINEL ? ZKEY_SENTINEL + 1u : k;
         dfast[sl] = ((unsigned long long)hint << 32) | c;
     }
@@ -683,9 +622,9 @@ __global__ void merge_peers_kernel(unsigned long long *dfast, ulonglong2 *drec, 
         for (int r = 0; r < peers.n; ++r) {
             c += (uint32_t)__ldcv(peers.fast[r] + sl);
             const unsigned long long oy = __ldcv(&peers.rec[r][p].y);
-            if (oy > d.y) { d.y = oy; d.x = __ldcv(&peers.rec[r][p].x); }
+            if (rec_order(oy) > rec_order(d.y)) { d.y = oy; d.x = __ldcv(&peers.rec[r][p].x); }
         }
-        const uint32_t k = (uint32_t)(d.y >> 32);
+        const uint32_t k = canon_key((uint32_t)(d.y >> 32));
         const uint32_t hint = k == ZKEY_SENTINEL ? ZKEY_SENTINEL + 1u : k;
         drec[p] = d;
         dfast[sl] = ((unsigned long long)hint << 32) | c;

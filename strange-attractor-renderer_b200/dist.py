@@ -183,6 +183,8 @@ class Frame:
         self.N.check(self.L.sar_runtime_reset_async(self.rt, sp))
 
     def render_async(self, sp, d_init=None) -> None:
+        # order keys are global over the ranks: rank r's jobs follow rank r-1's (include/sar.h)
+        self.N.check(self.L.sar_runtime_set_job_base(self.rt, self.first_job))
         if d_init is None:
             self.N.check(self.L.sar_render_seeded_async(C.byref(self.pod), self.rt, self.seed, self.first_job,
                                                         self.n_jobs, self.lanes, sp))

@@ -396,3 +396,47 @@ def test_small_renders_are_not_empty_in_auto_mode(S, oracle):
         _assert_image_close(img, None, oracle.colorize(ocfg, ort), None)
     assert r.plan(10**9, 1) == (lanes, 10**9 // lanes)          # large frames are unaffected
     r.shutdown()
+
+
+def test_negative_zero_z_is_kept_and_ties_with_positive_zero(S, oracle):
+    """`z2 as f32` can be -0.0; f32 `>` (lib.rs:728, 821) sees -0.0 == +0.0, but the stored bits
+    differ.  Through the checkpoint path: -0.0 survives upload/download bit for bit, and in a merge a
+    +0.0 never displaces a -0.0 (nor the reverse): ties keep self."""
+    cfg = _small(S.Config.poisson_saturne(), 4, 1, 10)
+    nz, pz = np.float32(-0.0), np.float32(0.0)
+    za = np.array([[nz, pz, nz, -0.5]], np.float32)
+    zb = np.array([[pz, nz, 0.25, nz]], np.float32)
+    ca, cb = np.array([[1, 2, 3, 4]], np.uint32), np.array([[10, 20, 30, 40]], np.uint32)
+    sa, sb = np.array([[0.1, 0.2, 0.3, 0.4]]), np.array([[0.5, 0.6, 0.7, 0.8]])
+    ra, rb = S.Runtime.new(cfg), S.Runtime.new(cfg)
+    ra.upload(ca, sa, za)
+    rb.upload(cb, sb, zb)
+    c, s, z, _ = ra.download()
+    assert np.array_equal(z.view(np.uint32), za.view(np.uint32)) and np.array_equal(s, sa) and np.array_equal(c, ca)
+    oa, ob = oracle.Runtime(4, 1), oracle.Runtime(4, 1)
+    oa.load(ca, sa, za)
+    ob.load(cb, sb, zb)
+    ra.merge(rb)
+    oa.merge(ob)
+    c, s, z, mx = ra.download()
+    assert np.array_equal(z.view(np.uint32), oa.zbuf.view(np.uint32)), (z, oa.zbuf)
+    assert np.array_equal(s, oa.steps) and np.array_equal(c, oa.count) and mx == oa.max
+    assert z.view(np.uint32).tolist() == [[0x80000000, 0x00000000, np.float32(0.25).view(np.uint32), 0x80000000]]
+
+
+def test_progressive_order_keys_are_linear(S, oracle):
+    """Order keys advance by the number of jobs rendered, whatever `first_job` positions in the seed
+    stream: many progressive render() calls on one Runtime stay exact, and the counter
+    refuses to wrap."""
+    cfg = _small(S.Config.poisson_saturne(), 64, 64, 500)
+    rt = S.Runtime.new(cfg, seed=11)
+    for _ in range(40):
+        S.render(cfg, rt)
+    jb = C.c_uint64()
+    S._native.check(S._native.lib().sar_runtime_get_job_base(rt._h, C.byref(jb)))
+    assert jb.value == 40
+    ort, _ = _oracle_state(oracle, cfg, oracle.seed_points(11, 0, 40))
+    _assert_state_equal(rt.download(), ort)
+    S._native.check(S._native.lib().sar_runtime_set_job_base(rt._h, (1 << 32) - 1))
+    with pytest.raises(S.SarError):
+        S.render(cfg, rt, initial_points=S.seed_points(1, 0, 2))

@@ -93,3 +93,25 @@ def test_angle_iter_follows_the_reference_cli():
     assert S.angle_iter(10.0, 20.0, 4.0) == [a * math.pi / 180.0 for a in (10.0, 14.0)]   # 18 + 2 >= 20 stops
     assert S.angle_iter(220.0, 220.0, 1.0) == [220.0]          # single image: passed through unconverted
     assert S.angle_iter(5.0, 5.4, 1.0) == [5.0]
+
+
+def test_product_library_has_no_diagnostic_kernels():
+    """no switch in the product library may make a handle produce incomplete
+    results.  diagnostic_mode != 0 is refused, and only the product instantiations of the iterate
+    kernel (MODE 0) are in the binary."""
+    import subprocess
+
+    from strange_attractor_renderer_b200 import _native as N
+
+    L = N.lib()
+    assert L.sar_set_option(b"diagnostic_mode", 0) == 0
+    for m in (1, 2, 4, 7):
+        assert L.sar_set_option(b"diagnostic_mode", m) == N.SAR_ERR_UNSUPPORTED
+    assert L.sar_set_option(b"defer", 1) == N.SAR_ERR_INVALID      # removed knob
+    for nt in (1, 2, 4):
+        assert L.sar_set_option(b"traj_per_thread", nt) == 0
+    assert L.sar_set_option(b"traj_per_thread", 3) == N.SAR_ERR_INVALID
+    assert L.sar_set_option(b"traj_per_thread", 2) == 0
+    syms = subprocess.run(["cuobjdump", "-symbols", N.LIB_PATH], capture_output=True, text=True).stdout
+    kernels = sorted({w for line in syms.splitlines() if "STO_ENTRY" in line for w in line.split() if "iterate_kernel" in w})
+    assert kernels and all(k.endswith("ELi0EEEvNS_10IterParamsE") for k in kernels), kernels
