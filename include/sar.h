@@ -105,9 +105,10 @@ int         sar_device_count(int *count);    /* SAR_ERR_CUDA when no driver/devi
 /* Default number of concurrent trajectory lanes on `device` (SM count × 896):
  * the GPU's answer to available_parallelism(), lib.rs:920-922. */
 int         sar_default_threads(int device, uint32_t *threads);
-/* Options.  "traj_per_thread" (1, 2 or 4): how many trajectories one GPU thread
- * carries side by side in the iterate kernel — a tuning knob that never changes
- * results.  "diagnostic_mode": the product library accepts only 0;
+/* Options.  Tuning knobs of the iterate kernel that never change results
+ * (DESIGN.md §5): "traj_per_thread" (1, 2 or 4) — how many trajectories one GPU
+ * thread carries side by side; "pipeline" (0 / 1) — make the depth test of an
+ * iteration after the arithmetic of the next one.  "diagnostic_mode": the product library accepts only 0;
  * the roofline-experiment variants of the iterate kernel (incomplete results by
  * design) exist only in the separately built libsar_b200_diag.so
  * (-DSAR_DIAGNOSTICS, tools/sweep_iterate.py) — SAR_ERR_UNSUPPORTED here. */

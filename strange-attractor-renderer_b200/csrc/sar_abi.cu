@@ -242,6 +242,10 @@ int sar_set_option(const char *name, int64_t value)
         if (!set_traj_per_thread((int)value)) return fail(SAR_ERR_INVALID, "traj_per_thread must be 1, 2 or 4");
         return SAR_OK;
     }
+    if (strcmp(name, "pipeline") == 0) {
+        if (!set_pipeline((int)value)) return fail(SAR_ERR_INVALID, "pipeline must be 0 or 1");
+        return SAR_OK;
+    }
     if (strcmp(name, "diagnostic_mode") == 0) {
 #ifdef SAR_DIAGNOSTICS
         if (!set_mode((int)value)) return fail(SAR_ERR_INVALID, "diagnostic_mode must be 0, 1, 2 or 4");

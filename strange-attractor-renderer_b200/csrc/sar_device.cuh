@@ -146,6 +146,7 @@ void launch_publish_max(Scalars *mine, const ScalList &targets, int my_rank, uns
 void launch_gather_max(Scalars *mine, int n_ranks, cudaStream_t s);
 unsigned long long launch_count();
 bool set_mode(int mode);     // SAR_DIAGNOSTICS builds only: 0 = product path; 1, 2, 4 = roofline experiments (incomplete results)
+bool set_pipeline(int on);          // tuning: depth test one iteration behind its atomic (0/1); never changes results
 bool set_traj_per_thread(int nt);   // tuning: trajectories carried per thread (1, 2 or 4); never changes results
 
 }  // namespace sar

@@ -8,9 +8,13 @@
 #include "sar_device.cuh"
 
 #include <atomic>
+#include <type_traits>
 
 #ifndef SAR_DEFAULT_NT
-#define SAR_DEFAULT_NT 2
+#define SAR_DEFAULT_NT 1
+#endif
+#ifndef SAR_DEFAULT_PIPE
+#define SAR_DEFAULT_PIPE 0
 #endif
 
 namespace sar {
@@ -37,6 +41,27 @@ __device__ __forceinline__ ulonglong2 cas128(ulonglong2 *addr, ulonglong2 expect
         "}"
         : "=l"(old.x), "=l"(old.y)
         : "l"(expect.x), "l"(expect.y), "l"(desired.x), "l"(desired.y), "l"(addr)
+        : "memory");
+    return old;
+}
+
+// count += 1 and fetch of the packed (zhint, count) word, predicated; the result is UNDEFINED when
+// !p (callers zero the candidate key of such lanes instead, so it is never looked at).  Written as
+// one predicated instruction with a single definition of the result because
+// `old = ~0; if (p) old = atomicAdd(..)` compiles to the atomic into a temporary plus a MOV that
+// waits for the L2 round trip right behind it (ncu: 52 % of all stall samples sat on that MOV),
+// which serialises the lanes a thread carries and defeats the deferred depth test.
+__device__ __forceinline__ unsigned long long atom_inc_if(bool p, unsigned long long *addr)
+{
+    unsigned long long old;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.u32 p, %2, 0;\n\t"
+        "@p atom.global.add.u64 %0, [%1], 1;\n\t"
+        "}"
+        : "=l"(old)
+        : "l"(addr), "r"((unsigned int)p)
         : "memory");
     return old;
 }
@@ -151,19 +176,33 @@ __device__ __forceinline__ void record_win(const IterParams &P, unsigned int idx
     }
 }
 
+__device__ __noinline__ void record_win_call(const IterParams *Pp, unsigned int idx, uint32_t key, uint32_t job_inv,
+                                             unsigned long long old, double dx, double dy, double dz,
+                                             double sx, double sy, double sz)
+{
+    record_win(*Pp, idx, key, job_inv, old, dx, dy, dz, sx, sy, sz);
+}
+
 // Everything that is not a plain in-view hit: out of view, non-finite coordinates, and the
 // corner pixel.  Evaluates lib.rs:789-802 literally.  Returns action << 32 | idx with action
 // 0 = not recorded (continue), 1 = record at idx, 2 = the state is NaN: this and every later iteration of the job hits
 // count[(0,0)] and can never win the depth test (NaN is absorbing).
-__device__ __noinline__ unsigned long long classify_rare(double fi, double fj, unsigned int W, unsigned int H,
+__device__ __noinline__ unsigned long long classify_rare(const IterParams *Pp, double sx, double sy, double sz,
                                                          double nx, double ny, double nz)
 {
-    const double w = (double)W, h = (double)H;
+    const IterParams &P = *Pp;
+    // the pixel coordinates again (lib.rs:776-786), same instructions on the same inputs as the hot loop
+    const double a = __dadd_rn(sx, P.ccx);
+    const double b = __dadd_rn(sz, P.ccy);
+    const double x2 = __dadd_rn(__dmul_rn(a, P.cv), __dmul_rn(b, P.sv));
+    const double fi = __dmul_rn(__dsub_rn(P.sam, x2), P.ws);
+    const double fj = __dsub_rn(P.half_h, __dmul_rn(__dadd_rn(sy, P.ccz), P.ws));
+    const double w = (double)P.W, h = (double)P.H;
     if (fi >= w || fj >= h || fi < 0. || fj < 0.) return 0ull;  // lib.rs:789; NaN passes every test
     if (nx != nx || ny != ny || nz != nz) return 2ull << 32;    // all of screen_space is NaN -> i = j = 0
     const unsigned int i = (fi != fi) ? 0u : __double2uint_rz(fi);   // `as u32`: truncates, NaN -> 0 (lib.rs:800-802)
     const unsigned int j = (fj != fj) ? 0u : __double2uint_rz(fj);
-    return (1ull << 32) | (unsigned long long)(j * W + i);
+    return (1ull << 32) | (unsigned long long)(j * P.W + i);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -180,8 +219,24 @@ __device__ __noinline__ unsigned long long classify_rare(double fi, double fj, u
 // product's atomic with the win path removed.  Modes != 0 leave the Runtime in a state that is
 // only good for timing (tools/sweep_iterate.py).
 // ---------------------------------------------------------------------------------------------
-template <int NT, int MODE>
-__global__ void __launch_bounds__(128)
+constexpr unsigned int IDX_RARE = 0xFFFFFFFFu;   // candidate that needs classify_rare (W*H <= 2^31, so never a pixel)
+
+// A recorded hit between its count atomic and its depth test: what the winning branch needs.
+struct Cand {
+    double dx, dy, dz;            // delta = current - previous point (lib.rs:822)
+    double sx, sy, sz;            // screen_space (lib.rs:773)
+    unsigned long long old;       // what the atomic returned: zhint << 32 | count; ~0 = no hit
+    unsigned int idx;
+    uint32_t key;                 // canonical z key; 0 = cannot win
+};
+
+// PIPE = 1: the depth test of iteration i is made after the arithmetic of iteration i+1, so the L2
+// round trip of the atomic is covered by ~130 FP64 instructions of the same warp instead of by
+// other warps alone — with NT lanes per thread there are only 3-4 warps per scheduler.  Within a
+// lane tests still retire in iteration order and before the next atomic is issued, so exact z ties
+// keep resolving to the earlier iteration.
+template <int NT, int MODE, int PIPE>
+__global__ void __launch_bounds__(128 / NT, NT == 1 ? (PIPE ? 5 : 7) : 8)   // register budgets: 7 x 128 / 5 x 128 / 8 x 64 / 8 x 32 threads per SM
 iterate_kernel(const __grid_constant__ IterParams P)
 {
     const unsigned long long nthreads = (unsigned long long)gridDim.x * blockDim.x;
@@ -216,76 +271,114 @@ iterate_kernel(const __grid_constant__ IterParams P)
             }
         }
 
-        for (unsigned long long it = 0; it < P.iterations; ++it) {            // lib.rs:769
-            double dx[NT], dy[NT], dz[NT], sx[NT], sy[NT], sz[NT], fi[NT], fj[NT];
-            unsigned int idx[NT];
-            uint32_t key[NT];
-            bool plain[NT];
-            // ---- arithmetic of the NT lanes, branch-free ----
+        // One iteration in three pieces (lambdas, all inlined): arith (branch-free arithmetic of the NT
+        // lanes -> candidate set), scatter (the count atomic), test (depth test on what the atomic
+        // returned).  PIPE 0: arith(A) scatter(A) test(A).  PIPE 1 ping-pongs two candidate sets:
+        //     scatter(A) | arith(B) test(A) | scatter(B) | arith(A) test(B) | ...
+        // so the L2 round trip of an atomic is covered by the next iteration's arithmetic, each atomic
+        // result is produced and consumed inside one loop trip (nothing is copied behind an atomic,
+        // which would wait for it), and within a lane tests retire in iteration order.
+        bool any = true;
+        auto arith = [&](Cand (&c)[NT]) {
 #pragma unroll
             for (int k = 0; k < NT; ++k) {
                 double nx, ny, nz;
                 SAR_NEXT_POINT(P, x[k], y[k], z[k], nx, ny, nz);              // lib.rs:770
                 // screen_space = rotation_matrix.mul_right(current_point), lib.rs:773 / 208-215
-                sx[k] = __dadd_rn(__dadd_rn(__dmul_rn(P.m[0][0], nx), __dmul_rn(P.m[0][1], ny)), __dmul_rn(P.m[0][2], nz));
-                sy[k] = __dadd_rn(__dadd_rn(__dmul_rn(P.m[1][0], nx), __dmul_rn(P.m[1][1], ny)), __dmul_rn(P.m[1][2], nz));
-                sz[k] = __dadd_rn(__dadd_rn(__dmul_rn(P.m[2][0], nx), __dmul_rn(P.m[2][1], ny)), __dmul_rn(P.m[2][2], nz));
+                const double sx = __dadd_rn(__dadd_rn(__dmul_rn(P.m[0][0], nx), __dmul_rn(P.m[0][1], ny)), __dmul_rn(P.m[0][2], nz));
+                const double sy = __dadd_rn(__dadd_rn(__dmul_rn(P.m[1][0], nx), __dmul_rn(P.m[1][1], ny)), __dmul_rn(P.m[1][2], nz));
+                const double sz = __dadd_rn(__dadd_rn(__dmul_rn(P.m[2][0], nx), __dmul_rn(P.m[2][1], ny)), __dmul_rn(P.m[2][2], nz));
                 // rotate around center_camera, lib.rs:776-779 (center_camera.y pairs with screen_space.z)
-                const double a = __dadd_rn(sx[k], P.ccx);
-                const double b = __dadd_rn(sz[k], P.ccy);
+                const double a = __dadd_rn(sx, P.ccx);
+                const double b = __dadd_rn(sz, P.ccy);
                 const double x2 = __dadd_rn(__dmul_rn(a, P.cv), __dmul_rn(b, P.sv));
                 const double z2 = __dsub_rn(__dmul_rn(a, P.sv), __dmul_rn(b, P.cv));
-                fi[k] = __dmul_rn(__dsub_rn(P.sam, x2), P.ws);                       // lib.rs:783
-                fj[k] = __dsub_rn(P.half_h, __dmul_rn(__dadd_rn(sy[k], P.ccz), P.ws));  // lib.rs:786
+                const double fi = __dmul_rn(__dsub_rn(P.sam, x2), P.ws);                       // lib.rs:783
+                const double fj = __dsub_rn(P.half_h, __dmul_rn(__dadd_rn(sy, P.ccz), P.ws));  // lib.rs:786
                 // Bounds test + `as u32` (lib.rs:789-802) for the common case in one step: floor-convert
                 // (saturating) and compare unsigned.  i in [0,W) <=> 0 <= floor(i) < W, and floor == trunc
-                // there.  Anything else — out of view, NaN, pixel 0 — takes classify_rare(), which applies
-                // the reference's comparisons literally.
-                const unsigned int ii = (unsigned int)__double2int_rd(fi[k]);
-                const unsigned int jj = (unsigned int)__double2int_rd(fj[k]);
-                idx[k] = jj * P.W + ii;
-                plain[k] = (ii < P.W && jj < P.H) && idx[k] != 0u;
+                // there.  Anything else — out of view, NaN, pixel 0 — is marked IDX_RARE and goes through
+                // classify_rare(), which applies the reference's comparisons literally.
+                const unsigned int ii = (unsigned int)__double2int_rd(fi);
+                const unsigned int jj = (unsigned int)__double2int_rd(fj);
+                const unsigned int idx = jj * P.W + ii;
+                c[k].idx = ((ii < P.W && jj < P.H) && idx != 0u) ? idx : IDX_RARE;
                 const float zf = __double2float_rn(z2) + 0.0f;                // `z2 as f32`; -0 folded onto +0 (f32 `>` sees them equal)
-                key[k] = zkey_of(zf);
-                if (key[k] > ZKEY_POS_INF) key[k] = 0u;                       // NaN never passes `>` (lib.rs:821)
-                dx[k] = __dsub_rn(nx, x[k]); dy[k] = __dsub_rn(ny, y[k]); dz[k] = __dsub_rn(nz, z[k]);   // delta, lib.rs:822
+                c[k].key = zkey_of(zf);
+                if (c[k].key > ZKEY_POS_INF) c[k].key = 0u;                   // NaN never passes `>` (lib.rs:821)
+                c[k].sx = sx; c[k].sy = sy; c[k].sz = sz;
+                c[k].dx = __dsub_rn(nx, x[k]); c[k].dy = __dsub_rn(ny, y[k]); c[k].dz = __dsub_rn(nz, z[k]);   // delta, lib.rs:822
                 x[k] = nx; y[k] = ny; z[k] = nz;                              // previous_point = current_point, lib.rs:793/836
             }
-            // ---- scatter: count += 1 (lib.rs:811) + fetch of the depth hint, one L2 atomic per lane ----
-            unsigned long long old[NT];
-            bool hit[NT];
+        };
+        // count += 1 (lib.rs:811) + fetch of the depth hint: one L2 atomic per recorded lane.  Runs right
+        // after arith() of the same candidate set, so (x,y,z) is still that iteration's current point.
+        auto scatter = [&](Cand (&c)[NT], unsigned long long it) {
+            any = false;
 #pragma unroll
             for (int k = 0; k < NT; ++k) {
-                hit[k] = live[k];
-                if (live[k] && !plain[k]) {
-                    const unsigned long long r = classify_rare(fi[k], fj[k], P.W, P.H, x[k], y[k], z[k]);
+                bool hit = live[k];
+                if (live[k] && c[k].idx == IDX_RARE) {
+                    const unsigned long long r = classify_rare(&P, c[k].sx, c[k].sy, c[k].sz, x[k], y[k], z[k]);
                     const unsigned int act = (unsigned int)(r >> 32);
-                    idx[k] = (unsigned int)r;
-                    hit[k] = act == 1u;
+                    c[k].idx = (unsigned int)r;
+                    hit = act == 1u;
                     if (act == 2u) {                                          // NaN state: pay the whole debt at once, the job is over
                         atomicAdd(&P.scal->nan_sink, P.iterations - it);
                         live[k] = false;
                     }
                 }
-                old[k] = ~0ull;
-                if (hit[k]) {
-                    unsigned long long *slot = P.fast + slot_of(idx[k], P.slots);
-                    if (MODE == 0 || MODE == 4) old[k] = atomicAdd(slot, 1ull);
-                    else if (MODE == 2) asm volatile("red.global.add.u64 [%0], 1;" ::"l"(slot) : "memory");
-                    else old[k] = ~0ull ^ (unsigned long long)(idx[k] == 0xFFFFFFFFu);
-                }
-            }
-            // ---- depth test (lib.rs:821) on the returned hints ----
-            bool any = false;
-#pragma unroll
-            for (int k = 0; k < NT; ++k) {
-                if (key[k] >= (uint32_t)(old[k] >> 32) && key[k] != 0u) {      // may beat zbuf
-                    if (MODE == 0) record_win(P, idx[k], key[k], job_inv[k], old[k], dx[k], dy[k], dz[k], sx[k], sy[k], sz[k]);
-                    else if (idx[k] == 0xFFFFFFF0u) P.scal->pad = key[k];     // diagnostics: keep the returned value live
+                unsigned long long *slot = P.fast + slot_of(c[k].idx, P.slots);
+                if (MODE == 0 || MODE == 4) {
+                    if (!hit) c[k].key = 0u;                                  // nothing recorded: nothing to test
+                    c[k].old = atom_inc_if(hit, slot);
+                } else {
+                    c[k].old = ~0ull;
+                    if (hit) {
+                        if (MODE == 2) asm volatile("red.global.add.u64 [%0], 1;" ::"l"(slot) : "memory");
+                        else c[k].old = ~0ull ^ (unsigned long long)(c[k].idx == 0xFFFFFFFEu);
+                    }
                 }
                 any |= live[k];
             }
-            if (!any) break;
+        };
+        // depth test (lib.rs:821) on the returned hints; the winning branch inline (in the loop) or as a call (loop exits)
+        auto test = [&](Cand (&c)[NT], auto inl) {
+#pragma unroll
+            for (int k = 0; k < NT; ++k)
+                if (c[k].key >= (uint32_t)(c[k].old >> 32) && c[k].key != 0u) {      // may beat zbuf
+                    if (MODE != 0) { if (c[k].idx == 0xFFFFFFF0u) P.scal->pad = c[k].key; }   // diagnostics: keep the returned value live
+                    else if (decltype(inl)::value) record_win(P, c[k].idx, c[k].key, job_inv[k], c[k].old, c[k].dx, c[k].dy, c[k].dz, c[k].sx, c[k].sy, c[k].sz);
+                    else record_win_call(&P, c[k].idx, c[k].key, job_inv[k], c[k].old, c[k].dx, c[k].dy, c[k].dz, c[k].sx, c[k].sy, c[k].sz);
+                }
+        };
+        using inl_t = std::integral_constant<bool, true>;
+        using call_t = std::integral_constant<bool, false>;
+
+        Cand A[NT];
+        unsigned long long it = 0;
+        if (PIPE) {
+            if (P.iterations > 0) {
+                Cand B[NT];
+                arith(A);
+                for (;;) {                                                    // lib.rs:769, two iterations per trip
+                    scatter(A, it);
+                    ++it;
+                    if (!(it < P.iterations && any)) { test(A, call_t{}); break; }
+                    arith(B);
+                    test(A, inl_t{});
+                    scatter(B, it);
+                    ++it;
+                    if (!(it < P.iterations && any)) { test(B, call_t{}); break; }
+                    arith(A);
+                    test(B, inl_t{});
+                }
+            }
+        } else {
+#pragma unroll 2
+            for (; it < P.iterations && any; ++it) {                          // lib.rs:769
+                arith(A); scatter(A, it); test(A, inl_t{});
+            }
         }
     }
 }
@@ -326,6 +419,13 @@ bool set_traj_per_thread(int nt)
     g_nt = nt;
     return true;
 }
+static std::atomic<int> g_pipe{SAR_DEFAULT_PIPE};
+bool set_pipeline(int on)
+{
+    if (on != 0 && on != 1) return false;
+    g_pipe = on;
+    return true;
+}
 #ifdef SAR_DIAGNOSTICS
 static std::atomic<int> g_mode{0};
 bool set_mode(int m)
@@ -347,10 +447,18 @@ static void launch_iterate_mode(const IterParams &p, unsigned long long want, cu
     const unsigned long long threads = (want + nt - 1) / nt;
     const unsigned int block = threads >= 148ull * 128ull ? 128u / (unsigned int)nt : 32u;
     const unsigned int grid = (unsigned int)((threads + block - 1) / block);
-    switch (nt) {
-    case 1: iterate_kernel<1, MODE><<<grid, block, 0, s>>>(p); break;
-    case 2: iterate_kernel<2, MODE><<<grid, block, 0, s>>>(p); break;
-    default: iterate_kernel<4, MODE><<<grid, block, 0, s>>>(p); break;
+    if (g_pipe.load()) {
+        switch (nt) {
+        case 1: iterate_kernel<1, MODE, 1><<<grid, block, 0, s>>>(p); break;
+        case 2: iterate_kernel<2, MODE, 1><<<grid, block, 0, s>>>(p); break;
+        default: iterate_kernel<4, MODE, 1><<<grid, block, 0, s>>>(p); break;
+        }
+    } else {
+        switch (nt) {
+        case 1: iterate_kernel<1, MODE, 0><<<grid, block, 0, s>>>(p); break;
+        case 2: iterate_kernel<2, MODE, 0><<<grid, block, 0, s>>>(p); break;
+        default: iterate_kernel<4, MODE, 0><<<grid, block, 0, s>>>(p); break;
+        }
     }
 }
 

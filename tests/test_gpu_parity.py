@@ -440,3 +440,33 @@ def test_progressive_order_keys_are_linear(S, oracle):
     S._native.check(S._native.lib().sar_runtime_set_job_base(rt._h, (1 << 32) - 1))
     with pytest.raises(S.SarError):
         S.render(cfg, rt, initial_points=S.seed_points(1, 0, 2))
+
+
+@pytest.mark.parametrize("nt,pipe", [(1, 0), (1, 1), (2, 0), (2, 1), (4, 0), (4, 1)])
+def test_every_kernel_variant_is_bit_exact(S, oracle, nt, pipe):
+    """The tuning knobs (trajectories per thread, depth test one iteration behind its atomic) never
+    change results: every instantiation against the oracle, on a case with NaN trajectories, a job
+    count that is not a multiple of the lanes, several jobs per lane and out-of-view points."""
+    L = S._native.lib()
+    try:
+        S._native.check(L.sar_set_option(b"traj_per_thread", nt))
+        S._native.check(L.sar_set_option(b"pipeline", pipe))
+        cfg = _small(S.Config.solar_sail(), 333, 217, 2_500)
+        cfg.angle, cfg.view.scale = 0.9, 2.6
+        n_jobs = 1000 + 37
+        rt = S.Runtime.new(cfg)
+        c = cfg.to_pod()
+        S._native.check(L.sar_render_seeded_async(C.byref(c), rt._h, 4711, 0, n_jobs, 384, None))   # 2.7 jobs per lane
+        S._native.check(L.sar_stream_synchronize(rt._h, None))
+        ort, st = _oracle_state(oracle, cfg, oracle.seed_points(4711, 0, n_jobs))
+        assert st.nan_iters > 0 and 0 < st.recorded < n_jobs * 2_500
+        _assert_state_equal(rt.download(), ort)
+        # one lane, one job: the pipelined tail (last iteration's pending test) on its own
+        cfg1 = _small(S.Config.poisson_saturne(), 64, 64, 333)
+        r1 = S.Runtime.new(cfg1)
+        S.render(cfg1, r1, initial_points=S.seed_points(3, 0, 1))
+        o1, _ = _oracle_state(oracle, cfg1, oracle.seed_points(3, 0, 1))
+        _assert_state_equal(r1.download(), o1)
+    finally:
+        L.sar_set_option(b"traj_per_thread", 1)     # the defaults (sar_kernels.cu: SAR_DEFAULT_NT / SAR_DEFAULT_PIPE)
+        L.sar_set_option(b"pipeline", 0)

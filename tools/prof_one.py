@@ -25,6 +25,8 @@ pod = cfg.to_pod()
 pod.iterations = 1_000_000_000 // lanes
 if nt:
     N.check(L.sar_set_option(b"traj_per_thread", nt))
+if os.environ.get("SAR_PIPE"):
+    N.check(L.sar_set_option(b"pipeline", int(os.environ["SAR_PIPE"])))
 rt = C.c_void_p()
 N.check(L.sar_runtime_new(W, H, 0, C.byref(rt)))
 for _ in range(3):

@@ -3,7 +3,7 @@
     python tools/sweep_iterate.py            # product library
     SWEEP_DIAG=1 python tools/sweep_iterate.py   # libsar_b200_diag.so: also mode 1 (arithmetic only) and 4 (no win path)
 
-env: SWEEP_NT=1,2,4  SWEEP_LANES=768,896,1024  SWEEP_SHAPES=poisson:2048x2048,solar:1800x2000,poisson:4096x4096
+env: SWEEP_NT=1,2,4  SWEEP_PIPE=0,1  SWEEP_LANES=768,896,1024  SWEEP_SHAPES=poisson:2048x2048,solar:1800x2000,poisson:4096x4096
      SWEEP_ITERS=1e9  SWEEP_MODES=0,1,4 (diag only)
 Prints the median of 3 launches as G recorded iterations/s (warm-up steps excluded)."""
 import ctypes as C
@@ -42,8 +42,11 @@ for shape in shapes:
     for mode in modes:
         if DIAG:
             N.check(L.sar_set_option(b"diagnostic_mode", mode))
-        for nt in [int(v) for v in os.environ.get("SWEEP_NT", "1,2,4").split(",")]:
+        combos = [(nt, pipe) for nt in (int(v) for v in os.environ.get("SWEEP_NT", "1,2,4").split(","))
+                  for pipe in (int(v) for v in os.environ.get("SWEEP_PIPE", "0,1").split(","))]
+        for nt, pipe in combos:
             N.check(L.sar_set_option(b"traj_per_thread", nt))
+            N.check(L.sar_set_option(b"pipeline", pipe))
             for lanes_per_sm in [int(v) for v in os.environ.get("SWEEP_LANES", "768,896,1024,1152").split(",")]:
                 lanes = SMS * lanes_per_sm
                 pod = cfg.to_pod()
@@ -59,7 +62,7 @@ for shape in shapes:
                     torch.cuda.synchronize()
                     ts.append(e0.elapsed_time(e1))
                 ms = sorted(ts)[1]
-                print(f"{preset} {W}x{H} {NAMES.get(mode, mode)} NT {nt} lanes/SM {lanes_per_sm}: {ms:.3f} ms "
+                print(f"{preset} {W}x{H} {NAMES.get(mode, mode)} NT {nt} pipe {pipe} lanes/SM {lanes_per_sm}: {ms:.3f} ms "
                       f"{pod.iterations * lanes / ms / 1e6:.2f} Git/s", flush=True)
     if DIAG:
         N.check(L.sar_set_option(b"diagnostic_mode", 0))
