@@ -137,6 +137,85 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------------
+# Parity of the N-rank frame against the oracle (outside every timed region)
+# --------------------------------------------------------------------------------------------
+def parity_frame(world, rank, local, group, preset="solar", depth=False, per_gpu=20_000_000, lanes=2048, jpt=2,
+                 width=450, height=501, seed=4321):
+    """One small frame on `world` ranks (trajectory-sharded render, NVLink stripe merge, stripe
+    colourise into rank 0) against the CPU oracle on the same job list: count / zbuf / steps /
+    RGBA16 image, all bit-exact.  Returns the dict of checks on rank 0 (None elsewhere)."""
+    import ctypes as C
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import strange_attractor_renderer_b200 as S
+    from strange_attractor_renderer_b200 import _native as N
+    from strange_attractor_renderer_b200 import dist as D
+
+    L = N.lib()
+    cfg = S.Config.solar_sail() if preset == "solar" else S.Config.poisson_saturne()
+    cfg.width, cfg.height, cfg.angle = width, height, 1.25          # height not divisible by the world size
+    if depth:
+        cfg.render = S.RenderKind.Depth
+    frame = D.Frame(cfg, device=local, world=world, rank=rank, group=group, lanes=lanes, jobs_per_thread=jpt,
+                    iterations_per_gpu=per_gpu, seed=seed)
+    stream = torch.cuda.Stream(device=local)
+    sp = C.c_void_p(stream.cuda_stream)
+    for _ in range(2):                                              # twice: reset / re-merge must be clean
+        frame.step_device(sp)
+    torch.cuda.synchronize(local)
+    frame.check_sync()
+    if group is not None:
+        D.barrier(group)
+    h, w = frame.h, frame.w
+    count = np.empty((h, w), np.uint32)
+    steps = np.empty((h, w), np.float64)
+    zbuf = np.empty((h, w), np.float32)
+    N.check(L.sar_runtime_download(frame.rt, count.ctypes.data_as(N._u32p), steps.ctypes.data_as(N._f64p),
+                                   zbuf.ctypes.data_as(N._f32p), None))
+    r0, n = frame.row0, frame.rows
+    part = (r0, n, count[r0:r0 + n].copy(), steps[r0:r0 + n].copy(), zbuf[r0:r0 + n].copy())
+    parts = [part]
+    if group is not None:
+        parts = [None] * world
+        dist.all_gather_object(parts, part)
+    checks = None
+    if rank == 0:
+        from oracle import oracle as O          # the checker, never the thing measured
+
+        img = np.empty((h, w, 4), np.uint16)
+        N.check(L.sar_runtime_image_download(frame.rt, 0, 0, img.ctypes.data_as(N._u16p), None))
+        for (a, m, c, s_, z) in parts:
+            count[a:a + m], steps[a:a + m], zbuf[a:a + m] = c, s_, z
+        ocfg = cfg.to_pod()
+        ocfg.iterations = frame.iterations_per_job
+        ort = O.Runtime(w, h)
+        O.render_jobs_mt(ocfg, ort, O.seed_points(seed, 0, lanes * jpt * world))
+        oimg = O.colorize(ocfg, ort)
+        d = np.abs(img.astype(np.int32) - oimg.astype(np.int32))
+        checks = {
+            "count": bool(np.array_equal(count, ort.count)),
+            "zbuf": bool(np.array_equal(zbuf.view(np.uint32), ort.zbuf.view(np.uint32))),
+            "steps": bool(np.array_equal(steps.view(np.uint64), ort.steps.view(np.uint64))),
+            # the device-resident frame cannot read max back; when max + 1 is beyond the host-libm ln table
+            # (solar-sail's NaN sink) the log base comes from the device log: <= 1 LSB (DESIGN.md §3)
+            "image": bool(d.max() == 0) if ort.max + 1 < (1 << 20) else bool(d.max() <= 1 and (d > 0).mean() < 1e-4),
+            "image_exact": bool(d.max() == 0),
+            "vs": "oracle",
+            "frame": f"{preset}{' depth' if depth else ''} {w}x{h}, {world} rank(s) x {lanes * jpt} jobs x {frame.iterations_per_job} iterations",
+            "recorded": int(ort.count.sum(dtype=np.uint64)), "max": int(ort.max),
+        }
+    if rank == 0:
+        N.check(L.sar_stream_synchronize(frame.rt, sp))
+    if group is not None:
+        D.barrier(group)
+    frame.close()
+    return checks
+
+
+# --------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------
 def run_ours(args):
@@ -173,6 +252,9 @@ def run_ours(args):
     if args.preset != "poisson-saturne":
         cfg.angle = 3.839724354387525   # 220 degrees (BASELINE configs[2])
     cfg.width, cfg.height, cfg.transparent = WIDTH, HEIGHT, False
+    strong = args.scaling == "strong"
+    if strong:                                   # fixed total work: ITERATIONS over the whole job, 1/N of it per GPU
+        ITERATIONS = ITERATIONS // world
     lanes = args.lanes or 0
     jpt = args.jobs_per_thread
     frame = D.Frame(cfg, device=local, world=world, rank=rank, group=group, lanes=lanes, jobs_per_thread=jpt,
@@ -256,9 +338,10 @@ def run_ours(args):
     if rank == 0:
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "width": WIDTH, "height": HEIGHT, "iterations_per_gpu": ITERATIONS,
+                       "iterations_per_frame": ITERATIONS * world,
                        "lanes_per_gpu": frame.lanes, "jobs_per_thread": jpt, "iterations_per_job": frame.iterations_per_job,
                        "warmup_iterations_per_job": 1000, "seed": SEED,
                        "l2": "256 MB buffer written between timed steps (L2 flush); accumulators (96 MB) are rewritten by reset each step",
@@ -278,7 +361,15 @@ def run_ours(args):
                                        "frac": frame.recorded_iterations_local() / (it_ms * 1e-3) / 127.9e9,
                                        "peak_source": "tools/micro_atomics.cu, ATOM.ADD.64 uniform random over 32 MB, 1x B200"}},
         }
+    frame.check_sync()
     frame.close()
+    # ---- parity of the N-rank path against the oracle (small frames, outside the timed regions) ------
+    if not args.no_parity:
+        p1 = parity_frame(world, rank, local, group, "solar", depth=False)
+        p2 = parity_frame(world, rank, local, group, "poisson", depth=True)
+        if rank == 0:
+            out["parity"] = {k: bool(p1[k] and p2[k]) for k in ("count", "zbuf", "steps", "image")}
+            out["parity"].update({"vs": "oracle", "frames": [p1, p2]})
     if rank == 0 and world == 1 and not args.no_cpu_baseline and not (args.size or args.iterations_per_gpu or args.preset != "poisson-saturne"):
         threads = os.cpu_count() or 8
         iters = cpu_sample_size(threads)
@@ -304,6 +395,9 @@ def main():
     ap.add_argument("--lanes", type=int, default=0, help="trajectory lanes per GPU (0 = library default, SM count x 896)")
     ap.add_argument("--jobs-per-thread", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the N-rank-vs-oracle parity frames")
+    ap.add_argument("--scaling", choices=["weak", "strong"], default="weak",
+                    help="weak (default): 1e9 iterations per GPU; strong: 1e9 iterations per frame, split over the GPUs")
     ap.add_argument("--preset", choices=["poisson-saturne", "solar-sail"], default="poisson-saturne")
     ap.add_argument("--size", default="", help="WxH override (default 2048x2048)")
     ap.add_argument("--iterations-per-gpu", default="", help="override of 1e9")

@@ -270,11 +270,13 @@ void sar_host_free(void *p);
 
 /* Cross-process peer access (one process per GPU, NVLink P2P via CUDA IPC).
  * A Runtime's accumulators and image live in ONE device allocation; export
- * gives its 64-byte cudaIpcMemHandle.  Each rank opens every peer's handle,
- * then sar_runtime_merge_peers_async() reduces ITS row stripe
- * [row0,row0+rows) over all ranks by reading peer memory directly: counts
- * add, the Δp record with the greatest (z, earlier job) wins — the
- * deterministic form of Runtime::merge (lib.rs:708-738), DESIGN.md §6. */
+ * gives its 64-byte cudaIpcMemHandle and each rank opens every peer's handle
+ * (the frame protocol below reads and writes peer memory through them).
+ * sar_runtime_merge_peers_async() is the plain building block: it reduces rows
+ * [row0,row0+rows) of `rt` with the given Runtimes' accumulators by direct
+ * loads — counts add, the Δp record with the greatest (z, earlier job) wins,
+ * the deterministic form of Runtime::merge (lib.rs:708-738) — with no
+ * synchronisation of its own (the in-process multi-device renderer uses it). */
 #define SAR_IPC_HANDLE_BYTES 64u
 int  sar_runtime_ipc_export(const sar_runtime *rt, uint8_t out[SAR_IPC_HANDLE_BYTES]);
 int  sar_peer_open(const uint8_t handle[SAR_IPC_HANDLE_BYTES], uint32_t width, uint32_t height,
@@ -282,24 +284,57 @@ int  sar_peer_open(const uint8_t handle[SAR_IPC_HANDLE_BYTES], uint32_t width, u
 void sar_peer_close(sar_peer *p);
 int  sar_runtime_merge_peers_async(sar_runtime *rt, sar_peer *const *peers, int n_peers,
                                    uint32_t row0, uint32_t rows, void *stream);
-/* Device-side synchronisation between the ranks of a frame, with no host round
- * trip: every Runtime holds one flag per (kind, source rank) in its exported
- * allocation.  signal: a 1-block kernel that stores `epoch` into flag[kind]
- * [my_rank] of every target (peers, and this runtime if include_self) — remote
- * stores over NVLink, ordered after all earlier work on `stream`.  wait: a
- * 1-block kernel that polls this runtime's own flags [kind][0..n_ranks) until
- * all are >= epoch (gives up after ~10 s and records an error instead of
- * hanging the GPU; see sar_runtime_sync_error).  exchange_max: the all-reduce
- * (max) of Runtime.max over the ranks' stripes (lib.rs:860's log base is
- * global): publish this rank's value to everyone, wait for all, take the max. */
-enum { SAR_SYNC_RENDER_DONE = 0, SAR_SYNC_MERGE_DONE = 1, SAR_SYNC_MAX_READY = 2,
-       SAR_SYNC_IMAGE_DONE = 3, SAR_SYNC_IMAGE_FREE = 4 };
-int  sar_runtime_signal_async(sar_runtime *rt, sar_peer *const *peers, int n_peers, int include_self,
-                              int kind, int my_rank, uint32_t epoch, void *stream);
-int  sar_runtime_wait_async(sar_runtime *rt, int kind, int n_ranks, uint32_t epoch, void *stream);
-int  sar_runtime_exchange_max_async(sar_runtime *rt, sar_peer *const *peers, int n_peers, int my_rank,
-                                    uint32_t epoch, void *stream);
-int  sar_runtime_sync_error(sar_runtime *rt, uint32_t *error);
+/* One frame of render_parallel (lib.rs:1051-1082) over N ranks (one process per
+ * GPU), with NO host round trip: rank r renders its slice of the jobs into its
+ * own Runtime, then reduces and colourises ROW STRIPE r of the frame.  Every
+ * Runtime holds, inside its exported allocation, one flag per (event kind,
+ * source rank); a rank announces an event by storing the frame epoch into that
+ * flag on its targets (remote stores over NVLink) and waits by polling its own
+ * memory.  Waits and signals are the prologues / epilogues of the kernels below,
+ * not launches of their own.  `peers_by_rank[r]` = sar_peer of rank r (entry
+ * my_rank is ignored, may be NULL); `epoch` = frame number, starting at 1 and
+ * growing by 1 per frame on every rank.  Per frame, on one stream, each rank
+ * enqueues:
+ *   sar_frame_reset_async      wait until every peer has finished reading this
+ *                              rank's accumulators of frame epoch-1, then
+ *                              Runtime::reset (lib.rs:682; job_base = 0)
+ *   sar_runtime_set_job_base(first global job of the rank) + a render call
+ *   sar_frame_export_async     counts -> pixel-order u32 array peers can read
+ *                              with coalesced loads; RENDER_DONE to every rank
+ *   sar_frame_merge_async      wait RENDER_DONE from all; rows [row0,row0+rows):
+ *                              counts add, the record with the greatest
+ *                              (z, earlier job) wins — Runtime::merge
+ *                              (lib.rs:708-738) made order-independent; the
+ *                              stripe's share of Runtime.max and of the Depth
+ *                              min/max (lib.rs:877-882) goes to every rank;
+ *                              MAX_READY + MERGE_DONE
+ *   sar_frame_colorize_async   wait MAX_READY from all (the log base of
+ *                              lib.rs:860 and the Depth range are global) and
+ *                              IMAGE_FREE(epoch-1) from the owner; colorize
+ *                              (lib.rs:841) of the stripe straight into rank
+ *                              `owner_rank`'s image; IMAGE_DONE to the owner
+ * and the owner additionally
+ *   sar_frame_image_wait_async wait IMAGE_DONE from all: the image is complete
+ *   (sar_runtime_image_download, or any use of the image on `stream`)
+ *   sar_frame_image_release_async  IMAGE_FREE to every rank.
+ * The N-rank frame is bit-identical to the same job list rendered on one GPU.
+ * A wait that sees no progress for "sync_timeout_ms" (sar_set_option, default
+ * 10 000) records an error instead of hanging the GPU; every later kernel of the
+ * protocol on that Runtime then does nothing.  sar_runtime_sync_error reads the
+ * error (0 = none, else 1 + the event kind that timed out) and optionally clears
+ * it: check it whenever a frame's result is consumed. */
+int  sar_frame_reset_async(sar_runtime *rt, int n_ranks, uint32_t epoch, void *stream);
+int  sar_frame_export_async(sar_runtime *rt, sar_peer *const *peers_by_rank, int n_ranks, int my_rank,
+                            uint32_t epoch, void *stream);
+int  sar_frame_merge_async(sar_runtime *rt, sar_peer *const *peers_by_rank, int n_ranks, int my_rank,
+                           uint32_t row0, uint32_t rows, uint32_t epoch, void *stream);
+int  sar_frame_colorize_async(const sar_config *cfg, sar_runtime *rt, sar_peer *const *peers_by_rank,
+                              int n_ranks, int my_rank, int owner_rank, uint32_t row0, uint32_t rows,
+                              uint32_t epoch, void *stream);
+int  sar_frame_image_wait_async(sar_runtime *rt, int n_ranks, uint32_t epoch, void *stream);
+int  sar_frame_image_release_async(sar_runtime *rt, sar_peer *const *peers_by_rank, int n_ranks, int my_rank,
+                                   uint32_t epoch, void *stream);
+int  sar_runtime_sync_error(sar_runtime *rt, uint32_t *error, int clear);
 
 #ifdef __cplusplus
 }

@@ -14,7 +14,6 @@ SAR_OK, SAR_ERR_INVALID, SAR_ERR_DIMS, SAR_ERR_CUDA, SAR_ERR_NOMEM, SAR_ERR_UNSU
 SAR_RENDER_GAS, SAR_RENDER_DEPTH = 0, 1
 SAR_CT_POISSON_SATURNE, SAR_CT_ADJUSTED_VELOCITY = 0, 1
 SAR_SEQ_SHARED_POINTS = 1
-SYNC_RENDER_DONE, SYNC_MERGE_DONE, SYNC_MAX_READY, SYNC_IMAGE_DONE, SYNC_IMAGE_FREE = range(5)
 FRAME_CALLBACK = C.CFUNCTYPE(None, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint16))
 
 
@@ -103,10 +102,13 @@ SYMBOLS = {
     "sar_peer_open": (C.c_int, [_u8p, C.c_uint32, C.c_uint32, C.c_int, _P(_vp)]),
     "sar_peer_close": (None, [_vp]),
     "sar_runtime_merge_peers_async": (C.c_int, [_vp, _P(_vp), C.c_int, C.c_uint32, C.c_uint32, _vp]),
-    "sar_runtime_signal_async": (C.c_int, [_vp, _P(_vp), C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, _vp]),
-    "sar_runtime_wait_async": (C.c_int, [_vp, C.c_int, C.c_int, C.c_uint32, _vp]),
-    "sar_runtime_exchange_max_async": (C.c_int, [_vp, _P(_vp), C.c_int, C.c_int, C.c_uint32, _vp]),
-    "sar_runtime_sync_error": (C.c_int, [_vp, _u32p]),
+    "sar_frame_reset_async": (C.c_int, [_vp, C.c_int, C.c_uint32, _vp]),
+    "sar_frame_export_async": (C.c_int, [_vp, _P(_vp), C.c_int, C.c_int, C.c_uint32, _vp]),
+    "sar_frame_merge_async": (C.c_int, [_vp, _P(_vp), C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, _vp]),
+    "sar_frame_colorize_async": (C.c_int, [_cfgp, _vp, _P(_vp), C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, _vp]),
+    "sar_frame_image_wait_async": (C.c_int, [_vp, C.c_int, C.c_uint32, _vp]),
+    "sar_frame_image_release_async": (C.c_int, [_vp, _P(_vp), C.c_int, C.c_int, C.c_uint32, _vp]),
+    "sar_runtime_sync_error": (C.c_int, [_vp, _u32p, C.c_int]),
 }
 
 _lib = None

@@ -51,12 +51,13 @@ struct sar_runtime {
     size_t npix = 0;
     size_t nslots = 0;               // power of two >= npix: size of the scrambled `fast` array
     SlotMap slots = {1u, 0u};
-    // one device allocation: rec | fast | image | scal   (so one IPC handle exports it all)
+    // one device allocation: rec | fast | image | cnt | scal   (so one IPC handle exports it all)
     void *block = nullptr;
     size_t block_bytes = 0;
     ulonglong2 *rec = nullptr;
     unsigned long long *fast = nullptr;
     uint16_t *image = nullptr;       // RGBA u16, FinalImage (lib.rs:625)
+    uint32_t *cnt = nullptr;         // counts in pixel order: what peers read in the multi-GPU exchange
     Scalars *scal = nullptr;
     cudaStream_t stream = nullptr;
     uint64_t job_base = 0;
@@ -77,6 +78,7 @@ struct sar_peer {
     ulonglong2 *rec = nullptr;
     unsigned long long *fast = nullptr;
     uint16_t *image = nullptr;
+    uint32_t *cnt = nullptr;
     Scalars *scal = nullptr;
 };
 
@@ -114,12 +116,16 @@ static SlotMap slotmap_for(size_t npix)
     return m;
 }
 
-static void layout(size_t npix, size_t &off_fast, size_t &off_image, size_t &off_scal, size_t &total)
+struct Layout { size_t fast, image, cnt, scal, total; };   // rec sits at offset 0
+static Layout layout(size_t npix)
 {
-    off_fast = align_up(npix * sizeof(ulonglong2), 256);
-    off_image = off_fast + align_up(slots_for(npix) * sizeof(unsigned long long), 256);
-    off_scal = off_image + align_up(npix * 4 * sizeof(uint16_t), 256);
-    total = off_scal + 1024;
+    Layout l;
+    l.fast = align_up(npix * sizeof(ulonglong2), 256);
+    l.image = l.fast + align_up(slots_for(npix) * sizeof(unsigned long long), 256);
+    l.cnt = l.image + align_up(npix * 4 * sizeof(uint16_t), 256);
+    l.scal = l.cnt + align_up(npix * sizeof(uint32_t) + 16, 256);      // pixel-order counts of the multi-GPU exchange (+ one group of slack)
+    l.total = l.scal + 1024;
+    return l;
 }
 
 static cudaStream_t pick(const sar_runtime *rt, void *stream) { return stream ? (cudaStream_t)stream : rt->stream; }
@@ -242,6 +248,11 @@ int sar_set_option(const char *name, int64_t value)
         if (!set_traj_per_thread((int)value)) return fail(SAR_ERR_INVALID, "traj_per_thread must be 1, 2 or 4");
         return SAR_OK;
     }
+    if (strcmp(name, "sync_timeout_ms") == 0) {
+        if (value < 1 || value > 3600000) return fail(SAR_ERR_INVALID, "sync_timeout_ms must be in 1..3600000");
+        set_sync_timeout_ms(value);
+        return SAR_OK;
+    }
     if (strcmp(name, "pipeline") == 0) {
         if (!set_pipeline((int)value)) return fail(SAR_ERR_INVALID, "pipeline must be 0 or 1");
         return SAR_OK;
@@ -357,15 +368,15 @@ int sar_runtime_new(uint32_t width, uint32_t height, int device, sar_runtime **o
     if (!rt) return fail(SAR_ERR_NOMEM, "host allocation failed");
     rt->device = device; rt->w = width; rt->h = height; rt->npix = (size_t)width * height;
     rt->nslots = slots_for(rt->npix); rt->slots = slotmap_for(rt->npix);
-    size_t of, oi, os, total;
-    layout(rt->npix, of, oi, os, total);
-    cudaError_t e = cudaMalloc(&rt->block, total);
-    if (e != cudaSuccess) { (void)cudaGetLastError(); delete rt; return fail(SAR_ERR_NOMEM, "cudaMalloc(%zu bytes): %s", total, cudaGetErrorString(e)); }
-    rt->block_bytes = total;
+    const Layout lay = layout(rt->npix);
+    cudaError_t e = cudaMalloc(&rt->block, lay.total);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); delete rt; return fail(SAR_ERR_NOMEM, "cudaMalloc(%zu bytes): %s", lay.total, cudaGetErrorString(e)); }
+    rt->block_bytes = lay.total;
     rt->rec = (ulonglong2 *)rt->block;
-    rt->fast = (unsigned long long *)((char *)rt->block + of);
-    rt->image = (uint16_t *)((char *)rt->block + oi);
-    rt->scal = (Scalars *)((char *)rt->block + os);
+    rt->fast = (unsigned long long *)((char *)rt->block + lay.fast);
+    rt->image = (uint16_t *)((char *)rt->block + lay.image);
+    rt->cnt = (uint32_t *)((char *)rt->block + lay.cnt);
+    rt->scal = (Scalars *)((char *)rt->block + lay.scal);
     e = cudaStreamCreateWithFlags(&rt->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { cudaFree(rt->block); delete rt; return fail(SAR_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
     cudaMemsetAsync(rt->scal, 0, 1024, rt->stream);         // flags/epochs start at 0; reset never touches them
@@ -487,11 +498,10 @@ int sar_runtime_merge(sar_runtime *dst, const sar_runtime *src)
     if (src->device != dst->device) {   // stage the source accumulators on dst's device
         if (int rc = ensure_scratch(dst, src->block_bytes)) return rc;
         SAR_CUDA(cudaMemcpyPeerAsync(dst->d_scratch, dst->device, src->block, src->device, src->block_bytes, dst->stream));
-        size_t of, oi, os, total;
-        layout(src->npix, of, oi, os, total);
+        const Layout lay = layout(src->npix);
         srec = (const ulonglong2 *)dst->d_scratch;
-        sfast = (const unsigned long long *)((char *)dst->d_scratch + of);
-        sscal = (const Scalars *)((char *)dst->d_scratch + os);
+        sfast = (const unsigned long long *)((char *)dst->d_scratch + lay.fast);
+        sscal = (const Scalars *)((char *)dst->d_scratch + lay.scal);
     }
     launch_merge(dst->fast, dst->rec, dst->scal, sfast, srec, sscal, dst->npix, dst->slots, dst->stream);
     SAR_CUDA(cudaGetLastError());
@@ -693,14 +703,14 @@ int sar_runtime_ipc_export(const sar_runtime *rt, uint8_t out[SAR_IPC_HANDLE_BYT
 
 static void peer_view(sar_peer *p, void *block, uint32_t w, uint32_t h)
 {
-    size_t of, oi, os, total;
-    layout((size_t)w * h, of, oi, os, total);
+    const Layout lay = layout((size_t)w * h);
     p->w = w; p->h = h; p->block = block;
     p->slots = slotmap_for((size_t)w * h);
     p->rec = (ulonglong2 *)block;
-    p->fast = (unsigned long long *)((char *)block + of);
-    p->image = (uint16_t *)((char *)block + oi);
-    p->scal = (Scalars *)((char *)block + os);
+    p->fast = (unsigned long long *)((char *)block + lay.fast);
+    p->image = (uint16_t *)((char *)block + lay.image);
+    p->cnt = (uint32_t *)((char *)block + lay.cnt);
+    p->scal = (Scalars *)((char *)block + lay.scal);
 }
 
 int sar_peer_open(const uint8_t handle[SAR_IPC_HANDLE_BYTES], uint32_t width, uint32_t height, int local_device, sar_peer **out)
@@ -750,65 +760,114 @@ int sar_runtime_merge_peers_async(sar_runtime *rt, sar_peer *const *peers, int n
     return SAR_OK;
 }
 
-// ---- device-side cross-GPU synchronisation ---------------------------------------
-static int make_scal_list(sar_runtime *rt, sar_peer *const *peers, int n_peers, bool include_self, ScalList &out)
+// ---- cross-GPU frame protocol: one process per GPU, device-side synchronisation -------
+static int make_frame_sync(sar_runtime *rt, sar_peer *const *peers_by_rank, int n_ranks, int my_rank, uint32_t epoch,
+                           FrameSync &S, PeerList *pl)
 {
-    if (n_peers < 0 || n_peers + (include_self ? 1 : 0) > SYNC_MAX_RANKS) return fail(SAR_ERR_INVALID, "too many ranks");
-    memset(&out, 0, sizeof out);
-    int k = 0;
-    if (include_self) out.scal[k++] = rt->scal;
-    for (int i = 0; i < n_peers; ++i) {
-        if (!peers || !peers[i]) return fail(SAR_ERR_INVALID, "peer %d is NULL", i);
-        out.scal[k++] = peers[i]->scal;
+    if (!rt) return fail(SAR_ERR_INVALID, "runtime is NULL");
+    if (n_ranks < 1 || n_ranks > SYNC_MAX_RANKS || my_rank < 0 || my_rank >= n_ranks)
+        return fail(SAR_ERR_INVALID, "bad rank %d of %d (at most %d ranks)", my_rank, n_ranks, SYNC_MAX_RANKS);
+    if (n_ranks > 1 && !peers_by_rank) return fail(SAR_ERR_INVALID, "peers_by_rank is NULL");
+    memset(&S, 0, sizeof S);
+    if (pl) memset(pl, 0, sizeof *pl);
+    S.n_ranks = n_ranks; S.my_rank = my_rank; S.epoch = epoch;
+    for (int r = 0; r < n_ranks; ++r) {
+        if (r == my_rank) { S.scal[r] = rt->scal; continue; }
+        const sar_peer *p = peers_by_rank[r];
+        if (!p) return fail(SAR_ERR_INVALID, "peer %d is NULL", r);
+        if (p->w != rt->w || p->h != rt->h) return fail(SAR_ERR_DIMS, "peer %d is %ux%u, runtime %ux%u", r, p->w, p->h, rt->w, rt->h);
+        S.scal[r] = p->scal;
+        if (pl) { pl->fast[pl->n] = p->fast; pl->rec[pl->n] = p->rec; pl->scal[pl->n] = p->scal; pl->cnt[pl->n] = p->cnt; ++pl->n; }
     }
-    out.n = k;
+    return SAR_OK;
+}
+static int check_rows(const sar_runtime *rt, uint32_t &row0, uint32_t &rows)
+{
+    if (rows == 0) { row0 = 0; rows = rt->h; }
+    if ((uint64_t)row0 + rows > rt->h) return fail(SAR_ERR_INVALID, "rows [%u,%u) outside image height %u", row0, row0 + rows, rt->h);
     return SAR_OK;
 }
 
-int sar_runtime_signal_async(sar_runtime *rt, sar_peer *const *peers, int n_peers, int include_self, int kind,
-                             int my_rank, uint32_t epoch, void *stream)
+int sar_frame_reset_async(sar_runtime *rt, int n_ranks, uint32_t epoch, void *stream)
 {
     if (!rt) return fail(SAR_ERR_INVALID, "runtime is NULL");
-    if (kind < 0 || kind >= SYNC_KINDS || my_rank < 0 || my_rank >= SYNC_MAX_RANKS) return fail(SAR_ERR_INVALID, "bad kind/rank");
-    ScalList t;
-    if (int rc = make_scal_list(rt, peers, n_peers, include_self != 0, t)) return rc;
+    if (n_ranks < 1 || n_ranks > SYNC_MAX_RANKS) return fail(SAR_ERR_INVALID, "bad n_ranks %d", n_ranks);
     SAR_CUDA(cudaSetDevice(rt->device));
-    launch_signal(t, kind, my_rank, epoch, pick(rt, stream));
+    launch_frame_reset(rt->fast, rt->rec, rt->scal, rt->npix, rt->nslots, n_ranks, epoch, pick(rt, stream));
+    SAR_CUDA(cudaGetLastError());
+    rt->job_base = 0;
+    rt->host_max_valid = false;
+    return SAR_OK;
+}
+
+int sar_frame_export_async(sar_runtime *rt, sar_peer *const *peers_by_rank, int n_ranks, int my_rank, uint32_t epoch, void *stream)
+{
+    FrameSync S;
+    if (int rc = make_frame_sync(rt, peers_by_rank, n_ranks, my_rank, epoch, S, nullptr)) return rc;
+    SAR_CUDA(cudaSetDevice(rt->device));
+    launch_frame_export(rt->fast, rt->scal, rt->cnt, rt->npix, rt->slots, S, pick(rt, stream));
     SAR_CUDA(cudaGetLastError());
     return SAR_OK;
 }
 
-int sar_runtime_wait_async(sar_runtime *rt, int kind, int n_ranks, uint32_t epoch, void *stream)
+int sar_frame_merge_async(sar_runtime *rt, sar_peer *const *peers_by_rank, int n_ranks, int my_rank, uint32_t row0, uint32_t rows,
+                          uint32_t epoch, void *stream)
 {
-    if (!rt) return fail(SAR_ERR_INVALID, "runtime is NULL");
-    if (kind < 0 || kind >= SYNC_KINDS || n_ranks < 0 || n_ranks > SYNC_MAX_RANKS) return fail(SAR_ERR_INVALID, "bad kind/n_ranks");
+    FrameSync S;
+    PeerList pl;
+    if (int rc = make_frame_sync(rt, peers_by_rank, n_ranks, my_rank, epoch, S, &pl)) return rc;
+    if (int rc = check_rows(rt, row0, rows)) return rc;
     SAR_CUDA(cudaSetDevice(rt->device));
-    launch_wait(rt->scal, kind, n_ranks, epoch, pick(rt, stream));
-    SAR_CUDA(cudaGetLastError());
-    return SAR_OK;
-}
-
-int sar_runtime_exchange_max_async(sar_runtime *rt, sar_peer *const *peers, int n_peers, int my_rank, uint32_t epoch, void *stream)
-{
-    if (!rt) return fail(SAR_ERR_INVALID, "runtime is NULL");
-    if (my_rank < 0 || my_rank >= SYNC_MAX_RANKS) return fail(SAR_ERR_INVALID, "bad rank");
-    ScalList t;
-    if (int rc = make_scal_list(rt, peers, n_peers, true, t)) return rc;
-    SAR_CUDA(cudaSetDevice(rt->device));
-    cudaStream_t s = pick(rt, stream);
-    launch_publish_max(rt->scal, t, my_rank, epoch, s);
-    launch_wait(rt->scal, SYNC_MAX_READY, t.n, epoch, s);
-    launch_gather_max(rt->scal, t.n, s);
+    launch_frame_merge(rt->fast, rt->rec, rt->cnt, rt->scal, pl, (size_t)row0 * rt->w, (size_t)rows * rt->w, rt->slots, S, pick(rt, stream));
     SAR_CUDA(cudaGetLastError());
     rt->host_max_valid = false;
     return SAR_OK;
 }
 
-int sar_runtime_sync_error(sar_runtime *rt, uint32_t *error)
+int sar_frame_colorize_async(const sar_config *cfg, sar_runtime *rt, sar_peer *const *peers_by_rank, int n_ranks, int my_rank,
+                             int owner_rank, uint32_t row0, uint32_t rows, uint32_t epoch, void *stream)
+{
+    FrameSync S;
+    if (int rc = make_frame_sync(rt, peers_by_rank, n_ranks, my_rank, epoch, S, nullptr)) return rc;
+    if (int rc = check_config(cfg, rt)) return rc;
+    if (int rc = check_rows(rt, row0, rows)) return rc;
+    if (owner_rank < 0 || owner_rank >= n_ranks) return fail(SAR_ERR_INVALID, "bad owner rank %d", owner_rank);
+    SAR_CUDA(cudaSetDevice(rt->device));
+    ColorParams cp;
+    make_color_params(cfg, rt, cp, row0, rows);
+    uint16_t *image = owner_rank == my_rank ? rt->image : peers_by_rank[owner_rank]->image;
+    launch_frame_colorize(cp, rt->cnt, rt->rec, rt->scal, image, S, owner_rank, pick(rt, stream));
+    SAR_CUDA(cudaGetLastError());
+    rt->host_max_valid = false;
+    return SAR_OK;
+}
+
+int sar_frame_image_wait_async(sar_runtime *rt, int n_ranks, uint32_t epoch, void *stream)
+{
+    if (!rt) return fail(SAR_ERR_INVALID, "runtime is NULL");
+    if (n_ranks < 1 || n_ranks > SYNC_MAX_RANKS) return fail(SAR_ERR_INVALID, "bad n_ranks %d", n_ranks);
+    SAR_CUDA(cudaSetDevice(rt->device));
+    launch_wait(rt->scal, SYNC_IMAGE_DONE, n_ranks, epoch, pick(rt, stream));
+    SAR_CUDA(cudaGetLastError());
+    return SAR_OK;
+}
+
+int sar_frame_image_release_async(sar_runtime *rt, sar_peer *const *peers_by_rank, int n_ranks, int my_rank, uint32_t epoch, void *stream)
+{
+    FrameSync S;
+    if (int rc = make_frame_sync(rt, peers_by_rank, n_ranks, my_rank, epoch, S, nullptr)) return rc;
+    SAR_CUDA(cudaSetDevice(rt->device));
+    launch_signal(S, SYNC_IMAGE_FREE, pick(rt, stream));
+    SAR_CUDA(cudaGetLastError());
+    return SAR_OK;
+}
+
+int sar_runtime_sync_error(sar_runtime *rt, uint32_t *error, int clear)
 {
     if (!rt || !error) return fail(SAR_ERR_INVALID, "NULL argument");
     SAR_CUDA(cudaSetDevice(rt->device));
     SAR_CUDA(cudaMemcpy(error, &rt->scal->sync_error, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (clear && *error) SAR_CUDA(cudaMemset(&rt->scal->sync_error, 0, sizeof(uint32_t)));
     return SAR_OK;
 }
 

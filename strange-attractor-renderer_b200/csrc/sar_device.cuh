@@ -75,7 +75,10 @@ struct Scalars {                      // device-resident scalar state of a Runti
     unsigned int sync_error;          // a wait timed out
     unsigned int pad2[3];
     unsigned int flag[SYNC_KINDS][SYNC_MAX_RANKS];
-    unsigned int stripe_max[SYNC_MAX_RANKS];   // rank r's share of Runtime.max for the current frame
+    unsigned int stripe_max[SYNC_MAX_RANKS];   // rank r's share of Runtime.max for the current frame (lib.rs:721-723)
+    unsigned int stripe_zmax[SYNC_MAX_RANKS];  // ... and of the Depth fold (lib.rs:877-882), as canonical z keys
+    unsigned int stripe_zmin[SYNC_MAX_RANKS];
+    unsigned int done_counter[4];              // blocks that have finished the export / merge / colourise kernel of the frame
 };
 static_assert(sizeof(Scalars) <= 1024, "Scalars must fit its slot of the runtime allocation");
 
@@ -133,17 +136,24 @@ void launch_pack(unsigned long long *fast, ulonglong2 *rec, Scalars *scal, size_
 void launch_merge(unsigned long long *dfast, ulonglong2 *drec, Scalars *dscal,
                   const unsigned long long *sfast, const ulonglong2 *srec, const Scalars *sscal,
                   size_t npix, SlotMap slots, cudaStream_t s);
-// deterministic all-ranks merge of one row stripe by direct peer loads; (z, ~job) max
-struct PeerList { const unsigned long long *fast[16]; const ulonglong2 *rec[16]; const Scalars *scal[16]; int n; };
+// deterministic merge with other Runtimes by direct loads: counts add, the record with the greatest (z, ~job) wins
+struct PeerList { const unsigned long long *fast[16]; const ulonglong2 *rec[16]; const Scalars *scal[16]; const uint32_t *cnt[16]; int n; };
 void launch_merge_peers(unsigned long long *dfast, ulonglong2 *drec, Scalars *dscal, const PeerList &peers,
                         size_t pix0, size_t npix, SlotMap slots, cudaStream_t s);
 void launch_seed_points(unsigned long long seed, unsigned long long first, unsigned long long n, double *out, cudaStream_t s);
-// device-side cross-GPU synchronisation: remote flag stores and local polling
-struct ScalList { Scalars *scal[SYNC_MAX_RANKS]; int n; };
-void launch_signal(const ScalList &targets, int kind, int my_rank, unsigned int epoch, cudaStream_t s);
+// cross-GPU frame protocol: waits and signals are prologues / epilogues of these kernels
+struct FrameSync { Scalars *scal[SYNC_MAX_RANKS]; int n_ranks, my_rank; unsigned int epoch; };   // every rank's scalars, by rank
+void launch_frame_reset(unsigned long long *fast, ulonglong2 *rec, Scalars *scal, size_t npix, size_t nslots,
+                        int n_ranks, unsigned int epoch, cudaStream_t s);
+void launch_frame_export(const unsigned long long *fast, Scalars *scal, uint32_t *cnt, size_t npix, SlotMap slots,
+                         const FrameSync &S, cudaStream_t s);
+void launch_frame_merge(unsigned long long *dfast, ulonglong2 *drec, uint32_t *dcnt, Scalars *dscal, const PeerList &peers,
+                        size_t pix0, size_t npix, SlotMap slots, const FrameSync &S, cudaStream_t s);
+void launch_frame_colorize(const ColorParams &cp, const uint32_t *cnt, const ulonglong2 *rec, Scalars *scal, uint16_t *rgba_u16,
+                           const FrameSync &S, int owner, cudaStream_t s);
+void launch_signal(const FrameSync &S, int kind, cudaStream_t s);
 void launch_wait(Scalars *mine, int kind, int n_ranks, unsigned int epoch, cudaStream_t s);
-void launch_publish_max(Scalars *mine, const ScalList &targets, int my_rank, unsigned int epoch, cudaStream_t s);
-void launch_gather_max(Scalars *mine, int n_ranks, cudaStream_t s);
+void set_sync_timeout_ms(long long ms);
 unsigned long long launch_count();
 bool set_mode(int mode);     // SAR_DIAGNOSTICS builds only: 0 = product path; 1, 2, 4 = roofline experiments (incomplete results)
 bool set_pipeline(int on);          // tuning: depth test one iteration behind its atomic (0/1); never changes results

@@ -548,6 +548,80 @@ void launch_max(const unsigned long long *fast, const ulonglong2 *rec, Scalars *
 }
 
 // ---------------------------------------------------------------------------------------------
+// Cross-GPU frame protocol without the host (one process per GPU).  Every rank keeps,
+// inside its exported allocation, one flag per (kind, source rank).  A source rank announces an
+// event by storing the frame epoch into that flag on every target (a remote store over NVLink,
+// release at system scope); a target polls its OWN memory.  The waits and signals are the prologues
+// and epilogues of the kernels that need them — reset, export, merge, colourise — not launches of
+// their own:
+//   prologue  every block polls the local flags it depends on (frame_wait);
+//   epilogue  every thread fences its writes to system scope, the block counts itself in, and the
+//             last block to do so stores the flags (frame_last_block).
+// A wait that sees no progress for sync_timeout (default ~10 s) records sync_error; every later
+// kernel of the protocol then does nothing, so a dead peer costs a timeout, never a GPU hang or a
+// frame computed from half-delivered data.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys(unsigned int *p, unsigned int v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int *p)
+{
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+static std::atomic<long long> g_sync_timeout_cycles{20000000000ll};   // ~10 s at 1.965 GHz
+void set_sync_timeout_ms(long long ms) { g_sync_timeout_cycles = ms * 1965000ll; }
+
+// All threads of the block call this.  Threads [0, n) poll mine->flag[kind][first + t] until it
+// reaches `epoch`.  Returns false (for the whole block) if the runtime already carries a sync error
+// or a wait times out.
+__device__ bool frame_wait(Scalars *mine, int kind, int first, int n, unsigned int epoch, long long timeout)
+{
+    __shared__ int s_bad;
+    if (threadIdx.x == 0) s_bad = *((volatile unsigned int *)&mine->sync_error) != 0u;
+    __syncthreads();
+    if ((int)threadIdx.x < n && !s_bad) {
+        const unsigned int *f = &mine->flag[kind][first + threadIdx.x];
+        const long long t0 = clock64();
+        while ((int)(ld_acquire_sys(f) - epoch) < 0) {              // epochs only grow; wrap-safe compare
+            __nanosleep(64);
+            if (clock64() - t0 > timeout) {                          // a peer is gone: give up, do not hang the GPU
+                atomicCAS(&mine->sync_error, 0u, 1u + (unsigned int)kind);
+                s_bad = 1;
+                break;
+            }
+        }
+    }
+    __syncthreads();
+    __threadfence_system();
+    return !s_bad;
+}
+// All threads call this after their last write of the kernel.  True in exactly one block, and only
+// after every block's writes are visible system-wide.  counter: one word per kernel kind, left at 0.
+__device__ bool frame_last_block(unsigned int *counter)
+{
+    __shared__ int s_last;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(counter, 1u);
+        s_last = t == gridDim.x - 1u;
+        if (s_last) *counter = 0u;
+    }
+    __syncthreads();
+    if (s_last) __threadfence_system();
+    return s_last;
+}
+__device__ __forceinline__ void frame_signal(const FrameSync &S, int kind, bool to_all, int only_rank)
+{
+    if ((int)threadIdx.x < S.n_ranks && (to_all || (int)threadIdx.x == only_rank))
+        st_release_sys(&S.scal[threadIdx.x]->flag[kind][S.my_rank], S.epoch);
+}
+
+// ---------------------------------------------------------------------------------------------
 // colorize() (lib.rs:841-904)
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint16_t sat_u16(double v)          // Rust `as u16`: saturating, NaN -> 0
@@ -563,6 +637,52 @@ __device__ __forceinline__ uint16_t sat_u16f(float v)
     return (uint16_t)(u > 65535u ? 65535u : u);
 }
 
+// One pixel of colorize(): Gas (lib.rs:853-874) or Depth (lib.rs:875-900).
+__device__ __forceinline__ void color_pixel(const ColorParams &C, const ulonglong2 r, uint32_t cnt, uint32_t max, double lnmax,
+                                            float zmax, float zmin, ushort4 &px, float4 &fx)
+{
+    if (C.render_kind == 0u) {                              // RenderKind::Gas
+        // Palette::interpolate(steps), lib.rs:442-472
+        double v = __longlong_as_double((long long)r.x);
+        if (v < 0.) v = 0.; else if (v >= 1.) v = 0.999999;
+        v = __dmul_rn(v, C.pal_len);
+        const double fl = floor(v);
+        unsigned int n = (fl > 0.) ? __double2uint_rz(fl) : 0u;   // `as usize`: NaN -> 0
+        if (n > C.palette_len - 1u) n = C.palette_len - 1u;
+        const double t = fmod(v, 1.);                       // `value % 1.`, lib.rs:454
+        const double t1 = __dsub_rn(1.0, t);
+        const double cr = __dsqrt_rn(__dadd_rn(__dmul_rn(C.pal[n + 1][0], t), __dmul_rn(C.pal[n][0], t1)));
+        const double cg = __dsqrt_rn(__dadd_rn(__dmul_rn(C.pal[n + 1][1], t), __dmul_rn(C.pal[n][1], t1)));
+        const double cb = __dsqrt_rn(__dadd_rn(__dmul_rn(C.pal[n + 1][2], t), __dmul_rn(C.pal[n][2], t1)));
+        const uint32_t c1 = cnt + 1u;
+        const double lnc = c1 < C.lnlut_len ? __ldg(C.lnlut + c1) : (cnt == max ? lnmax : log((double)c1));
+        const double factor = __ddiv_rn(lnc, lnmax);        // lib.rs:860
+        const double vr = __dmul_rn(__dadd_rn(__dmul_rn(cr, factor), C.bright_offset), C.bright_factor);
+        const double vg = __dmul_rn(__dadd_rn(__dmul_rn(cg, factor), C.bright_offset), C.bright_factor);
+        const double vb = __dmul_rn(__dadd_rn(__dmul_rn(cb, factor), C.bright_offset), C.bright_factor);
+        px.x = sat_u16(__dmul_rn(vr, 65535.));              // lib.rs:862-864
+        px.y = sat_u16(__dmul_rn(vg, 65535.));
+        px.z = sat_u16(__dmul_rn(vb, 65535.));
+        px.w = C.transparent ? sat_u16(__dmul_rn(factor, 65535.)) : (uint16_t)65535u;  // lib.rs:865-869
+        fx = make_float4((float)vr, (float)vg, (float)vb, C.transparent ? (float)factor : 1.0f);
+    } else {                                                // RenderKind::Depth
+        const uint32_t k = (uint32_t)(r.y >> 32);
+        float zz;
+        if (k == ZKEY_SENTINEL) zz = 0.0f;                  // z == -1.0, lib.rs:889-890
+        else zz = __fdiv_rn(__fsub_rn(__uint_as_float(zbits_from_key(k)), zmin), __fsub_rn(zmax, zmin));
+        const uint16_t g = sat_u16f(__fmul_rn(zz, 65535.0f));                          // lib.rs:895
+        px.x = g; px.y = g; px.z = g; px.w = 65535u;
+        fx = make_float4(zz, zz, zz, 1.0f);
+    }
+}
+// ln(max + 1): from the host when it has read max back (exact: the platform libm the reference's f64::ln
+// resolves to), else from the host-built table, else (max + 1 >= 2^20 on a device-resident path) the device log
+__device__ __forceinline__ double ln_max1(const ColorParams &C, uint32_t max)
+{
+    const uint32_t m1 = max + 1u;                           // f64::from(runtime.max + 1), lib.rs:860
+    return C.host_lnmax_valid ? C.ln_max1_host : (m1 < C.lnlut_len ? C.lnlut[m1] : log((double)m1));
+}
+
 __global__ void __launch_bounds__(256)
 colorize_kernel(const __grid_constant__ ColorParams C, const unsigned long long *__restrict__ fast,
                 const ulonglong2 *__restrict__ rec, const Scalars *__restrict__ scal,
@@ -570,9 +690,10 @@ colorize_kernel(const __grid_constant__ ColorParams C, const unsigned long long 
 {
     __shared__ double s_lnmax;
     __shared__ float s_zmax, s_zmin;
+    __shared__ uint32_t s_max;
     if (threadIdx.x == 0) {
-        const uint32_t m1 = scal->max + 1u;                     // f64::from(runtime.max + 1), lib.rs:860
-        s_lnmax = C.host_lnmax_valid ? C.ln_max1_host : (m1 < C.lnlut_len ? C.lnlut[m1] : log((double)m1));
+        s_max = scal->max;
+        s_lnmax = ln_max1(C, s_max);
         s_zmax = __uint_as_float(zbits_from_key(scal->zmax_key));
         s_zmin = __uint_as_float(zbits_from_key(scal->zmin_key));
     }
@@ -583,40 +704,7 @@ colorize_kernel(const __grid_constant__ ColorParams C, const unsigned long long 
         const size_t p = pix0 + i;
         ushort4 px;
         float4 fx;
-        if (C.render_kind == 0u) {                              // RenderKind::Gas, lib.rs:853-874
-            // Palette::interpolate(steps), lib.rs:442-472
-            double v = __longlong_as_double((long long)rec[p].x);
-            if (v < 0.) v = 0.; else if (v >= 1.) v = 0.999999;
-            v = __dmul_rn(v, C.pal_len);
-            const double fl = floor(v);
-            unsigned int n = (fl > 0.) ? __double2uint_rz(fl) : 0u;   // `as usize`: NaN -> 0
-            if (n > C.palette_len - 1u) n = C.palette_len - 1u;
-            const double t = fmod(v, 1.);                       // `value % 1.`, lib.rs:454
-            const double t1 = __dsub_rn(1.0, t);
-            const double r = __dsqrt_rn(__dadd_rn(__dmul_rn(C.pal[n + 1][0], t), __dmul_rn(C.pal[n][0], t1)));
-            const double g = __dsqrt_rn(__dadd_rn(__dmul_rn(C.pal[n + 1][1], t), __dmul_rn(C.pal[n][1], t1)));
-            const double b = __dsqrt_rn(__dadd_rn(__dmul_rn(C.pal[n + 1][2], t), __dmul_rn(C.pal[n][2], t1)));
-            const uint32_t cnt = pixel_count(fast, scal, p, C.slots);
-            const uint32_t c1 = cnt + 1u;
-            const double lnc = c1 < C.lnlut_len ? __ldg(C.lnlut + c1) : (cnt == scal->max ? s_lnmax : log((double)c1));
-            const double factor = __ddiv_rn(lnc, s_lnmax);       // lib.rs:860
-            const double vr = __dmul_rn(__dadd_rn(__dmul_rn(r, factor), C.bright_offset), C.bright_factor);
-            const double vg = __dmul_rn(__dadd_rn(__dmul_rn(g, factor), C.bright_offset), C.bright_factor);
-            const double vb = __dmul_rn(__dadd_rn(__dmul_rn(b, factor), C.bright_offset), C.bright_factor);
-            px.x = sat_u16(__dmul_rn(vr, 65535.));              // lib.rs:862-864
-            px.y = sat_u16(__dmul_rn(vg, 65535.));
-            px.z = sat_u16(__dmul_rn(vb, 65535.));
-            px.w = C.transparent ? sat_u16(__dmul_rn(factor, 65535.)) : (uint16_t)65535u;  // lib.rs:865-869
-            fx = make_float4((float)vr, (float)vg, (float)vb, C.transparent ? (float)factor : 1.0f);
-        } else {                                                // RenderKind::Depth, lib.rs:875-900
-            const uint32_t k = (uint32_t)(rec[p].y >> 32);
-            float zz;
-            if (k == ZKEY_SENTINEL) zz = 0.0f;                  // z == -1.0, lib.rs:889-890
-            else zz = __fdiv_rn(__fsub_rn(__uint_as_float(zbits_from_key(k)), s_zmin), __fsub_rn(s_zmax, s_zmin));
-            const uint16_t g = sat_u16f(__fmul_rn(zz, 65535.0f));                          // lib.rs:895
-            px.x = g; px.y = g; px.z = g; px.w = 65535u;
-            fx = make_float4(zz, zz, zz, 1.0f);
-        }
+        color_pixel(C, rec[p], pixel_count(fast, scal, p, C.slots), s_max, s_lnmax, s_zmax, s_zmin, px, fx);
         if (out16) reinterpret_cast<ushort4 *>(out16)[p] = px;
         if (out32) reinterpret_cast<float4 *>(out32)[p] = fx;
     }
@@ -630,6 +718,58 @@ void launch_colorize(const ColorParams &cp, const unsigned long long *fast, cons
     size_t g = (npix + block - 1) / block;
     const unsigned int grid = (unsigned int)(g > 148u * 32u ? 148u * 32u : g);
     colorize_kernel<<<grid, block, 0, s>>>(cp, fast, rec, scal, rgba_u16, rgba_f32);
+    ++g_launches;
+}
+
+// colorize() of this rank's stripe inside the cross-GPU frame protocol: wait for every rank's stripe
+// maximum (MAX_READY) and for the image owner to be done with the previous frame (IMAGE_FREE), fold
+// the stripe maxima — Runtime.max (the log base of lib.rs:860) and the Depth min/max (lib.rs:877-882)
+// are global —, colourise from the merged pixel-order counts straight into the owner's image (remote
+// stores over NVLink), and raise IMAGE_DONE at the owner.
+__global__ void __launch_bounds__(256)
+frame_colorize_kernel(const __grid_constant__ ColorParams C, const uint32_t *__restrict__ cnt,
+                      const ulonglong2 *__restrict__ rec, Scalars *scal, uint16_t *out16,
+                      const __grid_constant__ FrameSync S, int owner, long long timeout)
+{
+    __shared__ double s_lnmax;
+    __shared__ float s_zmax, s_zmin;
+    __shared__ uint32_t s_max;
+    if (!frame_wait(scal, SYNC_MAX_READY, 0, S.n_ranks, S.epoch, timeout)) return;
+    if (!frame_wait(scal, SYNC_IMAGE_FREE, owner, 1, S.epoch - 1u, timeout)) return;
+    if (threadIdx.x == 0) {
+        uint32_t m = 0, zmx = ZKEY_ZERO, zmn = ZKEY_FLT_MAX;
+        for (int r = 0; r < S.n_ranks; ++r) {
+            const uint32_t a = *((volatile unsigned int *)&scal->stripe_max[r]);
+            const uint32_t b = *((volatile unsigned int *)&scal->stripe_zmax[r]);
+            const uint32_t c = *((volatile unsigned int *)&scal->stripe_zmin[r]);
+            m = a > m ? a : m; zmx = b > zmx ? b : zmx; zmn = c < zmn ? c : zmn;
+        }
+        s_max = m;
+        s_lnmax = ln_max1(C, m);
+        s_zmax = __uint_as_float(zbits_from_key(zmx));
+        s_zmin = __uint_as_float(zbits_from_key(zmn));
+        if (blockIdx.x == 0) { scal->max = m; scal->zmax_key = zmx; scal->zmin_key = zmn; }   // Runtime.max of the whole frame
+    }
+    __syncthreads();
+    const size_t pix0 = (size_t)C.row0 * C.W, npix = (size_t)C.rows * C.W;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += stride) {
+        const size_t p = pix0 + i;
+        ushort4 px;
+        float4 fx;
+        color_pixel(C, rec[p], cnt[p], s_max, s_lnmax, s_zmax, s_zmin, px, fx);
+        reinterpret_cast<ushort4 *>(out16)[p] = px;
+    }
+    if (frame_last_block(&scal->done_counter[2])) frame_signal(S, SYNC_IMAGE_DONE, false, owner);
+}
+void launch_frame_colorize(const ColorParams &cp, const uint32_t *cnt, const ulonglong2 *rec, Scalars *scal, uint16_t *rgba_u16,
+                           const FrameSync &S, int owner, cudaStream_t s)
+{
+    const size_t npix = (size_t)cp.rows * cp.W;
+    const unsigned int block = 256;
+    size_t g = (npix + block - 1) / block;
+    const unsigned int grid = (unsigned int)(g > 148u * 16u ? 148u * 16u : (g ? g : 1));
+    frame_colorize_kernel<<<grid, block, 0, s>>>(cp, cnt, rec, scal, rgba_u16, S, owner, g_sync_timeout_cycles.load());
     ++g_launches;
 }
 
@@ -754,83 +894,161 @@ void launch_merge_peers(unsigned long long *dfast, ulonglong2 *drec, Scalars *ds
 }
 
 // ---------------------------------------------------------------------------------------------
-// Cross-GPU synchronisation without the host: every rank keeps, inside its exported allocation,
-// one flag per (kind, source rank).  A source rank announces an event by storing the frame epoch
-// into that flag on every target (a remote store over NVLink, release at system scope); a target
-// polls its OWN memory.  Kernel boundaries order the announced work before the flag store.
+// Cross-GPU frame protocol: kernels (helpers: frame_wait / frame_last_block / frame_signal above)
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void st_release_sys(unsigned int *p, unsigned int v)
-{
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int *p)
-{
-    unsigned int v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-
-__global__ void signal_kernel(const __grid_constant__ ScalList T, int kind, int my_rank, unsigned int epoch)
+// standalone forms (image hand-over on the owner rank; tests)
+__global__ void signal_kernel(const __grid_constant__ FrameSync S, int kind)
 {
     __threadfence_system();
-    if ((int)threadIdx.x < T.n) st_release_sys(&T.scal[threadIdx.x]->flag[kind][my_rank], epoch);
+    frame_signal(S, kind, true, -1);
 }
-void launch_signal(const ScalList &targets, int kind, int my_rank, unsigned int epoch, cudaStream_t s)
+void launch_signal(const FrameSync &S, int kind, cudaStream_t s)
 {
-    signal_kernel<<<1, 32, 0, s>>>(targets, kind, my_rank, epoch);
+    signal_kernel<<<1, 32, 0, s>>>(S, kind);
     ++g_launches;
 }
-
-__global__ void wait_kernel(Scalars *mine, int kind, int n_ranks, unsigned int epoch)
+__global__ void wait_kernel(Scalars *mine, int kind, int n_ranks, unsigned int epoch, long long timeout)
 {
-    if ((int)threadIdx.x < n_ranks) {
-        const unsigned int *f = &mine->flag[kind][threadIdx.x];
-        const long long t0 = clock64();
-        while ((int)(ld_acquire_sys(f) - epoch) < 0) {           // epochs only grow; wrap-safe compare
-            __nanosleep(100);
-            if (clock64() - t0 > 20000000000ll) {                // ~10 s: a peer is gone; do not hang the GPU
-                mine->sync_error = 1u + (unsigned int)kind;
-                break;
-            }
-        }
-    }
-    __syncthreads();
-    __threadfence_system();
+    (void)frame_wait(mine, kind, 0, n_ranks, epoch, timeout);
 }
 void launch_wait(Scalars *mine, int kind, int n_ranks, unsigned int epoch, cudaStream_t s)
 {
-    wait_kernel<<<1, 32, 0, s>>>(mine, kind, n_ranks, epoch);
+    wait_kernel<<<1, 32, 0, s>>>(mine, kind, n_ranks, epoch, g_sync_timeout_cycles.load());
     ++g_launches;
 }
 
-// rank r's stripe maximum (already in mine->max) to every rank, then the MAX_READY flag
-__global__ void publish_max_kernel(Scalars *mine, const __grid_constant__ ScalList T, int my_rank, unsigned int epoch)
+// Runtime::reset for a frame of the protocol: first wait until every peer has finished reading this
+// rank's accumulators of the previous frame (MERGE_DONE, epoch - 1).
+__global__ void frame_reset_kernel(unsigned long long *fast, ulonglong2 *rec, Scalars *scal, size_t npix, size_t nslots,
+                                   int n_ranks, unsigned int epoch, long long timeout)
 {
-    if ((int)threadIdx.x < T.n) {
-        const unsigned int m = mine->max;
-        *((volatile unsigned int *)&T.scal[threadIdx.x]->stripe_max[my_rank]) = m;
-        __threadfence_system();
-        st_release_sys(&T.scal[threadIdx.x]->flag[SYNC_MAX_READY][my_rank], epoch);
+    if (!frame_wait(scal, SYNC_MERGE_DONE, 0, n_ranks, epoch - 1u, timeout)) return;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nslots; i += stride) {
+        fast[i] = FAST_RESET;
+        if (i < npix) rec[i] = make_ulonglong2(0ull, REC_HI_RESET);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        scal->nan_sink = 0ull; scal->max = 0u;
+        scal->zmax_key = ZKEY_ZERO; scal->zmin_key = ZKEY_FLT_MAX; scal->pad = 0u;
     }
 }
-void launch_publish_max(Scalars *mine, const ScalList &targets, int my_rank, unsigned int epoch, cudaStream_t s)
+void launch_frame_reset(unsigned long long *fast, ulonglong2 *rec, Scalars *scal, size_t npix, size_t nslots,
+                        int n_ranks, unsigned int epoch, cudaStream_t s)
 {
-    publish_max_kernel<<<1, 32, 0, s>>>(mine, targets, my_rank, epoch);
+    const unsigned int block = 256;
+    size_t g = (nslots + block - 1) / block;
+    const unsigned int grid = (unsigned int)(g > 148u * 16u ? 148u * 16u : (g ? g : 1));
+    frame_reset_kernel<<<grid, block, 0, s>>>(fast, rec, scal, npix, nslots, n_ranks, epoch, g_sync_timeout_cycles.load());
     ++g_launches;
 }
-// Runtime.max = max over the stripes (the log base of lib.rs:860 is global)
-__global__ void gather_max_kernel(Scalars *mine, int n_ranks)
+
+// After the trajectories: the counts in PIXEL order (cnt[p], u32, NaN debt folded into pixel 0) so that
+// the stripe owners read them from this rank with coalesced 16-byte loads instead of one scattered
+// 8-byte `fast` word (= one 32-byte sector over NVLink) per pixel; then RENDER_DONE to every rank.
+__global__ void frame_export_kernel(const unsigned long long *fast, Scalars *scal, uint32_t *cnt, size_t npix, SlotMap slots,
+                                    const __grid_constant__ FrameSync S)
 {
-    unsigned int m = (int)threadIdx.x < n_ranks ? *((volatile unsigned int *)&mine->stripe_max[threadIdx.x]) : 0u;
-    for (int o = 16; o > 0; o >>= 1) {
-        const unsigned int m2 = __shfl_xor_sync(0xffffffffu, m, o);
-        m = m2 > m ? m2 : m;
-    }
-    if (threadIdx.x == 0) mine->max = m;
+    if (*((volatile unsigned int *)&scal->sync_error) != 0u) return;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += stride)
+        cnt[i] = pixel_count(fast, scal, i, slots);
+    if (frame_last_block(&scal->done_counter[0])) frame_signal(S, SYNC_RENDER_DONE, true, -1);
 }
-void launch_gather_max(Scalars *mine, int n_ranks, cudaStream_t s)
+void launch_frame_export(const unsigned long long *fast, Scalars *scal, uint32_t *cnt, size_t npix, SlotMap slots,
+                         const FrameSync &S, cudaStream_t s)
 {
-    gather_max_kernel<<<1, 32, 0, s>>>(mine, n_ranks);
+    const unsigned int block = 256;
+    size_t g = (npix + block - 1) / block;
+    frame_export_kernel<<<(unsigned int)(g > 148u * 16u ? 148u * 16u : (g ? g : 1)), block, 0, s>>>(fast, scal, cnt, npix, slots, S);
+    ++g_launches;
+}
+
+// All-ranks merge of one pixel stripe, reading every peer's counts and records directly over NVLink
+// (CUDA IPC mappings).  Deterministic form of Runtime::merge (lib.rs:708-738): counts add, the record
+// with the greatest (z, earlier job) wins — identical to rendering every job on one Runtime, whatever
+// the number of ranks.  A peer's 16-byte record is only fetched where that peer counted a hit
+// (~19 % of the pixels).  The stripe's share of Runtime.max (lib.rs:721-723) and of the Depth fold
+// (lib.rs:877-882) is reduced on the way; the last block publishes it to every rank and raises
+// MAX_READY and MERGE_DONE.
+__global__ void __launch_bounds__(256)
+frame_merge_kernel(unsigned long long *dfast, ulonglong2 *drec, uint32_t *dcnt, Scalars *dscal,
+                   const __grid_constant__ PeerList peers, size_t pix0, size_t npix, SlotMap slots,
+                   const __grid_constant__ FrameSync S, long long timeout)
+{
+    if (!frame_wait(dscal, SYNC_RENDER_DONE, 0, S.n_ranks, S.epoch, timeout)) return;
+    uint32_t m = 0, zmx = ZKEY_ZERO, zmn = ZKEY_FLT_MAX;
+    // groups of 4 pixels, aligned to 16 bytes of cnt[]; the stripe's ends may cut a group
+    const size_t g0 = pix0 / 4, g1 = (pix0 + npix + 3) / 4;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t g = g0 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < g1; g += stride) {
+        const uint4 own = reinterpret_cast<const uint4 *>(dcnt)[g];
+        uint32_t c[4] = {own.x, own.y, own.z, own.w};
+        bool in[4], changed[4];
+        ulonglong2 d[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const size_t p = 4 * g + j;
+            in[j] = p >= pix0 && p < pix0 + npix;
+            changed[j] = false;
+            d[j] = in[j] ? drec[p] : make_ulonglong2(0ull, REC_HI_RESET);
+        }
+        for (int r = 0; r < peers.n; ++r) {
+            const uint4 v4 = __ldcv(reinterpret_cast<const uint4 *>(peers.cnt[r]) + g);
+            const uint32_t v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (!in[j] || v[j] == 0u) continue;                      // this peer never hit the pixel: its record is the reset value
+                c[j] += v[j];                                            // lib.rs:719 (wrapping)
+                const ulonglong2 *pr = &peers.rec[r][4 * g + j];
+                const unsigned long long oy = __ldcv(&pr->y);
+                if (rec_order(oy) > rec_order(d[j].y)) { d[j].y = oy; d[j].x = __ldcv(&pr->x); changed[j] = true; }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (!in[j]) { c[j] = j == 0 ? own.x : j == 1 ? own.y : j == 2 ? own.z : own.w; continue; }
+            const size_t p = 4 * g + j;
+            const uint32_t k = canon_key((uint32_t)(d[j].y >> 32));
+            if (changed[j]) drec[p] = d[j];
+            dfast[slot_of((uint32_t)p, slots)] = ((unsigned long long)(k == ZKEY_SENTINEL ? ZKEY_SENTINEL + 1u : k) << 32) | c[j];
+            m = c[j] > m ? c[j] : m;
+            if (k != ZKEY_SENTINEL) { zmx = k > zmx ? k : zmx; zmn = k < zmn ? k : zmn; }
+        }
+        // merged counts back in pixel order for the colourise pass (pixels outside the stripe keep their value)
+        reinterpret_cast<uint4 *>(dcnt)[g] = make_uint4(c[0], c[1], c[2], c[3]);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const uint32_t m2 = __shfl_xor_sync(0xffffffffu, m, o);
+        const uint32_t a2 = __shfl_xor_sync(0xffffffffu, zmx, o);
+        const uint32_t b2 = __shfl_xor_sync(0xffffffffu, zmn, o);
+        m = m2 > m ? m2 : m; zmx = a2 > zmx ? a2 : zmx; zmn = b2 < zmn ? b2 : zmn;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (m) atomicMax(&dscal->max, m);
+        atomicMax(&dscal->zmax_key, zmx);
+        atomicMin(&dscal->zmin_key, zmn);
+    }
+    if (frame_last_block(&dscal->done_counter[1])) {
+        if ((int)threadIdx.x < S.n_ranks) {
+            Scalars *t = S.scal[threadIdx.x];
+            *((volatile unsigned int *)&t->stripe_max[S.my_rank]) = *((volatile unsigned int *)&dscal->max);
+            *((volatile unsigned int *)&t->stripe_zmax[S.my_rank]) = *((volatile unsigned int *)&dscal->zmax_key);
+            *((volatile unsigned int *)&t->stripe_zmin[S.my_rank]) = *((volatile unsigned int *)&dscal->zmin_key);
+            __threadfence_system();
+        }
+        if (pix0 == 0 && threadIdx.x == 0) dscal->nan_sink = 0ull;      // the debts of all ranks are inside the merged count of pixel 0 now
+        frame_signal(S, SYNC_MAX_READY, true, -1);
+        frame_signal(S, SYNC_MERGE_DONE, true, -1);
+    }
+}
+void launch_frame_merge(unsigned long long *dfast, ulonglong2 *drec, uint32_t *dcnt, Scalars *dscal, const PeerList &peers,
+                        size_t pix0, size_t npix, SlotMap slots, const FrameSync &S, cudaStream_t s)
+{
+    const unsigned int block = 256;
+    size_t g = (npix / 4 + block) / block;
+    frame_merge_kernel<<<(unsigned int)(g > 148u * 8u ? 148u * 8u : (g ? g : 1)), block, 0, s>>>(
+        dfast, drec, dcnt, dscal, peers, pix0, npix, slots, S, g_sync_timeout_cycles.load());
     ++g_launches;
 }
 

@@ -3,26 +3,28 @@
 The reference's only parallelism is render_parallel (lib.rs:1051-1082): N workers each own a
 private Runtime, take jobs off a counter, and the caller merges the N Runtimes and colourises.
 Here a worker is a GPU (a rank), its private Runtime lives in its HBM, and the merge is done
-stripe-wise by the GPUs themselves:
+stripe-wise by the GPUs themselves (include/sar.h, "One frame of render_parallel over N ranks"):
 
-    rank r renders jobs [r*J, (r+1)*J)                      (no communication)
-    flag RENDER_DONE to every rank, wait for everyone's
-    rank r reduces ROW STRIPE r over all ranks by loading the peers' accumulators directly
-        over NVLink (CUDA IPC mappings; csrc merge_peers_kernel): counts add, the Δp record
-        with the greatest (z, earlier job) wins — Runtime::merge (lib.rs:708-738) made
-        order-independent, so the frame is bit-identical for 1, 2, 4, 8 ranks
-    flag MERGE_DONE (peers may reset once everyone has read them)
-    max over the stripe, published into every rank's memory; each rank takes the max of all
-        (Runtime.max is the global log base, lib.rs:860)
-    rank r colourises stripe r and stores it straight into rank 0's image over NVLink
-    flag IMAGE_DONE to rank 0; rank 0 flags IMAGE_FREE when it is done with the frame's image
+    reset      (first waits until every peer has finished reading this rank's previous frame)
+    render     rank r renders jobs [r*J, (r+1)*J), order keys global       (no communication)
+    export     counts in pixel order for the peers; RENDER_DONE to every rank
+    merge      waits for everyone's RENDER_DONE; rank r reduces ROW STRIPE r over all ranks by
+               loading the peers' counts and Δp records directly over NVLink (CUDA IPC mappings):
+               counts add, the record with the greatest (z, earlier job) wins — Runtime::merge
+               (lib.rs:708-738) made order-independent, so the frame is bit-identical for 1, 2, 4,
+               8 ranks; the stripe's share of Runtime.max and of the Depth min/max goes to every
+               rank; MAX_READY + MERGE_DONE
+    colourise  waits for every stripe's maximum (the log base of lib.rs:860 and the Depth range of
+               lib.rs:877-882 are global) and for the owner's IMAGE_FREE; rank r colourises stripe
+               r straight into rank 0's image over NVLink; IMAGE_DONE to rank 0
+    rank 0     waits for IMAGE_DONE from all, uses the image, raises IMAGE_FREE
 
-All of that synchronisation is device-side: flags in the ranks' exported allocations, written by
-remote stores and polled locally by one-block kernels (sar_runtime_signal_async / _wait_async /
-_exchange_max_async) — the host only enqueues.  torch.distributed is plumbing for set-up: the
-rendezvous and the all-gather of the 64-byte IPC handles (plus max-over-ranks of timings in
-bench.py).  SAR_HOST_SYNC=1 selects the older host-driven variant (barriers + NCCL all-reduce).  Pure functions at the top (job_slice, stripe_rows,
-iterations_per_job) are the host logic; they are covered by CPU tests (gloo, world_size 2).
+All of that synchronisation is device-side — flags in the ranks' exported allocations, written by
+remote stores and polled locally, as prologues / epilogues of those five kernels — the host only
+enqueues.  torch.distributed is plumbing for set-up: the rendezvous and the all-gather of the
+64-byte IPC handles (plus max-over-ranks of timings in bench.py).  Pure functions at the top
+(job_slice, stripe_rows, iterations_per_job) are the host logic; they are covered by CPU tests
+(gloo, world_size 2).
 """
 from __future__ import annotations
 
@@ -163,11 +165,10 @@ class Frame:
                 hbuf = (C.c_uint8 * N.SAR_IPC_HANDLE_BYTES).from_buffer_copy(hb)
                 N.check(self.L.sar_peer_open(hbuf, self.w, self.h, device, C.byref(p)))
                 self.peers[r] = p
-            others = [p for p in self.peers if p is not None]
-            self.peer_arr = (C.c_void_p * len(others))(*[p.value for p in others])
-            self.owner_arr = (C.c_void_p * 1)(self.peers[0].value) if rank != 0 else None
+            self.peer_arr = (C.c_void_p * world)(*[(p.value if p is not None else None) for p in self.peers])
             barrier(group)                       # every rank has mapped every peer before the first remote store
-        self.device_sync = os.environ.get("SAR_HOST_SYNC", "0") != "1"
+        else:
+            self.peer_arr = None
         self.epoch = 0
         self._renderer = None
 
@@ -180,7 +181,10 @@ class Frame:
 
     # -- pieces
     def reset_async(self, sp) -> None:
-        self.N.check(self.L.sar_runtime_reset_async(self.rt, sp))
+        if self.world == 1:
+            self.N.check(self.L.sar_runtime_reset_async(self.rt, sp))
+        else:   # first waits (on the device) until every peer has read this rank's previous frame
+            self.N.check(self.L.sar_frame_reset_async(self.rt, self.world, self.epoch, sp))
 
     def render_async(self, sp, d_init=None) -> None:
         # order keys are global over the ranks: rank r's jobs follow rank r-1's (include/sar.h)
@@ -199,49 +203,20 @@ class Frame:
             N.check(L.sar_runtime_max_async(self.rt, 0, 0, sp))
             N.check(L.sar_colorize_rows_async(C.byref(self.pod), self.rt, 0, 0, None, sp))
             return
-        if not self.device_sync:
-            return self._finish_host_sync(sp)
-        e, n, r, others = self.epoch, self.world, self.rank, self.world - 1
-        N.check(L.sar_runtime_signal_async(self.rt, self.peer_arr, others, 1, N.SYNC_RENDER_DONE, r, e, sp))
-        N.check(L.sar_runtime_wait_async(self.rt, N.SYNC_RENDER_DONE, n, e, sp))          # every rank's trajectories are in its HBM
-        N.check(L.sar_runtime_merge_peers_async(self.rt, self.peer_arr, others, self.row0, self.rows, sp))
-        N.check(L.sar_runtime_signal_async(self.rt, self.peer_arr, others, 1, N.SYNC_MERGE_DONE, r, e, sp))
-        N.check(L.sar_runtime_max_async(self.rt, self.row0, self.rows, sp))
-        N.check(L.sar_runtime_exchange_max_async(self.rt, self.peer_arr, others, r, e, sp))
-        N.check(L.sar_runtime_wait_async(self.rt, N.SYNC_IMAGE_FREE, 1, e - 1, sp))       # owner is done with the previous image
-        N.check(L.sar_colorize_rows_async(C.byref(self.pod), self.rt, self.row0, self.rows, self.peers[0], sp))
+        e, n, r = self.epoch, self.world, self.rank
+        N.check(L.sar_frame_export_async(self.rt, self.peer_arr, n, r, e, sp))
+        N.check(L.sar_frame_merge_async(self.rt, self.peer_arr, n, r, self.row0, self.rows, e, sp))
+        N.check(L.sar_frame_colorize_async(C.byref(self.pod), self.rt, self.peer_arr, n, r, 0, self.row0, self.rows, e, sp))
         if r == 0:
-            N.check(L.sar_runtime_signal_async(self.rt, None, 0, 1, N.SYNC_IMAGE_DONE, r, e, sp))
-            N.check(L.sar_runtime_wait_async(self.rt, N.SYNC_IMAGE_DONE, n, e, sp))       # rank 0's image is complete
-        else:
-            N.check(L.sar_runtime_signal_async(self.rt, self.owner_arr, 1, 0, N.SYNC_IMAGE_DONE, r, e, sp))
+            N.check(L.sar_frame_image_wait_async(self.rt, n, e, sp))                     # rank 0's image is complete
 
     def release_image(self, sp) -> None:
         """Rank 0 is done with the frame's image (copied out, or not needed): peers may overwrite it."""
-        if self.world > 1 and self.device_sync and self.rank == 0:
-            self.N.check(self.L.sar_runtime_signal_async(self.rt, self.peer_arr, self.world - 1, 1,
-                                                         self.N.SYNC_IMAGE_FREE, 0, self.epoch, sp))
-
-    def _finish_host_sync(self, sp) -> None:
-        N, L = self.N, self.L
-        N.check(L.sar_stream_synchronize(self.rt, sp))
-        barrier(self.group)                       # every rank's trajectories are in its HBM
-        N.check(L.sar_runtime_merge_peers_async(self.rt, self.peer_arr, self.world - 1, self.row0, self.rows, sp))
-        N.check(L.sar_runtime_max_async(self.rt, self.row0, self.rows, sp))
-        mx = C.c_uint32()
-        N.check(L.sar_runtime_get_max(self.rt, C.byref(mx), sp))
-        gmax = allreduce_max_u32(int(mx.value), self.group, self.device)
-        N.check(L.sar_runtime_set_max(self.rt, gmax, sp))
-        N.check(L.sar_colorize_rows_async(C.byref(self.pod), self.rt, self.row0, self.rows, self.peers[0], sp))
-        N.check(L.sar_stream_synchronize(self.rt, sp))
-        barrier(self.group)                       # rank 0's image is complete; peers may reset
+        if self.world > 1 and self.rank == 0:
+            self.N.check(self.L.sar_frame_image_release_async(self.rt, self.peer_arr, self.world, 0, self.epoch, sp))
 
     def begin_frame(self, sp) -> None:
-        """New frame epoch; with device-side sync, wait until every peer has finished reading this
-        rank's accumulators of the previous frame before they are reset."""
         self.epoch += 1
-        if self.world > 1 and self.device_sync:
-            self.N.check(self.L.sar_runtime_wait_async(self.rt, self.N.SYNC_MERGE_DONE, self.world, self.epoch - 1, sp))
 
     def step_device(self, sp) -> None:
         self.begin_frame(sp)
@@ -251,8 +226,11 @@ class Frame:
         self.release_image(sp)
 
     def check_sync(self) -> None:
+        """Raise if a cross-GPU wait of an earlier frame timed out (its results are then void)."""
+        if self.world == 1:
+            return
         err = C.c_uint32()
-        self.N.check(self.L.sar_runtime_sync_error(self.rt, C.byref(err)))
+        self.N.check(self.L.sar_runtime_sync_error(self.rt, C.byref(err), 0))
         if err.value:
             raise RuntimeError(f"cross-GPU wait timed out (kind {err.value - 1}) on rank {self.rank}")
 
@@ -315,3 +293,5 @@ class _E2E:
         if f.rank == 0:
             N.check(L.sar_runtime_image_download(f.rt, 0, 0, C.c_void_p(self.h_img.data_ptr()), sp))
         f.release_image(sp)
+        if f.rank == 0:
+            f.check_sync()      # the image was just consumed: a timed-out wait must not pass silently

@@ -1,4 +1,5 @@
-"""N-rank frame == 1-GPU frame, bit for bit (needs >= 2 GPUs; skipped otherwise)."""
+"""N-rank frame == oracle, bit for bit (needs >= 2 GPUs; skipped otherwise — bench.py --gpus N runs the
+same check inside the driver's scaling run and reports it as "parity")."""
 import os
 import subprocess
 import sys
@@ -18,13 +19,13 @@ def _gpu_count():
         return 0
 
 
-@pytest.mark.parametrize("preset,world", [("solar", 2), ("poisson", 2), ("solar", 4), ("poisson", 8)])
-def test_n_rank_frame_equals_single_gpu(preset, world):
-    """Verified on an 8xB200 box at world = 2, 4 and 8 (profiles/r1_scaling.md)."""
+@pytest.mark.parametrize("preset,kind,world", [("solar", "gas", 2), ("poisson", "depth", 2), ("solar", "depth", 4), ("poisson", "gas", 8)])
+def test_n_rank_frame_equals_oracle(preset, kind, world):
+    """N-rank frame (incl. RenderKind::Depth, whose min/max is global) vs the oracle, bit for bit."""
     if _gpu_count() < world:
         pytest.skip(f"needs {world} GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
-           "--master-addr", "127.0.0.1", "--master-port", str(29533 + world), os.path.join(ROOT, "tools", "dist_check.py"), preset]
+           "--master-addr", "127.0.0.1", "--master-port", str(29533 + world), os.path.join(ROOT, "tools", "dist_check.py"), preset, kind]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0 and "DIST_CHECK_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
 
