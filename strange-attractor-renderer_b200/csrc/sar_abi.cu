@@ -83,9 +83,11 @@ struct sar_peer {
 };
 
 struct seq_device {                  // per-device pipeline state of sar_render_sequence
-    uint16_t *img[2] = {nullptr, nullptr};          // device images, double buffered
+    sar_runtime *rt[2] = {nullptr, nullptr};        // two Runtimes, frames alternate: frame f renders while frame f-1 is
+                                                    // colourised with ITS max read back by the host and copied out
     uint16_t *stage[2] = {nullptr, nullptr};        // pinned host staging (when the caller gives no frame array)
-    cudaEvent_t rendered[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr};
+    uint32_t *h_max = nullptr;                      // pinned: Runtime.max of the frame in each slot
+    cudaEvent_t max_ready[2] = {nullptr, nullptr}, rendered[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr};
     cudaStream_t copy_stream = nullptr;
     double *warm = nullptr; size_t warm_cap = 0;    // warmed states shared by all frames (SAR_SEQ_SHARED_POINTS)
     size_t img_bytes = 0;
@@ -901,11 +903,13 @@ static void seq_release(sar_renderer *r, size_t d)
     cudaSetDevice(r->devices[d]);
     if (q.copy_stream) { cudaStreamSynchronize(q.copy_stream); cudaStreamDestroy(q.copy_stream); }
     for (int k = 0; k < 2; ++k) {
-        cudaFree(q.img[k]);
+        sar_runtime_free(q.rt[k]);
         if (q.stage[k]) cudaFreeHost(q.stage[k]);
+        if (q.max_ready[k]) cudaEventDestroy(q.max_ready[k]);
         if (q.rendered[k]) cudaEventDestroy(q.rendered[k]);
         if (q.copied[k]) cudaEventDestroy(q.copied[k]);
     }
+    if (q.h_max) cudaFreeHost(q.h_max);
     cudaFree(q.warm);
     q = seq_device();
 }
@@ -1050,14 +1054,16 @@ static int seq_prepare(sar_renderer *r, size_t d, const sar_config &cfg, bool ne
     seq_device &q = r->seq[d];
     const size_t bytes = (size_t)cfg.width * cfg.height * 4 * sizeof(uint16_t);
     SAR_CUDA(cudaSetDevice(r->devices[d]));
-    if (q.img_bytes != bytes) {
+    if (q.img_bytes != bytes || (q.rt[0] && (q.rt[0]->w != cfg.width || q.rt[0]->h != cfg.height))) {
         seq_release(r, d);
         q.img_bytes = bytes;
     }
     if (!q.copy_stream) SAR_CUDA(cudaStreamCreateWithFlags(&q.copy_stream, cudaStreamNonBlocking));
+    if (!q.h_max) SAR_CUDA(cudaHostAlloc((void **)&q.h_max, 2 * sizeof(uint32_t), cudaHostAllocPortable));
     for (int k = 0; k < 2; ++k) {
-        if (!q.img[k]) SAR_CUDA(cudaMalloc((void **)&q.img[k], bytes));
+        if (!q.rt[k]) if (int rc = sar_runtime_new(cfg.width, cfg.height, r->devices[d], &q.rt[k])) return rc;
         if (need_stage && !q.stage[k]) SAR_CUDA(cudaHostAlloc((void **)&q.stage[k], bytes, cudaHostAllocPortable));
+        if (!q.max_ready[k]) SAR_CUDA(cudaEventCreateWithFlags(&q.max_ready[k], cudaEventDisableTiming));
         if (!q.rendered[k]) SAR_CUDA(cudaEventCreateWithFlags(&q.rendered[k], cudaEventDisableTiming));
         if (!q.copied[k]) SAR_CUDA(cudaEventCreateWithFlags(&q.copied[k], cudaEventDisableTiming));
     }
@@ -1089,21 +1095,44 @@ int sar_render_sequence(sar_renderer *r, const sar_config *cfg_in, const double 
         jobs[d] = (uint64_t)threads[d] * jobs_per_thread;
         lanes[d] = r->threads_per_device ? threads[d] : (uint32_t)(jobs[d] < renderer_lanes(r, d) ? jobs[d] : renderer_lanes(r, d));
         cfgs[d].iterations = cfg_in->iterations / threads[d] / jobs_per_thread;
-        if (r->rts[d] && (r->rts[d]->w != cfg_in->width || r->rts[d]->h != cfg_in->height)) { sar_runtime_free(r->rts[d]); r->rts[d] = nullptr; }
-        if (!r->rts[d]) if (int rc = sar_runtime_new(cfg_in->width, cfg_in->height, r->devices[d], &r->rts[d])) return rc;
         if (int rc = seq_prepare(r, d, *cfg_in, rgba_frames == nullptr)) return rc;
         if (shared) {   // warm the one shared list of start points once (lib.rs:748-752)
             seq_device &q = r->seq[d];
             const size_t need = (size_t)jobs[d] * 3 * sizeof(double);
             if (q.warm_cap < need) { cudaFree(q.warm); q.warm = nullptr; q.warm_cap = 0; SAR_CUDA(cudaMalloc((void **)&q.warm, need)); q.warm_cap = need; }
             IterParams p;
-            make_iter_params(&cfgs[d], r->rts[d], p);
+            make_iter_params(&cfgs[d], q.rt[0], p);
             p.init = nullptr; p.seed = seed; p.first_job = 0; p.n_jobs = jobs[d];
-            launch_warm(p, q.warm, r->rts[d]->stream);
+            launch_warm(p, q.warm, q.rt[0]->stream);
             SAR_CUDA(cudaGetLastError());
+            SAR_CUDA(cudaStreamSynchronize(q.rt[0]->stream));       // both Runtimes' streams read it
         }
     }
 
+    // Frame g's second half: its Runtime.max has been copied to the host — ln(max + 1), the log base of
+    // lib.rs:860, is computed by the host libm like every blocking entry point does, so the frame is
+    // bit-exact whatever max is (a solar-sail frame's NaN sink is far beyond the ln table) —, then
+    // colourise and start the copy out.  The other Runtime of the device is rendering meanwhile.
+    auto colourise = [&](uint32_t g) -> int {
+        const size_t d = g % nd;
+        const int slot = (int)((g / nd) % 2);
+        seq_device &q = r->seq[d];
+        sar_runtime *rt = q.rt[slot];
+        SAR_CUDA(cudaSetDevice(rt->device));
+        SAR_CUDA(cudaEventSynchronize(q.max_ready[slot]));
+        sar_config cfg = cfgs[d];
+        cfg.angle = angles_rad[g];
+        ColorParams cp;
+        make_color_params(&cfg, rt, cp, 0, rt->h, &q.h_max[slot]);
+        launch_colorize(cp, rt->fast, rt->rec, rt->scal, rt->image, nullptr, rt->stream);   // colorize, lib.rs:1080
+        SAR_CUDA(cudaGetLastError());
+        SAR_CUDA(cudaEventRecord(q.rendered[slot], rt->stream));
+        SAR_CUDA(cudaStreamWaitEvent(q.copy_stream, q.rendered[slot], 0));
+        uint16_t *dst = rgba_frames ? rgba_frames + (size_t)g * frame_u16 : q.stage[slot];
+        SAR_CUDA(cudaMemcpyAsync(dst, rt->image, q.img_bytes, cudaMemcpyDeviceToHost, q.copy_stream));
+        SAR_CUDA(cudaEventRecord(q.copied[slot], q.copy_stream));
+        return SAR_OK;
+    };
     auto finalize = [&](uint32_t g) -> int {     // wait for frame g's host copy, hand it to the caller
         const size_t d = g % nd;
         const int slot = (int)((g / nd) % 2);
@@ -1116,12 +1145,14 @@ int sar_render_sequence(sar_renderer *r, const sar_config *cfg_in, const double 
     for (uint32_t f = 0; f < n_frames; ++f) {
         const size_t d = f % nd;
         const int slot = (int)((f / nd) % 2);
-        sar_runtime *rt = r->rts[d];
         seq_device &q = r->seq[d];
+        sar_runtime *rt = q.rt[slot];
         SAR_CUDA(cudaSetDevice(rt->device));
         sar_config cfg = cfgs[d];
         cfg.angle = angles_rad[f];                                             // main.rs:497
-        if (f >= 2 * nd) SAR_CUDA(cudaStreamWaitEvent(rt->stream, q.copied[slot], 0));   // image slot free again
+        if (f >= 2 * nd) {                                                     // the slot's previous frame must have left the device
+            if (int rc = finalize(f - 2 * (uint32_t)nd)) return rc;            // in order: frames f-2nd .. are handed over here
+        }
         if (int rc = sar_runtime_reset_async(rt, nullptr)) return rc;           // Runtime::reset per frame, lib.rs:951
         if (shared) {
             if (int rc = render_launch(&cfg, rt, q.warm, 0, 0, jobs[d], lanes[d], rt->stream, true)) return rc;
@@ -1130,22 +1161,17 @@ int sar_render_sequence(sar_renderer *r, const sar_config *cfg_in, const double 
             if (int rc = render_launch(&cfg, rt, nullptr, seed, (uint64_t)f * jobs[d], jobs[d], lanes[d], rt->stream)) return rc;
         }
         if (int rc = sar_runtime_max_async(rt, 0, 0, nullptr)) return rc;
-        ColorParams cp;
-        make_color_params(&cfg, rt, cp, 0, rt->h);
-        launch_colorize(cp, rt->fast, rt->rec, rt->scal, q.img[slot], nullptr, rt->stream);   // colorize, lib.rs:1080
-        SAR_CUDA(cudaGetLastError());
-        SAR_CUDA(cudaEventRecord(q.rendered[slot], rt->stream));
-        SAR_CUDA(cudaStreamWaitEvent(q.copy_stream, q.rendered[slot], 0));
-        uint16_t *dst = rgba_frames ? rgba_frames + (size_t)f * frame_u16 : q.stage[slot];
-        SAR_CUDA(cudaMemcpyAsync(dst, q.img[slot], q.img_bytes, cudaMemcpyDeviceToHost, q.copy_stream));
-        SAR_CUDA(cudaEventRecord(q.copied[slot], q.copy_stream));
-        if (f >= nd) if (int rc = finalize(f - (uint32_t)nd)) return rc;        // in order, one round behind
+        SAR_CUDA(cudaMemcpyAsync(&q.h_max[slot], &rt->scal->max, sizeof(uint32_t), cudaMemcpyDeviceToHost, rt->stream));
+        SAR_CUDA(cudaEventRecord(q.max_ready[slot], rt->stream));
+        if (f >= nd) if (int rc = colourise(f - (uint32_t)nd)) return rc;       // the device's previous frame, one behind
     }
     for (uint32_t g = n_frames > nd ? n_frames - (uint32_t)nd : 0; g < n_frames; ++g)
+        if (int rc = colourise(g)) return rc;
+    for (uint32_t g = n_frames > 2 * nd ? n_frames - 2 * (uint32_t)nd : 0; g < n_frames; ++g)
         if (int rc = finalize(g)) return rc;
     for (size_t d = 0; d < nd; ++d) {
         SAR_CUDA(cudaSetDevice(r->devices[d]));
-        SAR_CUDA(cudaStreamSynchronize(r->rts[d]->stream));
+        for (int k = 0; k < 2; ++k) SAR_CUDA(cudaStreamSynchronize(r->seq[d].rt[k]->stream));
     }
     return SAR_OK;
 }

@@ -470,3 +470,26 @@ def test_every_kernel_variant_is_bit_exact(S, oracle, nt, pipe):
     finally:
         L.sar_set_option(b"traj_per_thread", 1)     # the defaults (sar_kernels.cu: SAR_DEFAULT_NT / SAR_DEFAULT_PIPE)
         L.sar_set_option(b"pipeline", 0)
+
+
+def test_sequence_frames_are_exact_beyond_the_ln_table(S, oracle):
+    """BASELINE configs[4] is a solar-sail sweep: the NaN sink pushes Runtime.max past the 2^20-entry
+    host-libm ln table on every frame.  The sequence driver reads each frame's max back (one frame
+    behind, on a second Runtime) so that ln(max + 1) — the log base of lib.rs:860 — comes from the
+    host libm: every frame equals the oracle's colorize bit for bit (d.max() == 0)."""
+    cfg = _small(S.Config.solar_sail(), 200, 220, 8_000_000)
+    cfg.transparent = True
+    angles = S.angle_iter(200.0, 245.0, 15.0)                    # 200, 215, 230 degrees
+    r = S.ParallelRenderer.new(threads=256)
+    frames = S.render_sequence(r, cfg, angles, 1, seed=77, shared_points=True)
+    ocfg = cfg.to_pod()
+    ocfg.iterations = 8_000_000 // 256
+    pts = oracle.seed_points(77, 0, 256)
+    for f, a in enumerate(angles):
+        ocfg.angle = a
+        ort = oracle.Runtime(200, 220)
+        oracle.render_jobs_mt(ocfg, ort, pts)
+        assert ort.max >= (1 << 20), "this test is about max beyond the ln table"
+        d = np.abs(frames[f].astype(np.int32) - oracle.colorize(ocfg, ort).astype(np.int32))
+        assert d.max() == 0, f"frame {f}: {(d > 0).sum()} values differ"
+    r.shutdown()
