@@ -220,6 +220,47 @@ typedef void (*sar_frame_callback)(void *user, uint32_t frame, const uint16_t *r
 int  sar_render_sequence(sar_renderer *r, const sar_config *cfg, const double *angles_rad,
                          uint32_t n_frames, uint64_t jobs_per_thread, uint64_t seed, uint32_t flags,
                          uint16_t *rgba_frames, sar_frame_callback cb, void *user);
+/* ---- output conversion + raw encoders (src/bin/main.rs:40-100) ----------
+ * write_image_matches converts the FinalImage by (transparent, 8bit)
+ * (main.rs:52-57): RGBA16 as is, to_rgb16(), to_rgba8(), to_rgb8(), and hands
+ * image.as_bytes() to an `image`-crate encoder (PAM main.rs:62-68, BMP
+ * main.rs:70-76, PNG main.rs:78-89).  Here the conversion runs on the device
+ * and the two RAW containers are written around it; PNG (deflate) is left to
+ * the caller, who gets the converted bytes (SAR_FILE_RAW).
+ * Third-party arithmetic: the u16 -> u8 narrowing of to_rgba8/to_rgb8 is
+ * image 0.25's `FromPrimitive<u16> for u8`, (c + 128) / 257 =
+ * round(c*255/65535); that crate is not vendored in the reference, so this is
+ * a restatement of its published source — parity unpinned (third-party).
+ * Bytes produced:
+ *   SAR_FILE_RAW  samples in native little-endian order, rows top-down
+ *   SAR_FILE_PAM  "P7\nWIDTH w\nHEIGHT h\nDEPTH d\nMAXVAL m\nTUPLTYPE RGB|RGB_ALPHA\nENDHDR\n"
+ *                 + samples, 16-bit ones most significant byte first
+ *   SAR_FILE_BMP  8-bit formats only (the reference's BmpEncoder panics on a
+ *                 16-bit image): BITMAPINFOHEADER 24 bpp / BITMAPV4HEADER 32 bpp
+ *                 BI_BITFIELDS, B,G,R[,A], rows bottom-up padded to 4 bytes */
+enum { SAR_PIX_RGBA16 = 0, SAR_PIX_RGB16 = 1, SAR_PIX_RGBA8 = 2, SAR_PIX_RGB8 = 3 };
+enum { SAR_FILE_RAW = 0, SAR_FILE_PAM = 1, SAR_FILE_BMP = 2 };
+/* bytes of one encoded image (header + pixels); 0 for an unsupported combination */
+size_t sar_encoded_size(uint32_t width, uint32_t height, uint32_t pixel_format, uint32_t container);
+/* the container header alone (host only, no GPU); out may be NULL to query header_bytes */
+int  sar_encode_header(uint32_t width, uint32_t height, uint32_t pixel_format, uint32_t container,
+                       uint8_t *out, size_t out_bytes, size_t *header_bytes);
+/* Convert the Runtime's device-resident image (the result of the last colorize
+ * on it) and copy header + pixels to `out` (sar_encoded_size bytes).  Blocking. */
+int  sar_runtime_encode(sar_runtime *rt, uint32_t pixel_format, uint32_t container,
+                        uint8_t *out, size_t out_bytes, void *stream);
+/* File::create(path) + write_all, main.rs:102-104 */
+int  sar_write_file(const char *path, const uint8_t *bytes, size_t n_bytes);
+/* sar_render_sequence with every frame converted on the device and handed over
+ * encoded: frames_out (n_frames x sar_encoded_size bytes, may be NULL) and/or
+ * cb(user, frame, bytes, n_bytes) in frame order — what the reference's encoder
+ * side threads (main.rs:508-511) would write to disk. */
+typedef void (*sar_frame_bytes_callback)(void *user, uint32_t frame, const uint8_t *bytes, size_t n_bytes);
+int  sar_render_sequence_encoded(sar_renderer *r, const sar_config *cfg, const double *angles_rad,
+                                 uint32_t n_frames, uint64_t jobs_per_thread, uint64_t seed, uint32_t flags,
+                                 uint32_t pixel_format, uint32_t container, uint8_t *frames_out,
+                                 sar_frame_bytes_callback cb, void *user);
+
 /* The merged Runtime of the last sar_render_parallel on the renderer's first
  * device (valid until the next call / shutdown); for inspection and tests. */
 int  sar_renderer_runtime(sar_renderer *r, sar_runtime **rt);

@@ -105,6 +105,8 @@ def lib() -> C.CDLL:
         L.orc_render_jobs_mt.restype = C.c_int
         L.orc_colorize.argtypes = [P(SarConfig), P(_OrcRuntime), P(C.c_uint16), dp]
         L.orc_render_parallel.argtypes = [P(SarConfig), C.c_uint32, C.c_uint64, dp, P(C.c_uint16), P(P(_OrcRuntime))]
+        L.orc_encode.argtypes = [P(C.c_uint16), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, P(C.c_uint8)]
+        L.orc_encode.restype = C.c_size_t
         L.orc_screen_bbox.argtypes = [P(SarConfig), dp, C.c_uint64, dp]
         L.orc_seed_points.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, dp]
         L.orc_config_poisson_saturne.argtypes = [P(SarConfig)]
@@ -275,3 +277,15 @@ def render_parallel(cfg, n_threads: int, jobs_per_thread: int, init_xyz, want_ru
     if rc != 0:
         raise RuntimeError("orc_render_parallel failed")
     return (out, Runtime(0, 0, _ptr=mp)) if want_runtime else out
+
+
+def encode(rgba_u16: np.ndarray, fmt: int, container: int):
+    """main.rs:52-98 on the host: converted + containerised bytes of an RGBA16 image (None if unsupported)."""
+    img = np.ascontiguousarray(rgba_u16, dtype=np.uint16)
+    h, w = img.shape[:2]
+    n = lib().orc_encode(img.ctypes.data_as(C.POINTER(C.c_uint16)), w, h, fmt, container, None)
+    if n == 0:
+        return None
+    out = np.empty(n, dtype=np.uint8)
+    lib().orc_encode(img.ctypes.data_as(C.POINTER(C.c_uint16)), w, h, fmt, container, out.ctypes.data_as(C.POINTER(C.c_uint8)))
+    return out

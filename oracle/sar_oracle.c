@@ -7,6 +7,7 @@
 #include <math.h>
 #include <pthread.h>
 #include <stdatomic.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -500,4 +501,64 @@ void orc_config_solar_sail(sar_config *c)      /* lib.rs:355-386 */
     c->ct_kind = SAR_CT_ADJUSTED_VELOCITY;
     c->ct_factor = -0.2; c->ct_offset = 0.8;   /* lib.rs:381-384 */
     config_defaults(c);
+}
+
+/* ---- output conversion + raw containers, src/bin/main.rs:40-100 ------------
+ * main.rs:52-57 picks DynamicImage::{as is, to_rgb16, to_rgba8, to_rgb8}; the PAM / BMP encoders of the
+ * `image` crate (0.25, Cargo.toml:15 — NOT vendored under /root/reference: third-party, restated from its
+ * published source, "parity unpinned (third-party)") then write image.as_bytes():
+ *   u16 -> u8 sample: `(c16 as u32 + 128) / 257` (image/src/color.rs, FromPrimitive<u16> for u8)
+ *   PAM: header "P7\nWIDTH..\nHEIGHT..\nDEPTH..\nMAXVAL..\nTUPLTYPE ..\nENDHDR\n", 16-bit samples big-endian
+ *   BMP: 8-bit only; Rgb8 -> BITMAPINFOHEADER (40), Rgba8 -> BITMAPV4HEADER (108) BI_BITFIELDS; BGR(A), bottom-up, rows padded to 4. */
+static size_t put_u16le(uint8_t *p, uint32_t v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); return 2; }
+static size_t put_u32le(uint8_t *p, uint32_t v) { put_u16le(p, v & 0xFFFFu); put_u16le(p + 2, v >> 16); return 4; }
+size_t orc_encode(const uint16_t *rgba, uint32_t w, uint32_t h, uint32_t fmt, uint32_t container, uint8_t *out)
+{
+    const int wide = fmt == SAR_PIX_RGBA16 || fmt == SAR_PIX_RGB16, alpha = fmt == SAR_PIX_RGBA16 || fmt == SAR_PIX_RGBA8;
+    const size_t nch = alpha ? 4 : 3, bpp = nch * (wide ? 2 : 1);
+    size_t stride = (size_t)w * bpp, n = 0;
+    if (container == SAR_FILE_BMP) {
+        if (wide) return 0;                                    /* BmpEncoder: unsupported color type -> the reference panics */
+        stride = (stride + 3) / 4 * 4;
+        const uint32_t dib = alpha ? 108u : 40u, off = 14u + dib, img = (uint32_t)(stride * h);
+        if (out) {
+            uint8_t *p = out;
+            *p++ = 'B'; *p++ = 'M'; p += put_u32le(p, img + off); p += put_u16le(p, 0); p += put_u16le(p, 0); p += put_u32le(p, off);
+            p += put_u32le(p, dib); p += put_u32le(p, w); p += put_u32le(p, h); p += put_u16le(p, 1); p += put_u16le(p, alpha ? 32 : 24);
+            p += put_u32le(p, alpha ? 3u : 0u); p += put_u32le(p, img);
+            for (int k = 0; k < 4; ++k) p += put_u32le(p, 0);
+            if (alpha) {
+                p += put_u32le(p, 0xFFu << 16); p += put_u32le(p, 0xFFu << 8); p += put_u32le(p, 0xFFu); p += put_u32le(p, 0xFFu << 24);
+                p += put_u32le(p, 0x73524742u);
+                for (int k = 0; k < 12; ++k) p += put_u32le(p, 0);
+            }
+        }
+        n = off;
+    } else if (container == SAR_FILE_PAM) {
+        char head[160];
+        n = (size_t)snprintf(head, sizeof head, "P7\nWIDTH %u\nHEIGHT %u\nDEPTH %u\nMAXVAL %u\nTUPLTYPE %s\nENDHDR\n",
+                             w, h, (unsigned)nch, wide ? 65535u : 255u, alpha ? "RGB_ALPHA" : "RGB");
+        if (out) memcpy(out, head, n);
+    }
+    if (out) {
+        for (uint32_t y = 0; y < h; ++y) {
+            uint8_t *row = out + n + (size_t)(container == SAR_FILE_BMP ? h - 1 - y : y) * stride;
+            memset(row, 0, stride);
+            for (uint32_t x = 0; x < w; ++x) {
+                const uint16_t *px = rgba + 4 * ((size_t)y * w + x);
+                uint8_t *o = row + (size_t)x * bpp;
+                for (size_t c = 0; c < nch; ++c) {
+                    if (wide) {
+                        if (container == SAR_FILE_PAM) { o[2 * c] = (uint8_t)(px[c] >> 8); o[2 * c + 1] = (uint8_t)px[c]; }
+                        else { o[2 * c] = (uint8_t)px[c]; o[2 * c + 1] = (uint8_t)(px[c] >> 8); }
+                    } else {
+                        const uint8_t v = (uint8_t)(((uint32_t)px[c] + 128u) / 257u);
+                        const size_t k = container == SAR_FILE_BMP && c < 3 ? 2 - c : c;     /* B,G,R[,A] */
+                        o[k] = v;
+                    }
+                }
+            }
+        }
+    }
+    return n + stride * h;
 }

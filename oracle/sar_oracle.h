@@ -103,6 +103,12 @@ int orc_render_parallel(const sar_config *cfg, uint32_t n_threads, uint64_t jobs
  * warm-up: the known answer of lib.rs:329-333.  box = {xmin,xmax,ymin,ymax,zmin,zmax}. */
 void orc_screen_bbox(const sar_config *cfg, const double init[3], uint64_t n, double box[6]);
 
+/* Output conversion + raw containers (src/bin/main.rs:40-100 + the `image` 0.25 crate it calls, which is
+ * third-party and not vendored: restated from its published source, parity unpinned).  fmt / container
+ * are the SAR_PIX_* / SAR_FILE_* values of include/sar.h.  Returns the byte count (0: unsupported, as the
+ * reference's BmpEncoder on 16-bit images); out may be NULL to query it. */
+size_t orc_encode(const uint16_t *rgba_u16, uint32_t w, uint32_t h, uint32_t fmt, uint32_t container, uint8_t *out);
+
 /* Same generator as sar_seed_points (include/sar.h), restated independently. */
 void orc_seed_points(uint64_t seed, uint64_t first, uint64_t n, double *out_xyz);
 

@@ -14,6 +14,9 @@ SAR_OK, SAR_ERR_INVALID, SAR_ERR_DIMS, SAR_ERR_CUDA, SAR_ERR_NOMEM, SAR_ERR_UNSU
 SAR_RENDER_GAS, SAR_RENDER_DEPTH = 0, 1
 SAR_CT_POISSON_SATURNE, SAR_CT_ADJUSTED_VELOCITY = 0, 1
 SAR_SEQ_SHARED_POINTS = 1
+SAR_PIX_RGBA16, SAR_PIX_RGB16, SAR_PIX_RGBA8, SAR_PIX_RGB8 = 0, 1, 2, 3
+SAR_FILE_RAW, SAR_FILE_PAM, SAR_FILE_BMP = 0, 1, 2
+FRAME_BYTES_CALLBACK = C.CFUNCTYPE(None, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint8), C.c_size_t)
 FRAME_CALLBACK = C.CFUNCTYPE(None, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint16))
 
 
@@ -84,6 +87,11 @@ SYMBOLS = {
     "sar_render_parallel": (C.c_int, [_vp, _cfgp, C.c_uint64, C.c_uint64, _f64p, _u16p]),
     "sar_renderer_runtime": (C.c_int, [_vp, _P(_vp)]),
     "sar_render_sequence": (C.c_int, [_vp, _cfgp, _f64p, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32, _u16p, _vp, _vp]),
+    "sar_encoded_size": (C.c_size_t, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]),
+    "sar_encode_header": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _u8p, C.c_size_t, _P(C.c_size_t)]),
+    "sar_runtime_encode": (C.c_int, [_vp, C.c_uint32, C.c_uint32, _u8p, C.c_size_t, _vp]),
+    "sar_write_file": (C.c_int, [C.c_char_p, _u8p, C.c_size_t]),
+    "sar_render_sequence_encoded": (C.c_int, [_vp, _cfgp, _f64p, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, _u8p, _vp, _vp]),
     "sar_render_seeded_async": (C.c_int, [_cfgp, _vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, _vp]),
     "sar_render_device_async": (C.c_int, [_cfgp, _vp, _vp, C.c_uint64, C.c_uint64, C.c_uint32, _vp]),
     "sar_runtime_reset_async": (C.c_int, [_vp, _vp]),

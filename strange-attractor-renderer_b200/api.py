@@ -373,6 +373,47 @@ def render_parallel(renderer: ParallelRenderer, config, jobs_per_thread: int, se
     return out
 
 
+# ---- output conversion + raw encoders (src/bin/main.rs:40-100) ---------------------------
+class PixelFormat(enum.Enum):
+    """What write_image_matches converts the FinalImage to, by (transparent, 8bit) — main.rs:52-57."""
+
+    Rgba16 = N.SAR_PIX_RGBA16   # (true, false): as is
+    Rgb16 = N.SAR_PIX_RGB16     # (false, false): to_rgb16()
+    Rgba8 = N.SAR_PIX_RGBA8     # (true, true): to_rgba8()
+    Rgb8 = N.SAR_PIX_RGB8       # (false, true): to_rgb8()
+
+    @staticmethod
+    def of(transparent: bool, eight_bit: bool) -> "PixelFormat":
+        return {(True, False): PixelFormat.Rgba16, (False, False): PixelFormat.Rgb16,
+                (True, True): PixelFormat.Rgba8, (False, True): PixelFormat.Rgb8}[(bool(transparent), bool(eight_bit))]
+
+
+class Container(enum.Enum):
+    Raw = N.SAR_FILE_RAW        # the converted image.as_bytes() alone (feed it to a PNG encoder)
+    Pam = N.SAR_FILE_PAM        # --pam, main.rs:62-68
+    Bmp = N.SAR_FILE_BMP        # --bmp, main.rs:70-76 (8-bit formats only)
+
+
+def encode_image(runtime: Runtime, pixel_format: PixelFormat, container: Container = Container.Raw) -> np.ndarray:
+    """The image of the last colorize() on `runtime`, converted on the device and wrapped in the
+    container: uint8 array of exactly the bytes the reference's encoder would write."""
+    n = N.lib().sar_encoded_size(runtime.width, runtime.height, pixel_format.value, container.value)
+    if n == 0:
+        raise SarError(N.SAR_ERR_UNSUPPORTED, f"{pixel_format.name} cannot be written as {container.name}")
+    out = np.empty(n, dtype=np.uint8)
+    N.check(N.lib().sar_runtime_encode(runtime._h, pixel_format.value, container.value, out.ctypes.data_as(N._u8p), n, None))
+    return out
+
+
+def write_image(runtime: Runtime, path: str, transparent: bool, eight_bit: bool, container: Container) -> str:
+    """write_image_matches (main.rs:40-100) for the PAM / BMP branches: convert, set the extension, write."""
+    data = encode_image(runtime, PixelFormat.of(transparent, eight_bit), container)
+    ext = {Container.Pam: ".pam", Container.Bmp: ".bmp", Container.Raw: ".raw"}[container]
+    path = os.path.splitext(path)[0] + ext                       # name.set_extension(..), main.rs:63, 71
+    N.check(N.lib().sar_write_file(path.encode(), data.ctypes.data_as(N._u8p), data.size))
+    return path
+
+
 # ---- frame sequences (src/bin/main.rs:107-176, 459-517) ---------------------------------
 def angle_iter(start: float, end: float, step: float) -> List[float]:
     """The angles AngleIter yields (main.rs:107-176): while curr + step/2 < end, curr (DEGREES)
@@ -414,5 +455,34 @@ def render_sequence(renderer: ParallelRenderer, config, angles: Sequence[float],
         renderer._h, C.byref(c), ang.ctypes.data_as(N._f64p), n, jobs_per_thread, seed & (2**64 - 1),
         N.SAR_SEQ_SHARED_POINTS if shared_points else 0,
         out.ctypes.data_as(N._u16p) if out is not None else None,
+        C.cast(cb_c, C.c_void_p) if cb_c is not None else None, None))
+    return out
+
+
+def render_sequence_encoded(renderer: ParallelRenderer, config, angles: Sequence[float], jobs_per_thread: int,
+                            pixel_format: PixelFormat, container: Container = Container.Raw, seed: Optional[int] = None,
+                            shared_points: bool = False, callback=None) -> Optional[np.ndarray]:
+    """render_sequence with every frame converted on the device (main.rs:52-57) and delivered encoded
+    (PAM / BMP / raw bytes) — what the reference's encoder side threads write (main.rs:508-511).
+    Returns [n_frames, n_bytes] uint8, or streams callback(frame_index, bytes_view) when given."""
+    c = _pod(config)
+    if seed is None:
+        seed = int.from_bytes(os.urandom(8), "little")
+    ang = np.ascontiguousarray(angles, dtype=np.float64)
+    n = int(ang.shape[0])
+    nb = N.lib().sar_encoded_size(c.width, c.height, pixel_format.value, container.value)
+    if nb == 0:
+        raise SarError(N.SAR_ERR_UNSUPPORTED, f"{pixel_format.name} cannot be written as {container.name}")
+    out = np.empty((n, nb), dtype=np.uint8) if callback is None else None
+    cb_c = None
+    if callback is not None:
+        def _cb(_user, frame, ptr, nbytes):
+            callback(int(frame), np.ctypeslib.as_array(ptr, shape=(nbytes,)))
+
+        cb_c = N.FRAME_BYTES_CALLBACK(_cb)
+    N.check(N.lib().sar_render_sequence_encoded(
+        renderer._h, C.byref(c), ang.ctypes.data_as(N._f64p), n, jobs_per_thread, seed & (2**64 - 1),
+        N.SAR_SEQ_SHARED_POINTS if shared_points else 0, pixel_format.value, container.value,
+        out.ctypes.data_as(N._u8p) if out is not None else None,
         C.cast(cb_c, C.c_void_p) if cb_c is not None else None, None))
     return out

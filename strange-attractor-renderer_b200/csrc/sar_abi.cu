@@ -85,7 +85,10 @@ struct sar_peer {
 struct seq_device {                  // per-device pipeline state of sar_render_sequence
     sar_runtime *rt[2] = {nullptr, nullptr};        // two Runtimes, frames alternate: frame f renders while frame f-1 is
                                                     // colourised with ITS max read back by the host and copied out
-    uint16_t *stage[2] = {nullptr, nullptr};        // pinned host staging (when the caller gives no frame array)
+    uint8_t *stage[2] = {nullptr, nullptr};         // pinned host staging (when the caller gives no frame array)
+    size_t stage_bytes = 0;
+    uint8_t *enc[2] = {nullptr, nullptr};           // device: converted pixels (formats other than RGBA16 native)
+    size_t enc_bytes = 0;
     uint32_t *h_max = nullptr;                      // pinned: Runtime.max of the frame in each slot
     cudaEvent_t max_ready[2] = {nullptr, nullptr}, rendered[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr};
     cudaStream_t copy_stream = nullptr;
@@ -905,6 +908,7 @@ static void seq_release(sar_renderer *r, size_t d)
     for (int k = 0; k < 2; ++k) {
         sar_runtime_free(q.rt[k]);
         if (q.stage[k]) cudaFreeHost(q.stage[k]);
+        cudaFree(q.enc[k]);
         if (q.max_ready[k]) cudaEventDestroy(q.max_ready[k]);
         if (q.rendered[k]) cudaEventDestroy(q.rendered[k]);
         if (q.copied[k]) cudaEventDestroy(q.copied[k]);
@@ -1044,12 +1048,115 @@ int sar_render_parallel(sar_renderer *r, const sar_config *cfg_in, uint64_t jobs
     return sar_runtime_image_download(rt0, 0, 0, rgba_u16, nullptr);
 }
 
+// ---- output conversion + raw encoders (src/bin/main.rs:40-100) -----------------------------------
+// `write_image_matches` converts the FinalImage (main.rs:52-57: RGBA16 as is, to_rgb16, to_rgba8, to_rgb8)
+// and hands `image.as_bytes()` to an encoder of the `image` crate (PAM main.rs:62-68, BMP :70-76, PNG :78-89).
+// Here the conversion runs on the device (convert_kernel) and the two RAW containers are written around it:
+// the host only formats the header.  PNG (deflate) stays with the caller: hand it the RAW bytes.
+struct OutSpec {
+    uint32_t fmt = SAR_PIX_RGBA16, container = SAR_FILE_RAW;
+    uint32_t order = ORDER_NATIVE;
+    size_t row_stride = 0, payload = 0, header = 0, total = 0;
+    uint8_t head[160] = {0};
+};
+static int make_outspec(uint32_t w, uint32_t h, uint32_t fmt, uint32_t container, OutSpec &o)
+{
+    if (fmt > SAR_PIX_RGB8) return fail(SAR_ERR_INVALID, "pixel_format %u", fmt);
+    if (container > SAR_FILE_BMP) return fail(SAR_ERR_INVALID, "container %u", container);
+    const bool wide = fmt == SAR_PIX_RGBA16 || fmt == SAR_PIX_RGB16, alpha = fmt == SAR_PIX_RGBA16 || fmt == SAR_PIX_RGBA8;
+    const size_t bpp = (alpha ? 4 : 3) * (wide ? 2 : 1);
+    o.fmt = fmt; o.container = container;
+    o.row_stride = (size_t)w * bpp;
+    o.order = ORDER_NATIVE;
+    o.header = 0;
+    if (container == SAR_FILE_PAM) {
+        // image 0.25 pnm encoder, ArbitraryMap subtype: "P7\nWIDTH w\nHEIGHT h\nDEPTH d\nMAXVAL m\nTUPLTYPE t\nENDHDR\n",
+        // 16-bit samples most significant byte first
+        o.order = wide ? ORDER_BIG_ENDIAN : ORDER_NATIVE;
+        o.header = (size_t)snprintf((char *)o.head, sizeof o.head, "P7\nWIDTH %u\nHEIGHT %u\nDEPTH %u\nMAXVAL %u\nTUPLTYPE %s\nENDHDR\n",
+                                    w, h, alpha ? 4u : 3u, wide ? 65535u : 255u, alpha ? "RGB_ALPHA" : "RGB");
+    } else if (container == SAR_FILE_BMP) {
+        // image 0.25 bmp encoder: 8-bit only (a 16-bit image makes the reference panic in write_image's unwrap, main.rs:36);
+        // Rgb8 -> BITMAPINFOHEADER, 24 bpp; Rgba8 -> BITMAPV4HEADER, 32 bpp BI_BITFIELDS, BGRA; rows bottom-up, padded to 4 bytes
+        if (wide) return fail(SAR_ERR_UNSUPPORTED, "BMP holds 8-bit samples only (the reference's BmpEncoder rejects 16-bit images)");
+        o.order = ORDER_BMP;
+        o.row_stride = align_up((size_t)w * bpp, 4);
+        const uint32_t dib = alpha ? 108u : 40u, off = 14u + dib;
+        const uint64_t img = (uint64_t)o.row_stride * h;
+        if (img + off > 0xFFFFFFFFull) return fail(SAR_ERR_INVALID, "image too large for a BMP file");
+        uint8_t *p = o.head;
+        auto u16le = [&](uint32_t v) { *p++ = (uint8_t)v; *p++ = (uint8_t)(v >> 8); };
+        auto u32le = [&](uint32_t v) { u16le(v & 0xFFFFu); u16le(v >> 16); };
+        *p++ = 'B'; *p++ = 'M'; u32le((uint32_t)(img + off)); u16le(0); u16le(0); u32le(off);
+        u32le(dib); u32le(w); u32le(h); u16le(1); u16le(alpha ? 32 : 24); u32le(alpha ? 3u : 0u); u32le((uint32_t)img);
+        u32le(0); u32le(0); u32le(0); u32le(0);
+        if (alpha) {
+            u32le(0xFFu << 16); u32le(0xFFu << 8); u32le(0xFFu); u32le(0xFFu << 24);   // R, G, B, A masks
+            u32le(0x73524742u);                                                          // "sRGB"
+            for (int k = 0; k < 12; ++k) u32le(0);                                       // endpoints + gamma
+        }
+        o.header = (size_t)(p - o.head);
+    }
+    o.payload = o.row_stride * h;
+    o.total = o.header + o.payload;
+    return SAR_OK;
+}
+
+size_t sar_encoded_size(uint32_t width, uint32_t height, uint32_t pixel_format, uint32_t container)
+{
+    OutSpec o;
+    if (check_dims(width, height) || make_outspec(width, height, pixel_format, container, o)) return 0;
+    return o.total;
+}
+
+int sar_encode_header(uint32_t width, uint32_t height, uint32_t pixel_format, uint32_t container, uint8_t *out, size_t out_bytes,
+                      size_t *header_bytes)
+{
+    OutSpec o;
+    if (int rc = check_dims(width, height)) return rc;
+    if (int rc = make_outspec(width, height, pixel_format, container, o)) return rc;
+    if (header_bytes) *header_bytes = o.header;
+    if (out) {
+        if (out_bytes < o.header) return fail(SAR_ERR_INVALID, "header needs %zu bytes", o.header);
+        memcpy(out, o.head, o.header);
+    }
+    return SAR_OK;
+}
+
+int sar_runtime_encode(sar_runtime *rt, uint32_t pixel_format, uint32_t container, uint8_t *out, size_t out_bytes, void *stream)
+{
+    if (!rt || !out) return fail(SAR_ERR_INVALID, "NULL argument");
+    OutSpec o;
+    if (int rc = make_outspec(rt->w, rt->h, pixel_format, container, o)) return rc;
+    if (out_bytes < o.total) return fail(SAR_ERR_INVALID, "output needs %zu bytes (got %zu)", o.total, out_bytes);
+    SAR_CUDA(cudaSetDevice(rt->device));
+    cudaStream_t s = pick(rt, stream);
+    if (int rc = ensure_scratch(rt, o.payload)) return rc;
+    launch_convert(rt->image, (uint8_t *)rt->d_scratch, rt->w, rt->h, o.fmt, o.order, o.row_stride, s);
+    SAR_CUDA(cudaGetLastError());
+    memcpy(out, o.head, o.header);
+    SAR_CUDA(cudaMemcpyAsync(out + o.header, rt->d_scratch, o.payload, cudaMemcpyDeviceToHost, s));
+    SAR_CUDA(cudaStreamSynchronize(s));
+    return SAR_OK;
+}
+
+int sar_write_file(const char *path, const uint8_t *bytes, size_t n_bytes)
+{
+    if (!path || (!bytes && n_bytes)) return fail(SAR_ERR_INVALID, "NULL argument");
+    FILE *f = fopen(path, "wb");                                 // File::create(path).unwrap(), main.rs:102-104
+    if (!f) return fail(SAR_ERR_INVALID, "cannot create '%s'", path);
+    const size_t n = fwrite(bytes, 1, n_bytes, f);
+    const int rc = fclose(f);
+    if (n != n_bytes || rc != 0) return fail(SAR_ERR_INVALID, "short write to '%s'", path);
+    return SAR_OK;
+}
+
 // ---- frame sequences -------------------------------------------------------------------------
 // The per-frame loop of the reference's binary (src/bin/main.rs:496-512): for each angle,
 // config.angle = angle; image = render_parallel(...); hand the image to an encoder thread.
 // Frames are independent, so they round-robin over the renderer's devices (replicas, no
 // collective); on each device the frame's device→host copy overlaps the next frame's render.
-static int seq_prepare(sar_renderer *r, size_t d, const sar_config &cfg, bool need_stage)
+static int seq_prepare(sar_renderer *r, size_t d, const sar_config &cfg, bool need_stage, const OutSpec &o)
 {
     seq_device &q = r->seq[d];
     const size_t bytes = (size_t)cfg.width * cfg.height * 4 * sizeof(uint16_t);
@@ -1062,20 +1169,35 @@ static int seq_prepare(sar_renderer *r, size_t d, const sar_config &cfg, bool ne
     if (!q.h_max) SAR_CUDA(cudaHostAlloc((void **)&q.h_max, 2 * sizeof(uint32_t), cudaHostAllocPortable));
     for (int k = 0; k < 2; ++k) {
         if (!q.rt[k]) if (int rc = sar_runtime_new(cfg.width, cfg.height, r->devices[d], &q.rt[k])) return rc;
-        if (need_stage && !q.stage[k]) SAR_CUDA(cudaHostAlloc((void **)&q.stage[k], bytes, cudaHostAllocPortable));
+        if (need_stage && (!q.stage[k] || q.stage_bytes < o.total)) {
+            if (q.stage[k]) cudaFreeHost(q.stage[k]);
+            q.stage[k] = nullptr;
+            SAR_CUDA(cudaHostAlloc((void **)&q.stage[k], o.total, cudaHostAllocPortable));
+        }
+        const bool convert = !(o.fmt == SAR_PIX_RGBA16 && o.order == ORDER_NATIVE);
+        if (convert && (!q.enc[k] || q.enc_bytes < o.payload)) {
+            cudaFree(q.enc[k]);
+            q.enc[k] = nullptr;
+            SAR_CUDA(cudaMalloc((void **)&q.enc[k], o.payload));
+        }
         if (!q.max_ready[k]) SAR_CUDA(cudaEventCreateWithFlags(&q.max_ready[k], cudaEventDisableTiming));
         if (!q.rendered[k]) SAR_CUDA(cudaEventCreateWithFlags(&q.rendered[k], cudaEventDisableTiming));
         if (!q.copied[k]) SAR_CUDA(cudaEventCreateWithFlags(&q.copied[k], cudaEventDisableTiming));
     }
+    if (need_stage) q.stage_bytes = q.stage_bytes < o.total ? o.total : q.stage_bytes;
+    q.enc_bytes = q.enc_bytes < o.payload ? o.payload : q.enc_bytes;
     return SAR_OK;
 }
 
-int sar_render_sequence(sar_renderer *r, const sar_config *cfg_in, const double *angles_rad, uint32_t n_frames,
-                        uint64_t jobs_per_thread, uint64_t seed, uint32_t flags, uint16_t *rgba_frames,
-                        sar_frame_callback cb, void *user)
+// frames_out: n_frames x o.total bytes (may be NULL); cb16 / cb8: at most one of them
+static int sequence_core(sar_renderer *r, const sar_config *cfg_in, const double *angles_rad, uint32_t n_frames,
+                         uint64_t jobs_per_thread, uint64_t seed, uint32_t flags, const OutSpec &o, uint8_t *frames_out,
+                         sar_frame_callback cb16, sar_frame_bytes_callback cb8, void *user)
 {
     if (!r || !cfg_in || (!angles_rad && n_frames)) return fail(SAR_ERR_INVALID, "NULL argument");
-    if (!rgba_frames && !cb) return fail(SAR_ERR_INVALID, "need a frame array or a callback");
+    if (!frames_out && !cb16 && !cb8) return fail(SAR_ERR_INVALID, "need a frame array or a callback");
+    uint8_t *const rgba_frames = frames_out;
+    const bool convert = !(o.fmt == SAR_PIX_RGBA16 && o.order == ORDER_NATIVE);
     if (jobs_per_thread == 0) return fail(SAR_ERR_INVALID, "jobs_per_thread must be non-zero");
     if (flags & ~SAR_SEQ_SHARED_POINTS) return fail(SAR_ERR_INVALID, "unknown flags 0x%x", flags);
     if (int rc = check_config(cfg_in, nullptr)) return rc;
@@ -1083,7 +1205,7 @@ int sar_render_sequence(sar_renderer *r, const sar_config *cfg_in, const double 
     if (n_frames == 0) return SAR_OK;
     const size_t nd = r->devices.size();
     const bool shared = (flags & SAR_SEQ_SHARED_POINTS) != 0;
-    const size_t frame_u16 = (size_t)cfg_in->width * cfg_in->height * 4;
+    const size_t frame_u16 = o.total;          // bytes of one delivered frame
 
     // every device renders whole frames with its own lanes: the decomposition of a frame is that
     // of a one-device render_parallel (lib.rs:1058-1062)
@@ -1095,7 +1217,7 @@ int sar_render_sequence(sar_renderer *r, const sar_config *cfg_in, const double 
         jobs[d] = (uint64_t)threads[d] * jobs_per_thread;
         lanes[d] = r->threads_per_device ? threads[d] : (uint32_t)(jobs[d] < renderer_lanes(r, d) ? jobs[d] : renderer_lanes(r, d));
         cfgs[d].iterations = cfg_in->iterations / threads[d] / jobs_per_thread;
-        if (int rc = seq_prepare(r, d, *cfg_in, rgba_frames == nullptr)) return rc;
+        if (int rc = seq_prepare(r, d, *cfg_in, rgba_frames == nullptr, o)) return rc;
         if (shared) {   // warm the one shared list of start points once (lib.rs:748-752)
             seq_device &q = r->seq[d];
             const size_t need = (size_t)jobs[d] * 3 * sizeof(double);
@@ -1126,10 +1248,16 @@ int sar_render_sequence(sar_renderer *r, const sar_config *cfg_in, const double 
         make_color_params(&cfg, rt, cp, 0, rt->h, &q.h_max[slot]);
         launch_colorize(cp, rt->fast, rt->rec, rt->scal, rt->image, nullptr, rt->stream);   // colorize, lib.rs:1080
         SAR_CUDA(cudaGetLastError());
+        if (convert) {                                                          // main.rs:52-57 on the device
+            launch_convert(rt->image, q.enc[slot], rt->w, rt->h, o.fmt, o.order, o.row_stride, rt->stream);
+            SAR_CUDA(cudaGetLastError());
+        }
         SAR_CUDA(cudaEventRecord(q.rendered[slot], rt->stream));
         SAR_CUDA(cudaStreamWaitEvent(q.copy_stream, q.rendered[slot], 0));
-        uint16_t *dst = rgba_frames ? rgba_frames + (size_t)g * frame_u16 : q.stage[slot];
-        SAR_CUDA(cudaMemcpyAsync(dst, rt->image, q.img_bytes, cudaMemcpyDeviceToHost, q.copy_stream));
+        uint8_t *dst = rgba_frames ? rgba_frames + (size_t)g * frame_u16 : q.stage[slot];
+        memcpy(dst, o.head, o.header);
+        SAR_CUDA(cudaMemcpyAsync(dst + o.header, convert ? (const void *)q.enc[slot] : (const void *)rt->image, o.payload,
+                                 cudaMemcpyDeviceToHost, q.copy_stream));
         SAR_CUDA(cudaEventRecord(q.copied[slot], q.copy_stream));
         return SAR_OK;
     };
@@ -1138,7 +1266,9 @@ int sar_render_sequence(sar_renderer *r, const sar_config *cfg_in, const double 
         const int slot = (int)((g / nd) % 2);
         SAR_CUDA(cudaSetDevice(r->devices[d]));
         SAR_CUDA(cudaEventSynchronize(r->seq[d].copied[slot]));
-        if (cb) cb(user, g, rgba_frames ? rgba_frames + (size_t)g * frame_u16 : r->seq[d].stage[slot]);
+        const uint8_t *bytes = rgba_frames ? rgba_frames + (size_t)g * frame_u16 : r->seq[d].stage[slot];
+        if (cb16) cb16(user, g, reinterpret_cast<const uint16_t *>(bytes));
+        if (cb8) cb8(user, g, bytes, o.total);
         return SAR_OK;
     };
 
@@ -1174,6 +1304,29 @@ int sar_render_sequence(sar_renderer *r, const sar_config *cfg_in, const double 
         for (int k = 0; k < 2; ++k) SAR_CUDA(cudaStreamSynchronize(r->seq[d].rt[k]->stream));
     }
     return SAR_OK;
+}
+
+int sar_render_sequence(sar_renderer *r, const sar_config *cfg_in, const double *angles_rad, uint32_t n_frames,
+                        uint64_t jobs_per_thread, uint64_t seed, uint32_t flags, uint16_t *rgba_frames,
+                        sar_frame_callback cb, void *user)
+{
+    if (!cfg_in) return fail(SAR_ERR_INVALID, "NULL argument");
+    OutSpec o;
+    if (int rc = check_dims(cfg_in->width, cfg_in->height)) return rc;
+    if (int rc = make_outspec(cfg_in->width, cfg_in->height, SAR_PIX_RGBA16, SAR_FILE_RAW, o)) return rc;
+    return sequence_core(r, cfg_in, angles_rad, n_frames, jobs_per_thread, seed, flags, o, reinterpret_cast<uint8_t *>(rgba_frames),
+                         cb, nullptr, user);
+}
+
+int sar_render_sequence_encoded(sar_renderer *r, const sar_config *cfg_in, const double *angles_rad, uint32_t n_frames,
+                                uint64_t jobs_per_thread, uint64_t seed, uint32_t flags, uint32_t pixel_format,
+                                uint32_t container, uint8_t *frames_out, sar_frame_bytes_callback cb, void *user)
+{
+    if (!cfg_in) return fail(SAR_ERR_INVALID, "NULL argument");
+    OutSpec o;
+    if (int rc = check_dims(cfg_in->width, cfg_in->height)) return rc;
+    if (int rc = make_outspec(cfg_in->width, cfg_in->height, pixel_format, container, o)) return rc;
+    return sequence_core(r, cfg_in, angles_rad, n_frames, jobs_per_thread, seed, flags, o, frames_out, nullptr, cb, user);
 }
 
 }  // extern "C"

@@ -120,6 +120,12 @@ struct ColorParams {
     double ln_max1_host;
 };
 
+// output conversion (src/bin/main.rs:52-57): pixel formats and sample orders of launch_convert
+enum { PIX_RGBA16 = 0, PIX_RGB16 = 1, PIX_RGBA8 = 2, PIX_RGB8 = 3 };
+enum { ORDER_NATIVE = 0, ORDER_BIG_ENDIAN = 1, ORDER_BMP = 2 };
+void launch_convert(const uint16_t *rgba, uint8_t *out, unsigned int W, unsigned int H, unsigned int fmt, unsigned int order,
+                    size_t row_stride, cudaStream_t s);
+
 // launchers (sar_kernels.cu); every one bumps the launch counter
 void launch_reset(unsigned long long *fast, ulonglong2 *rec, Scalars *scal, size_t npix, size_t nslots, cudaStream_t s);
 void launch_iterate(const IterParams &p, unsigned int lanes, cudaStream_t s);

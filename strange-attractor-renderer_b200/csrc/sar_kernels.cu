@@ -774,6 +774,60 @@ void launch_frame_colorize(const ColorParams &cp, const uint32_t *cnt, const ulo
 }
 
 // ---------------------------------------------------------------------------------------------
+// Output conversion (src/bin/main.rs:52-57): FinalImage (RGBA u16) -> what the encoders are handed.
+//   to_rgb16  drops alpha; to_rgba8 / to_rgb8 narrow every sample with the `image` crate's
+//   u16 -> u8 rule (image 0.25, color.rs, FromPrimitive<u16> for u8): (c + 128) / 257, i.e.
+//   round(c * 255 / 65535) — third-party code absent from /root/reference, restated from its
+//   published source ("parity unpinned (third-party)").
+// Sample order: native little-endian (what DynamicImage::as_bytes() holds), big-endian 16-bit
+// samples (what the PNM/PAM and PNG encoders write, main.rs:62-68), or BMP order (B,G,R[,A], rows
+// bottom-up, each row padded to 4 bytes; 8-bit only, main.rs:70-76).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t narrow_u16(uint32_t c) { return (c + 128u) / 257u; }
+
+__global__ void convert_kernel(const ushort4 *__restrict__ img, uint8_t *__restrict__ out, unsigned int W, unsigned int H,
+                               unsigned int fmt, unsigned int order, size_t row_stride)
+{
+    const size_t npix = (size_t)W * H;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += stride) {
+        const ushort4 v = img[p];
+        const unsigned int y = (unsigned int)(p / W), x = (unsigned int)(p - (size_t)y * W);
+        const bool alpha = fmt == PIX_RGBA16 || fmt == PIX_RGBA8;
+        if (fmt == PIX_RGBA16 || fmt == PIX_RGB16) {
+            uint16_t c[4] = {v.x, v.y, v.z, v.w};
+            if (order == ORDER_BIG_ENDIAN)
+                for (int k = 0; k < 4; ++k) c[k] = (uint16_t)((c[k] >> 8) | (c[k] << 8));
+            uint16_t *o = reinterpret_cast<uint16_t *>(out + (size_t)y * row_stride) + (size_t)x * (alpha ? 4 : 3);
+            if (alpha) *reinterpret_cast<ushort4 *>(o) = make_ushort4(c[0], c[1], c[2], c[3]);
+            else { o[0] = c[0]; o[1] = c[1]; o[2] = c[2]; }
+        } else {
+            const uint32_t r = narrow_u16(v.x), g = narrow_u16(v.y), b = narrow_u16(v.z), a = narrow_u16(v.w);
+            const unsigned int yy = order == ORDER_BMP ? H - 1u - y : y;
+            uint8_t *o = out + (size_t)yy * row_stride + (size_t)x * (alpha ? 4 : 3);
+            if (order == ORDER_BMP) {
+                if (alpha) *reinterpret_cast<uint32_t *>(o) = b | (g << 8) | (r << 16) | (a << 24);
+                else { o[0] = (uint8_t)b; o[1] = (uint8_t)g; o[2] = (uint8_t)r; }
+                if (x == W - 1u) for (size_t k = (size_t)W * (alpha ? 4 : 3); k < row_stride; ++k) out[(size_t)yy * row_stride + k] = 0;   // row padding
+            } else {
+                if (alpha) *reinterpret_cast<uint32_t *>(o) = r | (g << 8) | (b << 16) | (a << 24);
+                else { o[0] = (uint8_t)r; o[1] = (uint8_t)g; o[2] = (uint8_t)b; }
+            }
+        }
+    }
+}
+void launch_convert(const uint16_t *rgba, uint8_t *out, unsigned int W, unsigned int H, unsigned int fmt, unsigned int order,
+                    size_t row_stride, cudaStream_t s)
+{
+    const size_t npix = (size_t)W * H;
+    if (npix == 0) return;
+    const unsigned int block = 256;
+    size_t g = (npix + block - 1) / block;
+    convert_kernel<<<(unsigned int)(g > 148u * 16u ? 148u * 16u : g), block, 0, s>>>(reinterpret_cast<const ushort4 *>(rgba), out, W, H, fmt, order, row_stride);
+    ++g_launches;
+}
+
+// ---------------------------------------------------------------------------------------------
 // layout conversion to / from the reference's three textures (lib.rs:633-639)
 // ---------------------------------------------------------------------------------------------
 __global__ void unpack_kernel(const unsigned long long *fast, const ulonglong2 *rec, const Scalars *scal, size_t npix, SlotMap slots,

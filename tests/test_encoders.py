@@ -1,0 +1,111 @@
+"""Output conversion + raw containers (src/bin/main.rs:40-100): device path vs the oracle restatement.
+
+CPU part: container headers and sizes (host logic of the library, no GPU).  GPU part: every
+(pixel format, container) pair byte for byte, the encoded sequence, and the RGB16 known answer of
+the reference's published image (pixel (0,0) of media/solar-sail-220deg.png = 65535, 65535, 60849).
+The u16 -> u8 rule and the container layouts come from the `image` 0.25 crate, which is not under
+/root/reference: both sides restate its published source (parity unpinned, third-party)."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+FORMATS = [0, 1, 2, 3]           # SAR_PIX_RGBA16, RGB16, RGBA8, RGB8
+CONTAINERS = [0, 1, 2]           # SAR_FILE_RAW, PAM, BMP
+
+
+def test_headers_and_sizes_match_the_oracle(oracle):
+    from strange_attractor_renderer_b200 import _native as N
+
+    L = N.lib()
+    rng = np.random.default_rng(5)
+    for (w, h) in [(1, 1), (3, 2), (5, 7), (450, 501), (2048, 2048)]:
+        img = rng.integers(0, 65536, (h, w, 4), dtype=np.uint16) if w * h < 10_000 else np.zeros((h, w, 4), np.uint16)
+        for fmt in FORMATS:
+            for cont in CONTAINERS:
+                ref = oracle.encode(img, fmt, cont)
+                size = L.sar_encoded_size(w, h, fmt, cont)
+                if ref is None:                       # BMP cannot hold 16-bit samples (the reference panics)
+                    assert size == 0 and cont == 2 and fmt in (0, 1)
+                    assert L.sar_encode_header(w, h, fmt, cont, None, 0, None) == N.SAR_ERR_UNSUPPORTED
+                    continue
+                assert size == ref.size
+                hb = C.c_size_t()
+                N.check(L.sar_encode_header(w, h, fmt, cont, None, 0, C.byref(hb)))
+                head = np.zeros(hb.value, np.uint8)
+                N.check(L.sar_encode_header(w, h, fmt, cont, head.ctypes.data_as(N._u8p), head.size, None))
+                assert np.array_equal(head, ref[:hb.value])
+    # the PAM header is plain text: spot-check it against the format definition
+    hb = C.c_size_t()
+    buf = np.zeros(160, np.uint8)
+    N.check(L.sar_encode_header(12, 34, 1, 1, buf.ctypes.data_as(N._u8p), 160, C.byref(hb)))
+    assert bytes(buf[:hb.value]) == b"P7\nWIDTH 12\nHEIGHT 34\nDEPTH 3\nMAXVAL 65535\nTUPLTYPE RGB\nENDHDR\n"
+    assert L.sar_encoded_size(12, 34, 9, 0) == 0 and L.sar_encoded_size(0, 4, 0, 0) == 0
+
+
+def test_u16_to_u8_rule_is_round_to_nearest(oracle):
+    """image 0.25: (c + 128) / 257 == round(c * 255 / 65535) for every u16."""
+    c = np.arange(65536, dtype=np.uint32)
+    rule = (c + 128) // 257
+    assert np.array_equal(rule, np.floor(c * 255 / 65535 + 0.5).astype(np.uint32))
+    img = np.zeros((1, 65536, 4), np.uint16)
+    img[0, :, 0] = c
+    out = oracle.encode(img, 3, 0).reshape(65536, 3)
+    assert np.array_equal(out[:, 0], rule.astype(np.uint8))
+
+
+@pytest.mark.gpu
+def test_device_conversion_matches_oracle_bytes(oracle):
+    import strange_attractor_renderer_b200 as S
+
+    cfg = S.Config.solar_sail()
+    cfg.width, cfg.height, cfg.iterations, cfg.angle = 203, 97, 30_000, 220.0 * math.pi / 180.0
+    rt = S.Runtime.new(cfg)
+    S.render(cfg, rt, initial_points=S.seed_points(7, 0, 128))
+    for transparent in (True, False):
+        cfg.transparent = transparent
+        img = S.colorize(cfg, rt)
+        for fmt in S.PixelFormat:
+            for cont in S.Container:
+                ref = oracle.encode(img, fmt.value, cont.value)
+                if ref is None:
+                    with pytest.raises(S.SarError):
+                        S.encode_image(rt, fmt, cont)
+                    continue
+                got = S.encode_image(rt, fmt, cont)
+                assert np.array_equal(got, ref), (fmt, cont, int((got != ref).sum()))
+    # known answer of the reference's published image: pixel (0,0), RGB16 big-endian in a PAM
+    cfg.transparent = False
+    S.colorize(cfg, rt)
+    pam = S.encode_image(rt, S.PixelFormat.of(False, False), S.Container.Pam)
+    head = bytes(pam[:80]).split(b"ENDHDR\n")[0] + b"ENDHDR\n"
+    px = pam[len(head):len(head) + 6]
+    assert [int(px[0]) << 8 | px[1], int(px[2]) << 8 | px[3], int(px[4]) << 8 | px[5]] == [65535, 65535, 60849]
+
+
+@pytest.mark.gpu
+def test_encoded_sequence_equals_per_frame_encoding(oracle, tmp_path):
+    import strange_attractor_renderer_b200 as S
+
+    cfg = S.Config.poisson_saturne()
+    cfg.width, cfg.height, cfg.iterations, cfg.transparent = 160, 120, 2_000_000, True
+    angles = S.angle_iter(0.0, 60.0, 20.0)
+    r = S.ParallelRenderer.new(threads=128)
+    plain = S.render_sequence(r, cfg, angles, 1, seed=3)
+    for fmt, cont in ((S.PixelFormat.Rgb8, S.Container.Bmp), (S.PixelFormat.Rgba16, S.Container.Pam), (S.PixelFormat.Rgb16, S.Container.Raw)):
+        enc = S.render_sequence_encoded(r, cfg, angles, 1, fmt, cont, seed=3)
+        seen = []
+        S.render_sequence_encoded(r, cfg, angles, 1, fmt, cont, seed=3, callback=lambda f, b: seen.append((f, b.copy())))
+        assert [f for f, _ in seen] == list(range(len(angles)))
+        for f in range(len(angles)):
+            ref = oracle.encode(plain[f], fmt.value, cont.value)
+            assert np.array_equal(enc[f], ref) and np.array_equal(seen[f][1], ref)
+    # write_image_matches: convert, set the extension, write (main.rs:40-100)
+    rt = S.Runtime.new(cfg)
+    S.render(cfg, rt, initial_points=S.seed_points(1, 0, 32))
+    img = S.colorize(cfg, rt)
+    path = S.write_image(rt, str(tmp_path / "frame.png"), transparent=False, eight_bit=True, container=S.Container.Bmp)
+    assert path.endswith("frame.bmp")
+    assert np.array_equal(np.fromfile(path, dtype=np.uint8), oracle.encode(img, 3, 2))
+    r.shutdown()
