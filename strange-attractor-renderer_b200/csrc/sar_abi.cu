@@ -1184,8 +1184,9 @@ static int seq_prepare(sar_renderer *r, size_t d, const sar_config &cfg, bool ne
         if (!q.rendered[k]) SAR_CUDA(cudaEventCreateWithFlags(&q.rendered[k], cudaEventDisableTiming));
         if (!q.copied[k]) SAR_CUDA(cudaEventCreateWithFlags(&q.copied[k], cudaEventDisableTiming));
     }
-    if (need_stage) q.stage_bytes = q.stage_bytes < o.total ? o.total : q.stage_bytes;
-    q.enc_bytes = q.enc_bytes < o.payload ? o.payload : q.enc_bytes;
+    // capacities of what was (re)allocated above
+    if (need_stage && q.stage_bytes < o.total) q.stage_bytes = o.total;
+    if (!(o.fmt == SAR_PIX_RGBA16 && o.order == ORDER_NATIVE) && q.enc_bytes < o.payload) q.enc_bytes = o.payload;
     return SAR_OK;
 }
 

@@ -80,8 +80,8 @@ def test_device_conversion_matches_oracle_bytes(oracle):
     S.colorize(cfg, rt)
     pam = S.encode_image(rt, S.PixelFormat.of(False, False), S.Container.Pam)
     head = bytes(pam[:80]).split(b"ENDHDR\n")[0] + b"ENDHDR\n"
-    px = pam[len(head):len(head) + 6]
-    assert [int(px[0]) << 8 | px[1], int(px[2]) << 8 | px[3], int(px[4]) << 8 | px[5]] == [65535, 65535, 60849]
+    px = [int(v) for v in pam[len(head):len(head) + 6]]
+    assert [px[0] << 8 | px[1], px[2] << 8 | px[3], px[4] << 8 | px[5]] == [65535, 65535, 60849]
 
 
 @pytest.mark.gpu
