@@ -130,6 +130,28 @@ int sar_config_solar_sail(sar_config *cfg);
  * out_xyz[3*(k-first) + c] for k in [first, first+n). */
 int sar_seed_points(uint64_t seed, uint64_t first, uint64_t n, double *out_xyz);
 
+/* ---- auto-framing first pass ------------------------------------------ */
+/* The reference author's TODO (lib.rs:326-334): "Add option to make first-pass
+ * to get these values, to then compute center_camera".  n_jobs trajectories
+ * (start points init_xyz, or sar_seed_points(seed) when NULL), each 1000
+ * warm-up steps then `iterations` steps; box = {xmin,xmax,ymin,ymax,zmin,zmax}
+ * of screen_space = R·p (lib.rs:773) — the quantity of the comment's table —
+ * over every trajectory that stays bounded; `diverged` counts the others (for
+ * solar_sail ~38 % of the start points; they still render, into the NaN sink).
+ * center_camera = minus the box mid-points in the pairing the projection uses
+ * (x, screen z, screen y; lib.rs:776-786); scale = 0.95 x the largest scale
+ * that keeps the box in view from every view angle at cfg's aspect ratio
+ * (cfg->width/height; 1:1 when 0).  The box equals the oracle's bit for bit. */
+typedef struct sar_autoframe_result {
+    double   box[6];
+    double   center_camera[3];
+    double   scale;
+    uint64_t diverged;
+    uint64_t n_jobs;
+} sar_autoframe_result;
+int sar_autoframe(const sar_config *cfg, int device, uint64_t seed, const double *init_xyz,
+                  uint64_t n_jobs, uint64_t iterations, sar_autoframe_result *out);
+
 /* ---- Runtime ---------------------------------------------------------- */
 /* Runtime::new, lib.rs:660 (allocate + reset) on CUDA device `device`. */
 int  sar_runtime_new(uint32_t width, uint32_t height, int device, sar_runtime **out);

@@ -108,6 +108,8 @@ def lib() -> C.CDLL:
         L.orc_encode.argtypes = [P(C.c_uint16), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, P(C.c_uint8)]
         L.orc_encode.restype = C.c_size_t
         L.orc_screen_bbox.argtypes = [P(SarConfig), dp, C.c_uint64, dp]
+        L.orc_screen_bbox_jobs.argtypes = [P(SarConfig), dp, C.c_uint64, C.c_uint64, dp, P(C.c_uint64)]
+        L.orc_screen_bbox_jobs.restype = None
         L.orc_seed_points.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, dp]
         L.orc_config_poisson_saturne.argtypes = [P(SarConfig)]
         L.orc_config_solar_sail.argtypes = [P(SarConfig)]
@@ -289,3 +291,13 @@ def encode(rgba_u16: np.ndarray, fmt: int, container: int):
     out = np.empty(n, dtype=np.uint8)
     lib().orc_encode(img.ctypes.data_as(C.POINTER(C.c_uint16)), w, h, fmt, container, out.ctypes.data_as(C.POINTER(C.c_uint8)))
     return out
+
+
+def screen_bbox_jobs(cfg, init_xyz, n: int):
+    """-> (box[6], diverged): union of the screen-space boxes of the bounded trajectories."""
+    cfg = as_oracle_config(cfg)
+    pts = np.ascontiguousarray(init_xyz, dtype=np.float64).reshape(-1, 3)
+    box = np.empty(6, dtype=np.float64)
+    bad = C.c_uint64()
+    lib().orc_screen_bbox_jobs(C.byref(cfg), _dp(pts), pts.shape[0], n, _dp(box), C.byref(bad))
+    return box, int(bad.value)

@@ -438,6 +438,40 @@ void orc_screen_bbox(const sar_config *cfg, const double init[3], uint64_t n, do
     }
 }
 
+/* The first pass the reference's author sketches at lib.rs:326-334, over a list of start points: the
+ * union of the per-trajectory boxes of every trajectory that stays finite; the others are counted. */
+void orc_screen_bbox_jobs(const sar_config *cfg, const double *init_xyz, uint64_t n_jobs, uint64_t n,
+                          double box[6], uint64_t *diverged)
+{
+    box[0] = box[2] = box[4] = INFINITY;
+    box[1] = box[3] = box[5] = -INFINITY;
+    uint64_t bad = 0;
+    double R[3][3];
+    orc_rotation_matrix(cfg->axis, cfg->rotation, R);
+    for (uint64_t k = 0; k < n_jobs; ++k) {
+        double cur[3] = {init_xyz[3 * k], init_xyz[3 * k + 1], init_xyz[3 * k + 2]};
+        for (int i = 0; i < 1000; ++i) orc_next_point(cfg->coef, cur);
+        double b[6] = {INFINITY, -INFINITY, INFINITY, -INFINITY, INFINITY, -INFINITY};
+        for (uint64_t it = 0; it < n; ++it) {
+            orc_next_point(cfg->coef, cur);
+            double s[3];
+            orc_mul_right(R, cur, s);
+            for (int c = 0; c < 3; ++c) {
+                if (s[c] < b[2 * c]) b[2 * c] = s[c];
+                if (s[c] > b[2 * c + 1]) b[2 * c + 1] = s[c];
+            }
+        }
+        int ok = isfinite(cur[0]) && isfinite(cur[1]) && isfinite(cur[2]);
+        for (int c = 0; c < 6; ++c) ok = ok && isfinite(b[c]);
+        if (!ok) { ++bad; continue; }
+        for (int c = 0; c < 3; ++c) {
+            if (b[2 * c] < box[2 * c]) box[2 * c] = b[2 * c];
+            if (b[2 * c + 1] > box[2 * c + 1]) box[2 * c + 1] = b[2 * c + 1];
+        }
+    }
+    if (diverged) *diverged = bad;
+}
+
 /* ---- start-point generator (same definition as include/sar.h) -------------- */
 static inline uint64_t splitmix64_at(uint64_t seed, uint64_t n)   /* n-th output of the stream */
 {

@@ -103,6 +103,11 @@ int orc_render_parallel(const sar_config *cfg, uint32_t n_threads, uint64_t jobs
  * warm-up: the known answer of lib.rs:329-333.  box = {xmin,xmax,ymin,ymax,zmin,zmax}. */
 void orc_screen_bbox(const sar_config *cfg, const double init[3], uint64_t n, double box[6]);
 
+/* The same over a list of start points (the auto-framing first pass of the TODO at lib.rs:326-334):
+ * union of the boxes of the trajectories that stay finite; *diverged counts the rest. */
+void orc_screen_bbox_jobs(const sar_config *cfg, const double *init_xyz, uint64_t n_jobs, uint64_t n,
+                          double box[6], uint64_t *diverged);
+
 /* Output conversion + raw containers (src/bin/main.rs:40-100 + the `image` 0.25 crate it calls, which is
  * third-party and not vendored: restated from its published source, parity unpinned).  fmt / container
  * are the SAR_PIX_* / SAR_FILE_* values of include/sar.h.  Returns the byte count (0: unsupported, as the

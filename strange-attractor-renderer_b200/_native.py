@@ -47,6 +47,13 @@ class SarConfig(C.Structure):
     ]
 
 
+class SarAutoframeResult(C.Structure):
+    """`sar_autoframe_result` of include/sar.h."""
+
+    _fields_ = [("box", C.c_double * 6), ("center_camera", C.c_double * 3), ("scale", C.c_double),
+                ("diverged", C.c_uint64), ("n_jobs", C.c_uint64)]
+
+
 class SarError(RuntimeError):
     """A non-zero sar_status.  (The reference panics at the same places: lib.rs:678, 709-710, 1024.)"""
 
@@ -69,6 +76,7 @@ SYMBOLS = {
     "sar_config_poisson_saturne": (C.c_int, [_cfgp]),
     "sar_config_solar_sail": (C.c_int, [_cfgp]),
     "sar_seed_points": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, _f64p]),
+    "sar_autoframe": (C.c_int, [_cfgp, C.c_int, C.c_uint64, _f64p, C.c_uint64, C.c_uint64, _P(SarAutoframeResult)]),
     "sar_runtime_new": (C.c_int, [C.c_uint32, C.c_uint32, C.c_int, _P(_vp)]),
     "sar_runtime_free": (None, [_vp]),
     "sar_runtime_reset": (C.c_int, [_vp]),

@@ -373,6 +373,42 @@ def render_parallel(renderer: ParallelRenderer, config, jobs_per_thread: int, se
     return out
 
 
+# ---- auto-framing first pass (the TODO at lib.rs:326-334) ----------------------------------
+@dataclass
+class AutoFrame:
+    """box = screen-space (R·p) xmin, xmax, ymin, ymax, zmin, zmax of the bounded trajectories — the
+    table of the comment at lib.rs:329-333; center_camera / scale = a View that centres and fits it."""
+
+    box: List[float]
+    center_camera: Vec3
+    scale: float
+    diverged: int
+    n_jobs: int
+
+    @property
+    def diverged_fraction(self) -> float:
+        return self.diverged / self.n_jobs if self.n_jobs else 0.0
+
+    def apply(self, config: "Config") -> "Config":
+        """config.view.center_camera / scale replaced by the derived ones (in place; returns config)."""
+        config.view.center_camera = Vec3(self.center_camera.x, self.center_camera.y, self.center_camera.z)
+        config.view.scale = self.scale
+        return config
+
+
+def autoframe(config, n_jobs: int = 4096, iterations: int = 20_000, seed: int = 0, initial_points=None, device: int = 0) -> AutoFrame:
+    """The first pass the reference's author asks for (lib.rs:326-334), on the GPU: bounding box of the
+    attractor in screen space from a batch of short trajectories, and the View values derived from it."""
+    c = _pod(config)
+    res = N.SarAutoframeResult()
+    pts_p = None
+    if initial_points is not None:
+        pts = np.ascontiguousarray(initial_points, dtype=np.float64).reshape(-1, 3)
+        n_jobs, pts_p = pts.shape[0], pts.ctypes.data_as(N._f64p)
+    N.check(N.lib().sar_autoframe(C.byref(c), device, seed & (2**64 - 1), pts_p, n_jobs, iterations, C.byref(res)))
+    return AutoFrame(list(res.box), Vec3(*res.center_camera), float(res.scale), int(res.diverged), int(res.n_jobs))
+
+
 # ---- output conversion + raw encoders (src/bin/main.rs:40-100) ---------------------------
 class PixelFormat(enum.Enum):
     """What write_image_matches converts the FinalImage to, by (transparent, 8bit) — main.rs:52-57."""

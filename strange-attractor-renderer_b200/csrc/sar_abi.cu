@@ -587,6 +587,79 @@ int sar_render_seeded(const sar_config *cfg, sar_runtime *rt, uint64_t seed, uin
     return SAR_OK;
 }
 
+// ---- auto-framing first pass (lib.rs:326-334) ----------------------------------------------------
+static double dkey_to_double(unsigned long long k)
+{
+    const unsigned long long b = (k >> 63) ? (k & 0x7FFFFFFFFFFFFFFFull) : ~k;
+    double v;
+    memcpy(&v, &b, sizeof v);
+    return v;
+}
+
+int sar_autoframe(const sar_config *cfg, int device, uint64_t seed, const double *init_xyz, uint64_t n_jobs, uint64_t iterations,
+                  sar_autoframe_result *out)
+{
+    if (!cfg || !out) return fail(SAR_ERR_INVALID, "NULL argument");
+    if (n_jobs == 0 || iterations == 0) return fail(SAR_ERR_INVALID, "n_jobs and iterations must be non-zero");
+    if (int rc = check_config(cfg, nullptr)) return rc;
+    int ndev = 0;
+    SAR_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(SAR_ERR_CUDA, "CUDA device %d not available (%d visible)", device, ndev);
+    SAR_CUDA(cudaSetDevice(device));
+    sar_runtime dummy;                                   // make_iter_params only reads the accumulator pointers (unused here)
+    sar_config c = *cfg;
+    c.iterations = iterations;
+    if (c.width == 0) c.width = 1;
+    if (c.height == 0) c.height = 1;
+    IterParams p;
+    make_iter_params(&c, &dummy, p);
+    BBoxAccum h;
+    for (int k = 0; k < 3; ++k) { h.lo[k] = ~0ull; h.hi[k] = 0ull; }
+    h.diverged = 0;
+    BBoxAccum *d_acc = nullptr;
+    double *d_init = nullptr;
+    cudaStream_t s = nullptr;
+    int rc = SAR_OK;
+    do {
+        if (cudaMalloc((void **)&d_acc, sizeof h) != cudaSuccess) { rc = fail(SAR_ERR_NOMEM, "cudaMalloc"); break; }
+        if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) { rc = fail(SAR_ERR_CUDA, "cudaStreamCreate"); break; }
+        if (cudaMemcpyAsync(d_acc, &h, sizeof h, cudaMemcpyHostToDevice, s) != cudaSuccess) { rc = fail(SAR_ERR_CUDA, "cudaMemcpy"); break; }
+        if (init_xyz) {
+            const size_t bytes = (size_t)n_jobs * 3 * sizeof(double);
+            if (cudaMalloc((void **)&d_init, bytes) != cudaSuccess) { rc = fail(SAR_ERR_NOMEM, "cudaMalloc(%zu)", bytes); break; }
+            if (cudaMemcpyAsync(d_init, init_xyz, bytes, cudaMemcpyHostToDevice, s) != cudaSuccess) { rc = fail(SAR_ERR_CUDA, "cudaMemcpy"); break; }
+        }
+        p.init = d_init; p.seed = seed; p.first_job = 0; p.n_jobs = n_jobs;
+        launch_bbox(p, d_acc, s);
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&h, d_acc, sizeof h, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) { rc = fail(SAR_ERR_CUDA, "autoframe: %s", cudaGetErrorString(e)); break; }
+    } while (0);
+    cudaFree(d_acc); cudaFree(d_init);
+    if (s) cudaStreamDestroy(s);
+    (void)cudaGetLastError();
+    if (rc) return rc;
+    memset(out, 0, sizeof *out);
+    out->n_jobs = n_jobs; out->diverged = h.diverged;
+    if (h.diverged == n_jobs) return SAR_OK;             // nothing bounded: box stays 0, caller sees diverged == n_jobs
+    for (int k = 0; k < 3; ++k) { out->box[2 * k] = dkey_to_double(h.lo[k]); out->box[2 * k + 1] = dkey_to_double(h.hi[k]); }
+    // center_camera is ADDED to screen_space before projecting, x with x, y with screen z, z with screen y
+    // (lib.rs:776-786): centring means minus the mid-points, paired that way (cf. the values at lib.rs:335-340)
+    out->center_camera[0] = -(out->box[0] + out->box[1]) / 2.;
+    out->center_camera[1] = -(out->box[4] + out->box[5]) / 2.;
+    out->center_camera[2] = -(out->box[2] + out->box[3]) / 2.;
+    // largest scale that keeps the box in view from EVERY view angle (the view rotates about the vertical axis through
+    // the centre, lib.rs:776-779): horizontal |x2| < 0.5/scale (lib.rs:783), vertical |y| < height/(2 width scale) (lib.rs:786)
+    const double rx = std::hypot((out->box[1] - out->box[0]) / 2., (out->box[5] - out->box[4]) / 2.);
+    const double ry = (out->box[3] - out->box[2]) / 2.;
+    const double aspect = (double)c.height / (double)c.width;
+    double sc = rx > 0. ? 0.5 / rx : INFINITY;
+    if (ry > 0. && 0.5 * aspect / ry < sc) sc = 0.5 * aspect / ry;
+    out->scale = std::isfinite(sc) ? 0.95 * sc : 1.0;
+    return SAR_OK;
+}
+
 // ---- max / colorize ----------------------------------------------------------------------------
 int sar_runtime_max_async(sar_runtime *rt, uint32_t row0, uint32_t rows, void *stream)
 {

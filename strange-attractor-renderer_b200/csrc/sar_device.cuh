@@ -126,6 +126,11 @@ enum { ORDER_NATIVE = 0, ORDER_BIG_ENDIAN = 1, ORDER_BMP = 2 };
 void launch_convert(const uint16_t *rgba, uint8_t *out, unsigned int W, unsigned int H, unsigned int fmt, unsigned int order,
                     size_t row_stride, cudaStream_t s);
 
+// auto-framing first pass (lib.rs:326-334): screen-space bounding box as order-preserving u64 keys
+// (key(v) = bits ^ sign-fill, so unsigned min/max = f64 min/max); lo starts at ~0, hi at 0
+struct BBoxAccum { unsigned long long lo[3], hi[3], diverged; };
+void launch_bbox(const IterParams &p, BBoxAccum *acc, cudaStream_t s);
+
 // launchers (sar_kernels.cu); every one bumps the launch counter
 void launch_reset(unsigned long long *fast, ulonglong2 *rec, Scalars *scal, size_t npix, size_t nslots, cudaStream_t s);
 void launch_iterate(const IterParams &p, unsigned int lanes, cudaStream_t s);

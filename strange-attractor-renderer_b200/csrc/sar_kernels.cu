@@ -8,6 +8,7 @@
 #include "sar_device.cuh"
 
 #include <atomic>
+#include <math_constants.h>
 #include <type_traits>
 
 #ifndef SAR_DEFAULT_NT
@@ -412,6 +413,73 @@ void launch_warm(const IterParams &p, double *out, cudaStream_t s)
 }
 
 // Lanes per thread (NT): a tuning knob that never changes results.
+// ---------------------------------------------------------------------------------------------
+// Auto-framing first pass — the reference author's TODO at lib.rs:326-334: "Add option to make
+// first-pass to get these values [the attractor's extent in screen space], to then compute
+// center_camera".  One lane per trajectory: start point, warm-up, then `iterations` steps whose
+// screen_space = R·p (lib.rs:773) is folded into a per-lane bounding box.  A trajectory that
+// diverged (non-finite state — absorbing for this map) is left out and counted.
+// The fold is exact (min/max only), so the box equals the oracle's bit for bit.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long dkey_of(double v)      // order-preserving f64 -> u64
+{
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__global__ void __launch_bounds__(128)
+bbox_kernel(const __grid_constant__ IterParams P, BBoxAccum *acc)
+{
+    const unsigned long long job = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    double lo[3] = {CUDART_INF, CUDART_INF, CUDART_INF}, hi[3] = {-CUDART_INF, -CUDART_INF, -CUDART_INF};
+    bool ok = false;
+    if (job < P.n_jobs) {
+        double x, y, z;
+        if (P.init != nullptr) {
+            x = P.init[3 * job + 0]; y = P.init[3 * job + 1]; z = P.init[3 * job + 2];
+        } else {
+            const unsigned long long g = 3ull * (P.first_job + job);
+            x = seed_coord(P.seed, g); y = seed_coord(P.seed, g + 1); z = seed_coord(P.seed, g + 2);
+        }
+        for (unsigned int w = 0; w < P.warmup; ++w) {                         // lib.rs:750-752
+            double nx, ny, nz;
+            SAR_NEXT_POINT(P, x, y, z, nx, ny, nz);
+            x = nx; y = ny; z = nz;
+        }
+        for (unsigned long long it = 0; it < P.iterations; ++it) {
+            double nx, ny, nz;
+            SAR_NEXT_POINT(P, x, y, z, nx, ny, nz);
+            x = nx; y = ny; z = nz;
+            const double s[3] = {
+                __dadd_rn(__dadd_rn(__dmul_rn(P.m[0][0], nx), __dmul_rn(P.m[0][1], ny)), __dmul_rn(P.m[0][2], nz)),
+                __dadd_rn(__dadd_rn(__dmul_rn(P.m[1][0], nx), __dmul_rn(P.m[1][1], ny)), __dmul_rn(P.m[1][2], nz)),
+                __dadd_rn(__dadd_rn(__dmul_rn(P.m[2][0], nx), __dmul_rn(P.m[2][1], ny)), __dmul_rn(P.m[2][2], nz))};
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                if (s[c] < lo[c]) lo[c] = s[c];
+                if (s[c] > hi[c]) hi[c] = s[c];
+            }
+        }
+        ok = isfinite(x) && isfinite(y) && isfinite(z) && isfinite(lo[0]) && isfinite(hi[0]) && isfinite(lo[1]) && isfinite(hi[1])
+             && isfinite(lo[2]) && isfinite(hi[2]);
+        if (!ok) atomicAdd(&acc->diverged, 1ull);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        unsigned long long kl = ok ? dkey_of(lo[c]) : ~0ull, kh = ok ? dkey_of(hi[c]) : 0ull;
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long a = __shfl_xor_sync(0xffffffffu, kl, o), b = __shfl_xor_sync(0xffffffffu, kh, o);
+            kl = a < kl ? a : kl; kh = b > kh ? b : kh;
+        }
+        if ((threadIdx.x & 31) == 0) { atomicMin(&acc->lo[c], kl); atomicMax(&acc->hi[c], kh); }
+    }
+}
+void launch_bbox(const IterParams &p, BBoxAccum *acc, cudaStream_t s)
+{
+    if (p.n_jobs == 0) return;
+    bbox_kernel<<<(unsigned int)((p.n_jobs + 127) / 128), 128, 0, s>>>(p, acc);
+    ++g_launches;
+}
+
 static std::atomic<int> g_nt{SAR_DEFAULT_NT};
 bool set_traj_per_thread(int nt)
 {
