@@ -50,7 +50,7 @@
 extern "C" {
 #endif
 
-#define SAR_ABI_VERSION 1u
+#define SAR_ABI_VERSION 2u
 #define SAR_MAX_PALETTE 16u        /* palette entries carried across the boundary */
 #define SAR_WARMUP_ITERATIONS 1000u /* lib.rs:750 */
 
@@ -65,8 +65,21 @@ typedef enum sar_status {
 
 /* config::RenderKind, lib.rs:234-239 */
 enum { SAR_RENDER_GAS = 0, SAR_RENDER_DEPTH = 1 };
-/* the two shipped ColorTransform instantiations, lib.rs:503-559 */
-enum { SAR_CT_POISSON_SATURNE = 0, SAR_CT_ADJUSTED_VELOCITY = 1 };
+/* ColorTransform kinds (lib.rs:241-249).  0 and 1 are the two instantiations the
+ * reference ships (lib.rs:503-559).  2 = ScreenBlend, a device form of the
+ * closures the trait also accepts (lib.rs:245), built from exact operations only:
+ *   value = ((((s.x*w0) + s.y*w1) + s.z*w2) + |delta|*w3 + ct_offset) * ct_factor
+ * with s = screen_space, w = ct_weights, evaluated left to right, no FMA. */
+enum { SAR_CT_POISSON_SATURNE = 0, SAR_CT_ADJUSTED_VELOCITY = 1, SAR_CT_SCREEN_BLEND = 2 };
+/* Attractor kinds (lib.rs:71-77; README.md:8 "Adding more should be relatively
+ * easy").  0 = PolynomialSprott2Degree, the one the reference ships
+ * (lib.rs:575-620).  1 = PolynomialSprott3Degree, the cubic member of the same
+ * family: each coordinate continues the serial sum of lib.rs:588-600 with ten
+ * more terms, coef3[k][0..9] times [x³, x²y, x²z, xy², xyz, xz², y³, y²z, yz², z³],
+ * every cubic monomial formed as (quadratic monomial)*(variable): x³ = (x*x)*x,
+ * x²y = (x*x)*y, x²z = (x*x)*z, xy² = (x*y)*y, xyz = (x*y)*z, xz² = (x*z)*z,
+ * y³ = (y*y)*y, y²z = (y*y)*z, yz² = (y*z)*z, z³ = (z*z)*z. */
+enum { SAR_ATTRACTOR_SPROTT2 = 0, SAR_ATTRACTOR_SPROTT3 = 1 };
 
 /* Config<PolynomialSprott2Degree, {Function|AdjustedVelocity}>, lib.rs:265-287,
  * flattened with Colors (lib.rs:475-479), Palette (lib.rs:408-411),
@@ -89,10 +102,12 @@ typedef struct sar_config {
     double   ct_offset;                  /* AdjustedVelocity.offset, lib.rs:508 */
     double   ct_factor;                  /* AdjustedVelocity.factor, lib.rs:509 */
     uint32_t palette_len;                /* Palette::count(), lib.rs:435; 1..SAR_MAX_PALETTE */
-    uint32_t reserved0;
+    uint32_t attractor_kind;             /* SAR_ATTRACTOR_* (0 = the reference's PolynomialSprott2Degree) */
     double   palette_rgb[SAR_MAX_PALETTE][3]; /* Palette list WITHOUT the duplicated sentinel of lib.rs:418 */
     double   bright_offset;              /* colors.brighness.offset, lib.rs:394 */
     double   bright_factor;              /* colors.brighness.factor, lib.rs:395 */
+    double   coef3[3][10];               /* cubic coefficients, SAR_ATTRACTOR_SPROTT3 only */
+    double   ct_weights[4];              /* SAR_CT_SCREEN_BLEND only */
 } sar_config;
 
 typedef struct sar_runtime  sar_runtime;   /* Runtime, lib.rs:631-646 (device resident) */

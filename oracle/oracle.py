@@ -37,10 +37,12 @@ class SarConfig(C.Structure):
         ("ct_offset", C.c_double),
         ("ct_factor", C.c_double),
         ("palette_len", C.c_uint32),
-        ("reserved0", C.c_uint32),
+        ("attractor_kind", C.c_uint32),
         ("palette_rgb", (C.c_double * 3) * SAR_MAX_PALETTE),
         ("bright_offset", C.c_double),
         ("bright_factor", C.c_double),
+        ("coef3", (C.c_double * 10) * 3),
+        ("ct_weights", C.c_double * 4),
     ]
 
     def copy(self) -> "SarConfig":
@@ -90,6 +92,8 @@ def lib() -> C.CDLL:
         P = C.POINTER
         dp = P(C.c_double)
         L.orc_next_point.argtypes = [P((C.c_double * 10) * 3), dp]
+        L.orc_next_point_cfg.argtypes = [P(SarConfig), dp]
+        L.orc_next_point_cfg.restype = None
         L.orc_rotation_matrix.argtypes = [dp, C.c_double, dp]
         L.orc_mul_right.argtypes = [dp, dp, dp]
         L.orc_color_transform.argtypes = [P(SarConfig), dp, dp]
@@ -154,7 +158,7 @@ def seed_points(seed: int, first: int, n: int) -> np.ndarray:
 
 def next_point(cfg: SarConfig, p) -> np.ndarray:
     q = np.array(p, dtype=np.float64)
-    lib().orc_next_point(C.byref(cfg.coef), _dp(q))
+    lib().orc_next_point_cfg(C.byref(cfg), _dp(q))
     return q
 
 

@@ -48,6 +48,25 @@ void orc_next_point(const double coef[3][10], double p[3])
     p[2] = sum_coefficients(m, coef[2]);
 }
 
+/* Attractor kinds of include/sar.h.  Kind 0 is the reference's only Attractor impl (above).  Kind 1,
+ * PolynomialSprott3Degree, is this repository's extension "behind the same trait" (lib.rs:71-77,
+ * README.md:8): the same serial sum continued with ten cubic terms — defined here and in include/sar.h,
+ * there is no reference code to follow for it. */
+void orc_next_point_cfg(const sar_config *cfg, double p[3])
+{
+    if (cfg->attractor_kind != SAR_ATTRACTOR_SPROTT3) { orc_next_point(cfg->coef, p); return; }
+    const double x = p[0], y = p[1], z = p[2];
+    const double xx = x * x, xy = x * y, xz = x * z, yy = y * y, yz = y * z, zz = z * z;
+    const double m[20] = {1., x, xx, xy, xz, y, yy, yz, z, zz,
+                          xx * x, xx * y, xx * z, xy * y, xy * z, xz * z, yy * y, yy * z, yz * z, zz * z};
+    for (int k = 0; k < 3; ++k) {
+        double sum = 0.;
+        for (int i = 0; i < 10; ++i) sum += m[i] * cfg->coef[k][i];
+        for (int i = 0; i < 10; ++i) sum += m[10 + i] * cfg->coef3[k][i];
+        p[k] = sum;
+    }
+}
+
 /* ---- EulerAxisRotation::to_rotation_matrix, lib.rs:179-195 (release) ------ */
 void orc_rotation_matrix(const double axis[3], double rotation, double m[3][3])
 {
@@ -79,6 +98,13 @@ double orc_color_transform(const sar_config *cfg, const double delta[3], const d
 {
     if (cfg->ct_kind == SAR_CT_ADJUSTED_VELOCITY)
         return (magnitude(delta) + cfg->ct_offset) * cfg->ct_factor;      /* lib.rs:514 */
+    if (cfg->ct_kind == SAR_CT_SCREEN_BLEND) {   /* include/sar.h: a closure-style ColorTransform (lib.rs:245), left to right */
+        double t = p[0] * cfg->ct_weights[0];
+        t = t + p[1] * cfg->ct_weights[1];
+        t = t + p[2] * cfg->ct_weights[2];
+        t = t + magnitude(delta) * cfg->ct_weights[3];
+        return (t + cfg->ct_offset) * cfg->ct_factor;
+    }
 
     /* poisson_saturne: cos/sin(91π/360) as literals, lib.rs:529-536 */
     static const double COS = 0.7009092642998508981833083453238941729068756103515625;
@@ -158,7 +184,7 @@ int orc_runtime_merge(orc_runtime *a, const orc_runtime *b)   /* lib.rs:708-738 
 void orc_render(const sar_config *cfg, orc_runtime *rt, const double init[3], orc_stats *st)
 {
     double cur[3] = {init[0], init[1], init[2]};               /* lib.rs:748 (value injected) */
-    for (int i = 0; i < 1000; ++i) orc_next_point(cfg->coef, cur);   /* lib.rs:750-752 */
+    for (int i = 0; i < 1000; ++i) orc_next_point_cfg(cfg, cur);   /* lib.rs:750-752 */
 
     double R[3][3];
     orc_rotation_matrix(cfg->axis, cfg->rotation, R);          /* lib.rs:755 */
@@ -175,7 +201,7 @@ void orc_render(const sar_config *cfg, orc_runtime *rt, const double init[3], or
     uint64_t recorded = 0, wins = 0, nans = 0, ties = 0;
 
     for (uint64_t it = 0; it < cfg->iterations; ++it) {        /* lib.rs:769 */
-        orc_next_point(cfg->coef, cur);                        /* lib.rs:770 */
+        orc_next_point_cfg(cfg, cur);                        /* lib.rs:770 */
         double s[3];
         orc_mul_right(R, cur, s);                              /* lib.rs:773 */
         const double x2 = (s[0] + ccx) * cos_v + (s[2] + ccy) * sin_v;   /* lib.rs:776-777 */
@@ -422,13 +448,13 @@ int orc_render_parallel(const sar_config *cfg_in, uint32_t n_threads, uint64_t j
 void orc_screen_bbox(const sar_config *cfg, const double init[3], uint64_t n, double box[6])
 {
     double cur[3] = {init[0], init[1], init[2]};
-    for (int i = 0; i < 1000; ++i) orc_next_point(cfg->coef, cur);
+    for (int i = 0; i < 1000; ++i) orc_next_point_cfg(cfg, cur);
     double R[3][3];
     orc_rotation_matrix(cfg->axis, cfg->rotation, R);
     box[0] = box[2] = box[4] = INFINITY;
     box[1] = box[3] = box[5] = -INFINITY;
     for (uint64_t it = 0; it < n; ++it) {
-        orc_next_point(cfg->coef, cur);
+        orc_next_point_cfg(cfg, cur);
         double s[3];
         orc_mul_right(R, cur, s);
         for (int c = 0; c < 3; ++c) {
@@ -450,10 +476,10 @@ void orc_screen_bbox_jobs(const sar_config *cfg, const double *init_xyz, uint64_
     orc_rotation_matrix(cfg->axis, cfg->rotation, R);
     for (uint64_t k = 0; k < n_jobs; ++k) {
         double cur[3] = {init_xyz[3 * k], init_xyz[3 * k + 1], init_xyz[3 * k + 2]};
-        for (int i = 0; i < 1000; ++i) orc_next_point(cfg->coef, cur);
+        for (int i = 0; i < 1000; ++i) orc_next_point_cfg(cfg, cur);
         double b[6] = {INFINITY, -INFINITY, INFINITY, -INFINITY, INFINITY, -INFINITY};
         for (uint64_t it = 0; it < n; ++it) {
-            orc_next_point(cfg->coef, cur);
+            orc_next_point_cfg(cfg, cur);
             double s[3];
             orc_mul_right(R, cur, s);
             for (int c = 0; c < 3; ++c) {

@@ -59,6 +59,8 @@ typedef struct orc_stats {
 
 /* PolynomialSprott2Degree::next_point, lib.rs:585-620 (in place). */
 void orc_next_point(const double coef[3][10], double p[3]);
+/* next_point of cfg->attractor_kind (0: the above; 1: the cubic extension defined in include/sar.h). */
+void orc_next_point_cfg(const sar_config *cfg, double p[3]);
 /* EulerAxisRotation::to_rotation_matrix, lib.rs:179-195, release semantics. */
 void orc_rotation_matrix(const double axis[3], double rotation, double m[3][3]);
 /* Matrix3x3::mul_right, lib.rs:208-215. */

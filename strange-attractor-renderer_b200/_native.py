@@ -12,7 +12,8 @@ SAR_MAX_PALETTE = 16
 SAR_IPC_HANDLE_BYTES = 64
 SAR_OK, SAR_ERR_INVALID, SAR_ERR_DIMS, SAR_ERR_CUDA, SAR_ERR_NOMEM, SAR_ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 SAR_RENDER_GAS, SAR_RENDER_DEPTH = 0, 1
-SAR_CT_POISSON_SATURNE, SAR_CT_ADJUSTED_VELOCITY = 0, 1
+SAR_CT_POISSON_SATURNE, SAR_CT_ADJUSTED_VELOCITY, SAR_CT_SCREEN_BLEND = 0, 1, 2
+SAR_ATTRACTOR_SPROTT2, SAR_ATTRACTOR_SPROTT3 = 0, 1
 SAR_SEQ_SHARED_POINTS = 1
 SAR_PIX_RGBA16, SAR_PIX_RGB16, SAR_PIX_RGBA8, SAR_PIX_RGB8 = 0, 1, 2, 3
 SAR_FILE_RAW, SAR_FILE_PAM, SAR_FILE_BMP = 0, 1, 2
@@ -40,10 +41,12 @@ class SarConfig(C.Structure):
         ("ct_offset", C.c_double),
         ("ct_factor", C.c_double),
         ("palette_len", C.c_uint32),
-        ("reserved0", C.c_uint32),
+        ("attractor_kind", C.c_uint32),
         ("palette_rgb", (C.c_double * 3) * SAR_MAX_PALETTE),
         ("bright_offset", C.c_double),
         ("bright_factor", C.c_double),
+        ("coef3", (C.c_double * 10) * 3),
+        ("ct_weights", C.c_double * 4),
     ]
 
 
@@ -142,8 +145,8 @@ def lib() -> C.CDLL:
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(L, name)  # AttributeError = ABI mismatch, loud by design
             fn.restype, fn.argtypes = res, args
-        if L.sar_abi_version() != 1:
-            raise RuntimeError(f"libsar_b200.so ABI {L.sar_abi_version()} != 1")
+        if L.sar_abi_version() != 2:
+            raise RuntimeError(f"libsar_b200.so ABI {L.sar_abi_version()} != 2")
         _lib = L
     return _lib
 

@@ -111,11 +111,34 @@ class attractors:  # namespace, lib.rs:567
         z: List[float]
 
 
+    @dataclass
+    class PolynomialSprott3Degree:
+        """The cubic member of the family (include/sar.h: SAR_ATTRACTOR_SPROTT3) — an Attractor the
+        reference does not ship (README.md:8).  x/y/z: the 10 quadratic coefficients in the reference's
+        order; x3/y3/z3: those of [x³, x²y, x²z, xy², xyz, xz², y³, y²z, yz², z³]."""
+
+        x: List[float]
+        y: List[float]
+        z: List[float]
+        x3: List[float]
+        y3: List[float]
+        z3: List[float]
+
+
 class color_transforms:  # namespace, lib.rs:498
     @dataclass
     class AdjustedVelocity:
         offset: float
         factor: float
+
+    @dataclass
+    class ScreenBlend:
+        """A device form of the closures ColorTransform also accepts (lib.rs:245; include/sar.h:
+        SAR_CT_SCREEN_BLEND): ((s.x*w0 + s.y*w1 + s.z*w2 + |delta|*w3) + offset) * factor."""
+
+        weights: List[float]
+        offset: float = 0.0
+        factor: float = 1.0
 
     class _PoissonSaturne:
         """Marker for the fn item `color_transforms::poisson_saturne` (lib.rs:520)."""
@@ -148,10 +171,15 @@ class Config:
 
     @staticmethod
     def _from_pod(c: SarConfig) -> "Config":
-        att = attractors.PolynomialSprott2Degree(list(c.coef[0]), list(c.coef[1]), list(c.coef[2]))
+        if c.attractor_kind == N.SAR_ATTRACTOR_SPROTT3:
+            att = attractors.PolynomialSprott3Degree(list(c.coef[0]), list(c.coef[1]), list(c.coef[2]),
+                                                     list(c.coef3[0]), list(c.coef3[1]), list(c.coef3[2]))
+        else:
+            att = attractors.PolynomialSprott2Degree(list(c.coef[0]), list(c.coef[1]), list(c.coef[2]))
         view = View(Vec3(*c.center_camera), EulerAxisRotation(Vec3(*c.axis), c.rotation), c.scale)
         ct = (color_transforms.poisson_saturne if c.ct_kind == N.SAR_CT_POISSON_SATURNE
-              else color_transforms.AdjustedVelocity(offset=c.ct_offset, factor=c.ct_factor))
+              else color_transforms.AdjustedVelocity(offset=c.ct_offset, factor=c.ct_factor) if c.ct_kind == N.SAR_CT_ADJUSTED_VELOCITY
+              else color_transforms.ScreenBlend(list(c.ct_weights), offset=c.ct_offset, factor=c.ct_factor))
         pal = Palette([tuple(c.palette_rgb[i]) for i in range(c.palette_len)])
         return Config(att, view, ct, iterations=c.iterations, width=c.width, height=c.height,
                       render=RenderKind(c.render_kind), transparent=bool(c.transparent), angle=c.angle,
@@ -177,8 +205,15 @@ class Config:
         c.render_kind = self.render.value
         c.transparent, c.silent, c.angle = int(bool(self.transparent)), int(bool(self.silent)), float(self.angle)
         a = self.attractor
-        if not isinstance(a, attractors.PolynomialSprott2Degree):
-            raise SarError(N.SAR_ERR_UNSUPPORTED, "only PolynomialSprott2Degree has a device implementation")
+        if isinstance(a, attractors.PolynomialSprott3Degree):
+            c.attractor_kind = N.SAR_ATTRACTOR_SPROTT3
+            for k, lst in enumerate((a.x3, a.y3, a.z3)):
+                if len(lst) != 10:
+                    raise SarError(N.SAR_ERR_INVALID, "cubic coefficient lists have 10 entries (include/sar.h)")
+                for i, v in enumerate(lst):
+                    c.coef3[k][i] = float(v)
+        elif not isinstance(a, attractors.PolynomialSprott2Degree):
+            raise SarError(N.SAR_ERR_UNSUPPORTED, "only PolynomialSprott2Degree / PolynomialSprott3Degree have a device implementation")
         for k, lst in enumerate((a.x, a.y, a.z)):
             if len(lst) != 10:
                 raise SarError(N.SAR_ERR_INVALID, "coefficient lists have 10 entries (lib.rs:577-579)")
@@ -191,11 +226,16 @@ class Config:
         t = self.color_transform
         if isinstance(t, color_transforms.AdjustedVelocity):
             c.ct_kind, c.ct_offset, c.ct_factor = N.SAR_CT_ADJUSTED_VELOCITY, float(t.offset), float(t.factor)
+        elif isinstance(t, color_transforms.ScreenBlend):
+            if len(t.weights) != 4:
+                raise SarError(N.SAR_ERR_INVALID, "ScreenBlend takes 4 weights (include/sar.h)")
+            c.ct_kind, c.ct_offset, c.ct_factor = N.SAR_CT_SCREEN_BLEND, float(t.offset), float(t.factor)
+            c.ct_weights[:] = [float(v) for v in t.weights]
         elif t is color_transforms.poisson_saturne:
             c.ct_kind = N.SAR_CT_POISSON_SATURNE
         else:
             raise SarError(N.SAR_ERR_UNSUPPORTED,
-                           "only color_transforms.poisson_saturne and AdjustedVelocity have a device implementation")
+                           "only color_transforms.poisson_saturne, AdjustedVelocity and ScreenBlend have a device implementation")
         pal = self.colors.palette
         c.palette_len = pal.count()
         for i, rgb in enumerate(pal.list):

@@ -147,8 +147,10 @@ static int check_config(const sar_config *cfg, const sar_runtime *rt)
     if (!cfg) return fail(SAR_ERR_INVALID, "cfg is NULL");
     if (cfg->palette_len == 0 || cfg->palette_len > SAR_MAX_PALETTE)   // Palette::new panics on an empty list, lib.rs:415-418
         return fail(SAR_ERR_INVALID, "palette_len must be in 1..%u (got %u)", SAR_MAX_PALETTE, cfg->palette_len);
-    if (cfg->ct_kind > SAR_CT_ADJUSTED_VELOCITY)
+    if (cfg->ct_kind > SAR_CT_SCREEN_BLEND)
         return fail(SAR_ERR_UNSUPPORTED, "ct_kind %u has no device implementation", cfg->ct_kind);
+    if (cfg->attractor_kind > SAR_ATTRACTOR_SPROTT3)
+        return fail(SAR_ERR_UNSUPPORTED, "attractor_kind %u has no device implementation", cfg->attractor_kind);
     if (cfg->render_kind > SAR_RENDER_DEPTH) return fail(SAR_ERR_INVALID, "render_kind %u", cfg->render_kind);
     if (rt && (cfg->width != rt->w || cfg->height != rt->h))
         return fail(SAR_ERR_DIMS, "config is %ux%u but runtime is %ux%u", cfg->width, cfg->height, rt->w, rt->h);
@@ -207,6 +209,9 @@ static void make_iter_params(const sar_config *cfg, sar_runtime *rt, IterParams 
     p.sam = 0.5 / cfg->scale;                                                    // lib.rs:764
     p.half_h = height / 2.;                                                      // lib.rs:786
     p.ct_offset = cfg->ct_offset; p.ct_factor = cfg->ct_factor;
+    for (int i = 0; i < 4; ++i) p.ct_w[i] = cfg->ct_weights[i];
+    for (int k = 0; k < 3; ++k) for (int i = 0; i < 10; ++i) p.c3[k][i] = cfg->coef3[k][i];
+    p.attractor_kind = cfg->attractor_kind;
     p.fast = rt->fast; p.rec = rt->rec; p.scal = rt->scal;
     p.W = cfg->width; p.H = cfg->height; p.ct_kind = cfg->ct_kind;
     p.slots = rt->slots;
@@ -301,7 +306,7 @@ int sar_config_defaults(sar_config *c)
     c->transparent = 1;                   // lib.rs:296
     c->angle = 0.0;                       // lib.rs:297
     c->silent = 1;                        // lib.rs:299
-    c->palette_len = 6; c->reserved0 = 0;
+    c->palette_len = 6;
     const double r[6] = {1., 0.5, 1., 0.5, 0.5, 1.}, g[6] = {1., 1., 0.5, 1., 0.5, 0.5}, b[6] = {0.5, 0.5, 0.5, 1., 1., 1.};  // lib.rs:483-487
     memset(c->palette_rgb, 0, sizeof c->palette_rgb);
     for (int i = 0; i < 6; ++i) { c->palette_rgb[i][0] = r[i]; c->palette_rgb[i][1] = g[i]; c->palette_rgb[i][2] = b[i]; }

@@ -88,7 +88,9 @@ struct IterParams {                   // everything the iterate kernel reads; li
     double ccx, ccy, ccz;             // center_camera (lib.rs:758)
     double cv, sv;                    // cos/sin(angle) (lib.rs:756-757), host computed
     double sam, ws, half_h;           // scale_adjusted_mid, width_scaled, height/2 (lib.rs:763-764, 786)
-    double ct_offset, ct_factor;      // AdjustedVelocity (lib.rs:507-510)
+    double ct_offset, ct_factor;      // AdjustedVelocity (lib.rs:507-510); also ScreenBlend
+    double ct_w[4];                   // ScreenBlend weights (include/sar.h)
+    double c3[3][10];                 // cubic coefficients of attractor kind 1 (include/sar.h)
     unsigned long long *fast;
     ulonglong2 *rec;
     Scalars *scal;
@@ -100,6 +102,7 @@ struct IterParams {                   // everything the iterate kernel reads; li
     unsigned int job_key0;            // order key of job 0 (Runtime job counter)
     unsigned int W, H;
     unsigned int ct_kind;
+    unsigned int attractor_kind;
     SlotMap slots;                    // pixel -> slot map of the fast array
     unsigned int warmup;              // unrecorded steps before the recorded ones: 1000 (lib.rs:750), or 0 when `init` holds warmed states
 };

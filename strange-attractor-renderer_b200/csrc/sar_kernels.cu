@@ -98,14 +98,49 @@ __device__ __forceinline__ double sprott_sum(const double (&c)[10], double x, do
     s = __dadd_rn(s, __dmul_rn(zz, c[9]));
     return s;
 }
-#define SAR_NEXT_POINT(P, x, y, z, nx, ny, nz)                                       \
-    {                                                                                \
-        const double xx_ = __dmul_rn(x, x), xy_ = __dmul_rn(x, y), xz_ = __dmul_rn(x, z); \
-        const double yy_ = __dmul_rn(y, y), yz_ = __dmul_rn(y, z), zz_ = __dmul_rn(z, z); \
-        nx = sprott_sum(P.c[0], x, y, z, xx_, xy_, xz_, yy_, yz_, zz_);              \
-        ny = sprott_sum(P.c[1], x, y, z, xx_, xy_, xz_, yy_, yz_, zz_);              \
-        nz = sprott_sum(P.c[2], x, y, z, xx_, xy_, xz_, yy_, yz_, zz_);              \
+// The ten cubic monomials of AK 1 continue the same serial sum (see next_point<AK>).
+__device__ __forceinline__ double cubic_tail(double s, const double (&c)[10], double xxx, double xxy, double xxz, double xyy,
+                                             double xyz, double xzz, double yyy, double yyz, double yzz, double zzz)
+{
+    s = __dadd_rn(s, __dmul_rn(xxx, c[0]));
+    s = __dadd_rn(s, __dmul_rn(xxy, c[1]));
+    s = __dadd_rn(s, __dmul_rn(xxz, c[2]));
+    s = __dadd_rn(s, __dmul_rn(xyy, c[3]));
+    s = __dadd_rn(s, __dmul_rn(xyz, c[4]));
+    s = __dadd_rn(s, __dmul_rn(xzz, c[5]));
+    s = __dadd_rn(s, __dmul_rn(yyy, c[6]));
+    s = __dadd_rn(s, __dmul_rn(yyz, c[7]));
+    s = __dadd_rn(s, __dmul_rn(yzz, c[8]));
+    s = __dadd_rn(s, __dmul_rn(zzz, c[9]));
+    return s;
+}
+// Attractor::next_point (lib.rs:71-77) for the attractor kinds behind sar_config.attractor_kind:
+//   AK 0  PolynomialSprott2Degree (lib.rs:575-620): 3 x 10 coefficients over [1,x,x²,xy,xz,y,y²,yz,z,z²]
+//   AK 1  PolynomialSprott3Degree (the cubic member of the same family, README.md:8 "Adding more should
+//         be relatively easy"): the ten cubic monomials [x³,x²y,x²z,xy²,xyz,xz²,y³,y²z,yz²,z³] — each
+//         formed as (quadratic monomial)·(variable) — appended to the same left-to-right sum.
+template <int AK>
+__device__ __forceinline__ void next_point(const IterParams &P, double x, double y, double z, double &nx, double &ny, double &nz)
+{
+    const double xx = __dmul_rn(x, x), xy = __dmul_rn(x, y), xz = __dmul_rn(x, z);
+    const double yy = __dmul_rn(y, y), yz = __dmul_rn(y, z), zz = __dmul_rn(z, z);
+    nx = sprott_sum(P.c[0], x, y, z, xx, xy, xz, yy, yz, zz);
+    ny = sprott_sum(P.c[1], x, y, z, xx, xy, xz, yy, yz, zz);
+    nz = sprott_sum(P.c[2], x, y, z, xx, xy, xz, yy, yz, zz);
+    if (AK == 1) {
+        const double xxx = __dmul_rn(xx, x), xxy = __dmul_rn(xx, y), xxz = __dmul_rn(xx, z), xyy = __dmul_rn(xy, y), xyz = __dmul_rn(xy, z);
+        const double xzz = __dmul_rn(xz, z), yyy = __dmul_rn(yy, y), yyz = __dmul_rn(yy, z), yzz = __dmul_rn(yz, z), zzz = __dmul_rn(zz, z);
+        nx = cubic_tail(nx, P.c3[0], xxx, xxy, xxz, xyy, xyz, xzz, yyy, yyz, yzz, zzz);
+        ny = cubic_tail(ny, P.c3[1], xxx, xxy, xxz, xyy, xyz, xzz, yyy, yyz, yzz, zzz);
+        nz = cubic_tail(nz, P.c3[2], xxx, xxy, xxz, xyy, xyz, xzz, yyy, yyz, yzz, zzz);
     }
+}
+// for the kernels off the hot path (warm-up, auto-framing): one uniform branch per step
+__device__ __forceinline__ void next_point_any(const IterParams &P, double x, double y, double z, double &nx, double &ny, double &nz)
+{
+    if (P.attractor_kind == 1u) next_point<1>(P, x, y, z, nx, ny, nz);
+    else next_point<0>(P, x, y, z, nx, ny, nz);
+}
 
 // Vec3::magnitude (lib.rs:129-131)
 __device__ __forceinline__ double magnitude(double x, double y, double z)
@@ -120,6 +155,13 @@ __device__ __forceinline__ double transform_ds(const IterParams &P, double dx, d
 {
     const double mag = magnitude(dx, dy, dz);
     if (P.ct_kind == 1u) return __dmul_rn(__dadd_rn(mag, P.ct_offset), P.ct_factor);   // AdjustedVelocity, lib.rs:514
+    if (P.ct_kind == 2u) {                                                               // ScreenBlend (include/sar.h): a ColorTransform
+        double t = __dmul_rn(sx, P.ct_w[0]);                                             // closure (lib.rs:245) made of exact operations
+        t = __dadd_rn(t, __dmul_rn(sy, P.ct_w[1]));
+        t = __dadd_rn(t, __dmul_rn(sz, P.ct_w[2]));
+        t = __dadd_rn(t, __dmul_rn(mag, P.ct_w[3]));
+        return __dmul_rn(__dadd_rn(t, P.ct_offset), P.ct_factor);
+    }
     // color_transforms::poisson_saturne, lib.rs:520-558 (COS/SIN literals lib.rs:529-536)
     const double COS = 0.7009092642998508981833083453238941729068756103515625;
     const double SIN = 0.7132504491541815649924274111981503665447235107421875;
@@ -236,8 +278,8 @@ struct Cand {
 // other warps alone — with NT lanes per thread there are only 3-4 warps per scheduler.  Within a
 // lane tests still retire in iteration order and before the next atomic is issued, so exact z ties
 // keep resolving to the earlier iteration.
-template <int NT, int MODE, int PIPE>
-__global__ void __launch_bounds__(128 / NT, NT == 1 ? (PIPE ? 5 : 7) : 8)   // register budgets: 7 x 128 / 5 x 128 / 8 x 64 / 8 x 32 threads per SM
+template <int NT, int MODE, int PIPE, int AK>
+__global__ void __launch_bounds__(128 / NT, (NT == 1 && AK == 0) ? (PIPE ? 5 : 7) : (NT == 1 ? 4 : 8))   // register budgets: 7 x 128 / 5 x 128 / 8 x 64 / 8 x 32 threads per SM
 iterate_kernel(const __grid_constant__ IterParams P)
 {
     const unsigned long long nthreads = (unsigned long long)gridDim.x * blockDim.x;
@@ -267,7 +309,7 @@ iterate_kernel(const __grid_constant__ IterParams P)
 #pragma unroll
             for (int k = 0; k < NT; ++k) {
                 double nx, ny, nz;
-                SAR_NEXT_POINT(P, x[k], y[k], z[k], nx, ny, nz);
+                next_point<AK>(P, x[k], y[k], z[k], nx, ny, nz);
                 x[k] = nx; y[k] = ny; z[k] = nz;
             }
         }
@@ -284,7 +326,7 @@ iterate_kernel(const __grid_constant__ IterParams P)
 #pragma unroll
             for (int k = 0; k < NT; ++k) {
                 double nx, ny, nz;
-                SAR_NEXT_POINT(P, x[k], y[k], z[k], nx, ny, nz);              // lib.rs:770
+                next_point<AK>(P, x[k], y[k], z[k], nx, ny, nz);               // lib.rs:770
                 // screen_space = rotation_matrix.mul_right(current_point), lib.rs:773 / 208-215
                 const double sx = __dadd_rn(__dadd_rn(__dmul_rn(P.m[0][0], nx), __dmul_rn(P.m[0][1], ny)), __dmul_rn(P.m[0][2], nz));
                 const double sy = __dadd_rn(__dadd_rn(__dmul_rn(P.m[1][0], nx), __dmul_rn(P.m[1][1], ny)), __dmul_rn(P.m[1][2], nz));
@@ -400,7 +442,7 @@ warm_kernel(const __grid_constant__ IterParams P, double *__restrict__ out)
     }
     for (unsigned int w = 0; w < P.warmup; ++w) {
         double nx, ny, nz;
-        SAR_NEXT_POINT(P, x, y, z, nx, ny, nz);
+        next_point_any(P, x, y, z, nx, ny, nz);
         x = nx; y = ny; z = nz;
     }
     out[3 * job + 0] = x; out[3 * job + 1] = y; out[3 * job + 2] = z;
@@ -442,12 +484,12 @@ bbox_kernel(const __grid_constant__ IterParams P, BBoxAccum *acc)
         }
         for (unsigned int w = 0; w < P.warmup; ++w) {                         // lib.rs:750-752
             double nx, ny, nz;
-            SAR_NEXT_POINT(P, x, y, z, nx, ny, nz);
+            next_point_any(P, x, y, z, nx, ny, nz);
             x = nx; y = ny; z = nz;
         }
         for (unsigned long long it = 0; it < P.iterations; ++it) {
             double nx, ny, nz;
-            SAR_NEXT_POINT(P, x, y, z, nx, ny, nz);
+            next_point_any(P, x, y, z, nx, ny, nz);
             x = nx; y = ny; z = nz;
             const double s[3] = {
                 __dadd_rn(__dadd_rn(__dmul_rn(P.m[0][0], nx), __dmul_rn(P.m[0][1], ny)), __dmul_rn(P.m[0][2], nz)),
@@ -515,17 +557,22 @@ static void launch_iterate_mode(const IterParams &p, unsigned long long want, cu
     const unsigned long long threads = (want + nt - 1) / nt;
     const unsigned int block = threads >= 148ull * 128ull ? 128u / (unsigned int)nt : 32u;
     const unsigned int grid = (unsigned int)((threads + block - 1) / block);
+    if (p.attractor_kind == 1u) {            // the cubic family: one instantiation (the knobs above are tuned for AK 0)
+        const unsigned int blk = want >= 148ull * 128ull ? 128u : 32u;
+        iterate_kernel<1, MODE, 0, 1><<<(unsigned int)((want + blk - 1) / blk), blk, 0, s>>>(p);
+        return;
+    }
     if (g_pipe.load()) {
         switch (nt) {
-        case 1: iterate_kernel<1, MODE, 1><<<grid, block, 0, s>>>(p); break;
-        case 2: iterate_kernel<2, MODE, 1><<<grid, block, 0, s>>>(p); break;
-        default: iterate_kernel<4, MODE, 1><<<grid, block, 0, s>>>(p); break;
+        case 1: iterate_kernel<1, MODE, 1, 0><<<grid, block, 0, s>>>(p); break;
+        case 2: iterate_kernel<2, MODE, 1, 0><<<grid, block, 0, s>>>(p); break;
+        default: iterate_kernel<4, MODE, 1, 0><<<grid, block, 0, s>>>(p); break;
         }
     } else {
         switch (nt) {
-        case 1: iterate_kernel<1, MODE, 0><<<grid, block, 0, s>>>(p); break;
-        case 2: iterate_kernel<2, MODE, 0><<<grid, block, 0, s>>>(p); break;
-        default: iterate_kernel<4, MODE, 0><<<grid, block, 0, s>>>(p); break;
+        case 1: iterate_kernel<1, MODE, 0, 0><<<grid, block, 0, s>>>(p); break;
+        case 2: iterate_kernel<2, MODE, 0, 0><<<grid, block, 0, s>>>(p); break;
+        default: iterate_kernel<4, MODE, 0, 0><<<grid, block, 0, s>>>(p); break;
         }
     }
 }

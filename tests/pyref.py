@@ -23,14 +23,19 @@ def as_uint(v: float, top: int) -> int:
     return int(v)
 
 
-def next_point(coef, p):                                     # lib.rs:585-620
+def next_point(coef, p, coef3=None):                         # lib.rs:585-620; coef3: the cubic kind of include/sar.h
     x, y, z = p
     m = [1.0, x, x * x, x * y, x * z, y, y * y, y * z, z, z * z]
+    if coef3 is not None:
+        m3 = [m[2] * x, m[2] * y, m[2] * z, m[3] * y, m[3] * z, m[4] * z, m[6] * y, m[6] * z, m[7] * z, m[9] * z]
     out = []
     for k in range(3):
         s = 0.0
         for i in range(10):
             s += m[i] * coef[k][i]
+        if coef3 is not None:
+            for i in range(10):
+                s += m3[i] * coef3[k][i]
         out.append(s)
     return out
 
@@ -56,6 +61,13 @@ def magnitude(v):                                            # lib.rs:129-131
 def color_transform(cfg, delta, p):                          # lib.rs:511-516, 520-558
     if cfg.ct_kind == 1:
         return (magnitude(delta) + cfg.ct_offset) * cfg.ct_factor
+    if cfg.ct_kind == 2:                                     # ScreenBlend, include/sar.h
+        w = list(cfg.ct_weights)
+        t = p[0] * w[0]
+        t = t + p[1] * w[1]
+        t = t + p[2] * w[2]
+        t = t + magnitude(delta) * w[3]
+        return (t + cfg.ct_offset) * cfg.ct_factor
     COS = 0.7009092642998508981833083453238941729068756103515625
     SIN = 0.7132504491541815649924274111981503665447235107421875
     x2 = (p[0] + cfg.center_camera[0]) * COS + (p[2] + cfg.center_camera[1]) * SIN
@@ -95,8 +107,9 @@ class Runtime:                                               # lib.rs:631-699
 def render(cfg, rt, init):                                   # lib.rs:747-838
     cur = list(init)
     coef = [list(cfg.coef[k]) for k in range(3)]
+    coef3 = [list(cfg.coef3[k]) for k in range(3)] if cfg.attractor_kind == 1 else None
     for _ in range(1000):
-        cur = next_point(coef, cur)
+        cur = next_point(coef, cur, coef3)
     R = rotation_matrix(list(cfg.axis), cfg.rotation)
     sin_v, cos_v = math.sin(cfg.angle), math.cos(cfg.angle)
     cc = list(cfg.center_camera)
@@ -105,7 +118,7 @@ def render(cfg, rt, init):                                   # lib.rs:747-838
     scale_adjusted_mid = 0.5 / cfg.scale
     prev = list(cur)
     for _ in range(cfg.iterations):
-        cur = next_point(coef, cur)
+        cur = next_point(coef, cur, coef3)
         s = mul_right(R, cur)
         x2 = (s[0] + cc[0]) * cos_v + (s[2] + cc[1]) * sin_v
         z2 = (s[0] + cc[0]) * sin_v - (s[2] + cc[1]) * cos_v

@@ -33,7 +33,7 @@ def test_every_declared_symbol_is_exported_and_bound(S):
     missing = [s for s in declared if not hasattr(L, s)]
     assert not missing, f"declared in include/sar.h but not exported: {missing}"
     assert sorted(S._native.SYMBOLS) == declared, set(declared) ^ set(S._native.SYMBOLS)
-    assert S._native.lib().sar_abi_version() == 1
+    assert S._native.lib().sar_abi_version() == 2
 
 
 def test_library_does_not_link_the_oracle(S):
@@ -47,7 +47,7 @@ def test_library_does_not_link_the_oracle(S):
 
 
 def test_config_struct_layout_matches_header(S, oracle):
-    assert C.sizeof(S.SarConfig) == C.sizeof(oracle.SarConfig) == 8 + 6 * 4 + 8 + 240 + 24 + 24 + 8 * 4 + 8 + 16 * 24 + 16
+    assert C.sizeof(S.SarConfig) == C.sizeof(oracle.SarConfig) == 8 + 6 * 4 + 8 + 240 + 24 + 24 + 8 * 4 + 8 + 16 * 24 + 16 + 240 + 32
     # presets held by the library == presets restated by the oracle, byte for byte
     assert bytes(S.Config.poisson_saturne().to_pod()) == bytes(oracle.poisson_saturne())
     assert bytes(S.Config.solar_sail().to_pod()) == bytes(oracle.solar_sail())
