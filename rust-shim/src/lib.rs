@@ -4,8 +4,9 @@
 //! so this file documents the binding a maintainer adds; it has not been compiled.
 //!
 //! Only the shipped instantiations can run on the GPU: `PolynomialSprott2Degree` with
-//! `color_transforms::poisson_saturne` or `AdjustedVelocity`.  They implement [`DeviceConfig`];
-//! any other `Attractor` / `ColorTransform` keeps using the reference's CPU functions.
+//! `color_transforms::poisson_saturne` or `AdjustedVelocity`, wrapped in [`GpuConfig`] together with
+//! the palette list (which the reference keeps private).  They implement [`DeviceConfig`]; any other
+//! `Attractor` / `ColorTransform` keeps using the reference's CPU functions.
 use std::ffi::CStr;
 use std::os::raw::{c_char, c_int};
 
@@ -36,10 +37,12 @@ pub struct SarConfig {
     pub ct_offset: f64,
     pub ct_factor: f64,
     pub palette_len: u32,
-    pub reserved0: u32,
+    pub attractor_kind: u32,
     pub palette_rgb: [[f64; 3]; SAR_MAX_PALETTE],
     pub bright_offset: f64,
     pub bright_factor: f64,
+    pub coef3: [[f64; 10]; 3],
+    pub ct_weights: [f64; 4],
 }
 
 #[repr(C)]
@@ -81,9 +84,42 @@ fn os_seed() -> u64 {
     RandomState::new().build_hasher().finish()
 }
 
-/// Configs the GPU can run.
+/// Configs the GPU can run.  `palette` is the colour list `config.colors.palette` was built from
+/// (`Palette::new` / `from_rgb`, lib.rs:413-433, WITHOUT the sentinel `new` appends): the reference keeps
+/// that list private (lib.rs:408-411), so it has to be handed over explicitly — see [`GpuConfig`].
 pub trait DeviceConfig {
     fn to_pod(&self) -> SarConfig;
+}
+
+/// The default palette, `Colors::default()` (lib.rs:483-487).
+pub const DEFAULT_PALETTE: [[f64; 3]; 6] =
+    [[1., 1., 0.5], [0.5, 1., 0.5], [1., 0.5, 0.5], [0.5, 1., 1.], [0.5, 0.5, 1.], [1., 0.5, 1.]];
+
+/// A `Config` together with the palette list it was built from.  There is deliberately no way to
+/// construct one without saying what the palette is: a custom `Palette` must never be replaced by
+/// the default one silently (the GPU image would then differ from the reference's `colorize`).
+pub struct GpuConfig<A: reference::Attractor, T: reference::ColorTransform> {
+    pub config: Config<A, T>,
+    palette: Vec<[f64; 3]>,
+}
+impl<A: reference::Attractor, T: reference::ColorTransform> GpuConfig<A, T> {
+    /// `palette`: the list given to `Palette::new` / `from_rgb` for `config.colors.palette`.  Checked
+    /// against the palette through its public `interpolate` (lib.rs:442) at the knots: panics on a mismatch.
+    pub fn new(config: Config<A, T>, palette: &[[f64; 3]]) -> Self {
+        assert!(!palette.is_empty() && palette.len() <= SAR_MAX_PALETTE, "1..=16 palette entries cross the C ABI");
+        assert_eq!(config.colors.palette.count(), palette.len(), "palette list does not match config.colors.palette");
+        for (k, rgb) in palette.iter().enumerate() {
+            let got = config.colors.palette.interpolate(k as f64 / palette.len() as f64);
+            for (g, want) in got.0.iter().zip(rgb.iter()) {
+                assert!((g - want.sqrt()).abs() < 1e-12, "palette list does not match config.colors.palette at entry {k}");
+            }
+        }
+        Self { config, palette: palette.to_vec() }
+    }
+    /// For configs that use `Colors::default()` (as `Config::new` does, lib.rs:303); verified like `new`.
+    pub fn with_default_colors(config: Config<A, T>) -> Self {
+        Self::new(config, &DEFAULT_PALETTE)
+    }
 }
 
 fn fill_common<A: reference::Attractor, T: reference::ColorTransform>(
@@ -91,7 +127,6 @@ fn fill_common<A: reference::Attractor, T: reference::ColorTransform>(
     palette: &[[f64; 3]],
 ) -> SarConfig {
     let mut palette_rgb = [[0.0; 3]; SAR_MAX_PALETTE];
-    assert!(!palette.is_empty() && palette.len() <= SAR_MAX_PALETTE);
     palette_rgb[..palette.len()].copy_from_slice(palette);
     SarConfig {
         iterations: c.iterations as u64,
@@ -110,31 +145,29 @@ fn fill_common<A: reference::Attractor, T: reference::ColorTransform>(
         ct_offset,
         ct_factor,
         palette_len: palette.len() as u32,
-        reserved0: 0,
+        attractor_kind: 0, // PolynomialSprott2Degree, the only Attractor the reference ships
         palette_rgb,
         bright_offset: c.colors.brighness.offset,
         bright_factor: c.colors.brighness.factor,
+        coef3: [[0.0; 10]; 3],
+        ct_weights: [0.0; 4],
     }
 }
 
-/// `Palette`'s list is private in the reference (lib.rs:408-411); the shim needs one accessor
-/// added upstream (`Palette::colors(&self) -> &[Rgb<f64>]`, without the duplicated sentinel),
-/// or callers pass the list they built the palette from.  The default palette (lib.rs:483-487):
-pub const DEFAULT_PALETTE: [[f64; 3]; 6] =
-    [[1., 1., 0.5], [0.5, 1., 0.5], [1., 0.5, 0.5], [0.5, 1., 1.], [0.5, 0.5, 1.], [1., 0.5, 1.]];
-
-impl DeviceConfig for Config<PolynomialSprott2Degree, color_transforms::AdjustedVelocity> {
+impl DeviceConfig for GpuConfig<PolynomialSprott2Degree, color_transforms::AdjustedVelocity> {
     fn to_pod(&self) -> SarConfig {
-        fill_common(self, &self.attractor, 1, self.color_transform.offset, self.color_transform.factor, &DEFAULT_PALETTE)
+        let c = &self.config;
+        fill_common(c, &c.attractor, 1, c.color_transform.offset, c.color_transform.factor, &self.palette)
     }
 }
-impl DeviceConfig for Config<PolynomialSprott2Degree, color_transforms::Function> {
+impl DeviceConfig for GpuConfig<PolynomialSprott2Degree, color_transforms::Function> {
     /// Only valid when `color_transform` is `color_transforms::poisson_saturne`; a different fn
     /// pointer has no device form and must stay on the reference's CPU path.
     fn to_pod(&self) -> SarConfig {
-        assert!(self.color_transform as usize == color_transforms::poisson_saturne as usize,
+        let c = &self.config;
+        assert!(c.color_transform as usize == color_transforms::poisson_saturne as usize,
                 "only color_transforms::poisson_saturne has a device implementation");
-        fill_common(self, &self.attractor, 0, 0.0, 0.0, &DEFAULT_PALETTE)
+        fill_common(c, &c.attractor, 0, 0.0, 0.0, &self.palette)
     }
 }
 

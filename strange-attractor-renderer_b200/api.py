@@ -24,6 +24,7 @@ from __future__ import annotations
 import ctypes as C
 import enum
 import os
+import warnings
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence
 
@@ -255,6 +256,7 @@ def seed_points(seed: int, first: int, n: int) -> np.ndarray:
     return out
 
 
+_warned_serial = False
 FinalImage = np.ndarray  # [height, width, 4] uint16, RGBA — ImageBuffer<Rgba<u16>, Vec<u16>>, lib.rs:625
 
 
@@ -317,10 +319,21 @@ class Runtime:
 
 def render(config, runtime: Runtime, initial_points=None) -> None:
     """render(&config, &mut runtime), lib.rs:747: one trajectory of config.iterations recorded
-    steps accumulated into `runtime` (which is NOT reset).  The start point comes from the
+    steps accumulated into `runtime` (which is NOT reset).  NB one trajectory is strictly serial
+    (lib.rs:769-837) and occupies ONE GPU lane: this call is the parity interface, not the fast one —
+    render_parallel() is what decomposes a frame over the device's ~130 000 lanes (lib.rs:1058-1062).  The start point comes from the
     Runtime's generator (seeded at Runtime.new) unless `initial_points` ([n,3] f64) is given, in
     which case it is n successive render() calls, one per point."""
     c = _pod(config)
+    n_pts = 1 if initial_points is None else int(np.asarray(initial_points).size // 3)
+    if c.iterations * max(n_pts, 1) >= 1_000_000 and n_pts < 1024:
+        # the reference's render() is ONE serial trajectory (lib.rs:769-837): on a GPU that is one lane out of
+        # ~130 000, slower than a CPU core.  Exact, but almost never what a port wants: say so once per process.
+        global _warned_serial
+        if not _warned_serial:
+            _warned_serial = True
+            warnings.warn("render() runs each start point as one serial trajectory on ONE GPU lane (reference semantics, "
+                          "lib.rs:747); for throughput use render_parallel() or pass >= 1e4 initial_points", stacklevel=2)
     if initial_points is None:
         N.check(N.lib().sar_render_seeded(C.byref(c), runtime._h, runtime._seed & (2**64 - 1), runtime._draws, 1))
         runtime._draws += 1
