@@ -60,6 +60,8 @@ struct sar_runtime {
     uint32_t *cnt = nullptr;         // counts in pixel order: what peers read in the multi-GPU exchange
     Scalars *scal = nullptr;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;            // render_parallel: stripe-wise device→host copy behind the colourise
+    cudaEvent_t stripe_done[4] = {nullptr, nullptr, nullptr, nullptr};
     uint64_t job_base = 0;
     uint32_t host_max = 0;           // Runtime.max as last read back / forced by the host ...
     bool host_max_valid = false;     // ... valid until the accumulators change
@@ -402,6 +404,8 @@ void sar_runtime_free(sar_runtime *rt)
     if (!rt) return;
     cudaSetDevice(rt->device);
     if (rt->stream) { cudaStreamSynchronize(rt->stream); cudaStreamDestroy(rt->stream); }
+    if (rt->copy_stream) { cudaStreamSynchronize(rt->copy_stream); cudaStreamDestroy(rt->copy_stream); }
+    for (auto &e : rt->stripe_done) if (e) cudaEventDestroy(e);
     cudaFree(rt->block); cudaFree(rt->d_init); cudaFree(rt->d_scratch);
     delete rt;
 }
@@ -1119,11 +1123,25 @@ int sar_render_parallel(sar_renderer *r, const sar_config *cfg_in, uint64_t jobs
     if (int rc = sar_runtime_max_async(rt0, 0, 0, nullptr)) return rc;
     uint32_t host_max = 0;
     if (int rc = sar_runtime_get_max(rt0, &host_max, nullptr)) return rc;
-    ColorParams cp;
-    make_color_params(&cfg, rt0, cp, 0, rt0->h, &host_max);
-    launch_colorize(cp, rt0->fast, rt0->rec, rt0->scal, rt0->image, nullptr, rt0->stream);   // lib.rs:1080
-    SAR_CUDA(cudaGetLastError());
-    return sar_runtime_image_download(rt0, 0, 0, rgba_u16, nullptr);
+    // colorize (lib.rs:1080) stripe by stripe, each stripe's copy to the host starting as soon as it is coloured
+    if (!rt0->copy_stream) {
+        SAR_CUDA(cudaStreamCreateWithFlags(&rt0->copy_stream, cudaStreamNonBlocking));
+        for (auto &e : rt0->stripe_done) SAR_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    const uint32_t n_stripes = rt0->h >= 64 ? (uint32_t)(sizeof rt0->stripe_done / sizeof rt0->stripe_done[0]) : 1u;
+    for (uint32_t k = 0; k < n_stripes; ++k) {
+        const uint32_t row0 = (uint32_t)((uint64_t)rt0->h * k / n_stripes), row1 = (uint32_t)((uint64_t)rt0->h * (k + 1) / n_stripes);
+        ColorParams cp;
+        make_color_params(&cfg, rt0, cp, row0, row1 - row0, &host_max);
+        launch_colorize(cp, rt0->fast, rt0->rec, rt0->scal, rt0->image, nullptr, rt0->stream);
+        SAR_CUDA(cudaGetLastError());
+        SAR_CUDA(cudaEventRecord(rt0->stripe_done[k], rt0->stream));
+        SAR_CUDA(cudaStreamWaitEvent(rt0->copy_stream, rt0->stripe_done[k], 0));
+        const size_t off = (size_t)row0 * rt0->w * 4, cnt = (size_t)(row1 - row0) * rt0->w * 4;
+        SAR_CUDA(cudaMemcpyAsync(rgba_u16 + off, rt0->image + off, cnt * sizeof(uint16_t), cudaMemcpyDeviceToHost, rt0->copy_stream));
+    }
+    SAR_CUDA(cudaStreamSynchronize(rt0->copy_stream));
+    return SAR_OK;
 }
 
 // ---- output conversion + raw encoders (src/bin/main.rs:40-100) -----------------------------------
