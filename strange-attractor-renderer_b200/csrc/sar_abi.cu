@@ -1105,17 +1105,30 @@ int sar_render_parallel(sar_renderer *r, const sar_config *cfg_in, uint64_t jobs
         } else if (int rc = render_launch(&cfg, rt, nullptr, seed, first, n, lanes, rt->stream)) return rc;
         first += n;
     }
-    // merge every other device into the first (lib.rs:1070-1076), deterministically
+    // merge every other device into the first (lib.rs:1070-1076), deterministically: device 0 reads the other
+    // devices' accumulators in place over NVLink when peer access can be enabled (only the touched records move),
+    // else from a staged copy of the whole block
     sar_runtime *rt0 = r->rts[0];
     for (size_t d = 1; d < nd; ++d) {
         sar_runtime *src = r->rts[d];
         SAR_CUDA(cudaSetDevice(src->device));
         SAR_CUDA(cudaStreamSynchronize(src->stream));
         SAR_CUDA(cudaSetDevice(rt0->device));
-        if (int rc = ensure_scratch(rt0, src->block_bytes)) return rc;
-        SAR_CUDA(cudaMemcpyPeerAsync(rt0->d_scratch, rt0->device, src->block, src->device, src->block_bytes, rt0->stream));
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, rt0->device, src->device) != cudaSuccess) can = 0;
+        if (can) {
+            const cudaError_t e = cudaDeviceEnablePeerAccess(src->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) can = 0;
+            (void)cudaGetLastError();
+        }
         sar_peer view;
-        peer_view(&view, rt0->d_scratch, cfg.width, cfg.height);
+        if (can) {
+            peer_view(&view, src->block, cfg.width, cfg.height);
+        } else {
+            if (int rc = ensure_scratch(rt0, src->block_bytes)) return rc;
+            SAR_CUDA(cudaMemcpyPeerAsync(rt0->d_scratch, rt0->device, src->block, src->device, src->block_bytes, rt0->stream));
+            peer_view(&view, rt0->d_scratch, cfg.width, cfg.height);
+        }
         sar_peer *pv = &view;
         if (int rc = sar_runtime_merge_peers_async(rt0, &pv, 1, 0, 0, nullptr)) return rc;
     }

@@ -1037,7 +1037,9 @@ __global__ void merge_peers_kernel(unsigned long long *dfast, ulonglong2 *drec, 
         uint32_t c = (uint32_t)dfast[sl];
         ulonglong2 d = drec[p];
         for (int r = 0; r < peers.n; ++r) {
-            c += (uint32_t)__ldcv(peers.fast[r] + sl);
+            const uint32_t pc = (uint32_t)__ldcv(peers.fast[r] + sl);
+            if (pc == 0u) continue;                                      // never hit there: its record is the reset value
+            c += pc;
             const unsigned long long oy = __ldcv(&peers.rec[r][p].y);
             if (rec_order(oy) > rec_order(d.y)) { d.y = oy; d.x = __ldcv(&peers.rec[r][p].x); }
         }
