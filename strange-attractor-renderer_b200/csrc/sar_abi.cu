@@ -1337,40 +1337,10 @@ static int sequence_core(sar_renderer *r, const sar_config *cfg_in, const double
             p.init = nullptr; p.seed = seed; p.first_job = 0; p.n_jobs = jobs[d];
             launch_warm(p, q.warm, q.rt[0]->stream);
             SAR_CUDA(cudaGetLastError());
-            SAR_CUDA(cudaStreamSynchronize(q.rt[0]->stream));       // both Runtimes' streams read it
+            SAR_CUDA(cudaStreamSynchronize(q.rt[0]->stream));
         }
     }
 
-    // Frame g's second half: its Runtime.max has been copied to the host — ln(max + 1), the log base of
-    // lib.rs:860, is computed by the host libm like every blocking entry point does, so the frame is
-    // bit-exact whatever max is (a solar-sail frame's NaN sink is far beyond the ln table) —, then
-    // colourise and start the copy out.  The other Runtime of the device is rendering meanwhile.
-    auto colourise = [&](uint32_t g) -> int {
-        const size_t d = g % nd;
-        const int slot = (int)((g / nd) % 2);
-        seq_device &q = r->seq[d];
-        sar_runtime *rt = q.rt[slot];
-        SAR_CUDA(cudaSetDevice(rt->device));
-        SAR_CUDA(cudaEventSynchronize(q.max_ready[slot]));
-        sar_config cfg = cfgs[d];
-        cfg.angle = angles_rad[g];
-        ColorParams cp;
-        make_color_params(&cfg, rt, cp, 0, rt->h, &q.h_max[slot]);
-        launch_colorize(cp, rt->fast, rt->rec, rt->scal, rt->image, nullptr, rt->stream);   // colorize, lib.rs:1080
-        SAR_CUDA(cudaGetLastError());
-        if (convert) {                                                          // main.rs:52-57 on the device
-            launch_convert(rt->image, q.enc[slot], rt->w, rt->h, o.fmt, o.order, o.row_stride, rt->stream);
-            SAR_CUDA(cudaGetLastError());
-        }
-        SAR_CUDA(cudaEventRecord(q.rendered[slot], rt->stream));
-        SAR_CUDA(cudaStreamWaitEvent(q.copy_stream, q.rendered[slot], 0));
-        uint8_t *dst = rgba_frames ? rgba_frames + (size_t)g * frame_u16 : q.stage[slot];
-        memcpy(dst, o.head, o.header);
-        SAR_CUDA(cudaMemcpyAsync(dst + o.header, convert ? (const void *)q.enc[slot] : (const void *)rt->image, o.payload,
-                                 cudaMemcpyDeviceToHost, q.copy_stream));
-        SAR_CUDA(cudaEventRecord(q.copied[slot], q.copy_stream));
-        return SAR_OK;
-    };
     auto finalize = [&](uint32_t g) -> int {     // wait for frame g's host copy, hand it to the caller
         const size_t d = g % nd;
         const int slot = (int)((g / nd) % 2);
@@ -1382,6 +1352,44 @@ static int sequence_core(sar_renderer *r, const sar_config *cfg_in, const double
         return SAR_OK;
     };
 
+    // Frame g's second half: its Runtime.max has been copied to the host — ln(max + 1), the log base of
+    // lib.rs:860, is computed by the host libm like every blocking entry point does, so the frame is
+    // bit-exact whatever max is (a solar-sail frame's NaN sink is far beyond the ln table) —, then
+    // colourise and start the copy out.  Both Runtimes of a device share ONE compute stream: the next frame's
+    // render is already queued behind this frame's max, so the device never waits for the host, and no two of
+    // the big kernels run side by side (a reset or colourise streaming 100 MB through the L2 while the other
+    // Runtime's iterate kernel works out of it cost 24 %; measured, tools/seq_bench.py).
+    auto colourise = [&](uint32_t g) -> int {
+        const size_t d = g % nd;
+        const int slot = (int)((g / nd) % 2);
+        seq_device &q = r->seq[d];
+        sar_runtime *rt = q.rt[slot];
+        SAR_CUDA(cudaSetDevice(rt->device));
+        SAR_CUDA(cudaEventSynchronize(q.max_ready[slot]));
+        sar_config cfg = cfgs[d];
+        cfg.angle = angles_rad[g];
+        ColorParams cp;
+        make_color_params(&cfg, rt, cp, 0, rt->h, &q.h_max[slot]);
+        cudaStream_t cs = q.rt[0]->stream;                                      // the device's compute stream
+        SAR_CUDA(cudaStreamWaitEvent(cs, q.copied[slot], 0));                   // the slot's previous image has left the device
+        launch_colorize(cp, rt->fast, rt->rec, rt->scal, rt->image, nullptr, cs);           // colorize, lib.rs:1080
+        SAR_CUDA(cudaGetLastError());
+        if (convert) {                                                          // main.rs:52-57 on the device
+            launch_convert(rt->image, q.enc[slot], rt->w, rt->h, o.fmt, o.order, o.row_stride, cs);
+            SAR_CUDA(cudaGetLastError());
+        }
+        SAR_CUDA(cudaEventRecord(q.rendered[slot], cs));
+        SAR_CUDA(cudaStreamWaitEvent(q.copy_stream, q.rendered[slot], 0));
+        // the slot's previous frame (g - 2 nd) is handed to the caller here — its copy finished a frame ago, so the
+        // host does not stall, and the slot's staging buffer is free again before this frame's copy is queued
+        if (g >= 2 * nd) if (int rc = finalize(g - 2 * (uint32_t)nd)) return rc;
+        uint8_t *dst = rgba_frames ? rgba_frames + (size_t)g * frame_u16 : q.stage[slot];
+        memcpy(dst, o.head, o.header);
+        SAR_CUDA(cudaMemcpyAsync(dst + o.header, convert ? (const void *)q.enc[slot] : (const void *)rt->image, o.payload,
+                                 cudaMemcpyDeviceToHost, q.copy_stream));
+        SAR_CUDA(cudaEventRecord(q.copied[slot], q.copy_stream));
+        return SAR_OK;
+    };
     for (uint32_t f = 0; f < n_frames; ++f) {
         const size_t d = f % nd;
         const int slot = (int)((f / nd) % 2);
@@ -1390,19 +1398,17 @@ static int sequence_core(sar_renderer *r, const sar_config *cfg_in, const double
         SAR_CUDA(cudaSetDevice(rt->device));
         sar_config cfg = cfgs[d];
         cfg.angle = angles_rad[f];                                             // main.rs:497
-        if (f >= 2 * nd) {                                                     // the slot's previous frame must have left the device
-            if (int rc = finalize(f - 2 * (uint32_t)nd)) return rc;            // in order: frames f-2nd .. are handed over here
-        }
-        if (int rc = sar_runtime_reset_async(rt, nullptr)) return rc;           // Runtime::reset per frame, lib.rs:951
+        cudaStream_t cs = q.rt[0]->stream;                                      // the device's compute stream (both Runtimes)
+        if (int rc = sar_runtime_reset_async(rt, cs)) return rc;                // Runtime::reset per frame, lib.rs:951
         if (shared) {
-            if (int rc = render_launch(&cfg, rt, q.warm, 0, 0, jobs[d], lanes[d], rt->stream, true)) return rc;
+            if (int rc = render_launch(&cfg, rt, q.warm, 0, 0, jobs[d], lanes[d], cs, true)) return rc;
         } else {
             // fresh start points per frame, like the reference: frame f takes the next jobs[d] points of the stream
-            if (int rc = render_launch(&cfg, rt, nullptr, seed, (uint64_t)f * jobs[d], jobs[d], lanes[d], rt->stream)) return rc;
+            if (int rc = render_launch(&cfg, rt, nullptr, seed, (uint64_t)f * jobs[d], jobs[d], lanes[d], cs)) return rc;
         }
-        if (int rc = sar_runtime_max_async(rt, 0, 0, nullptr)) return rc;
-        SAR_CUDA(cudaMemcpyAsync(&q.h_max[slot], &rt->scal->max, sizeof(uint32_t), cudaMemcpyDeviceToHost, rt->stream));
-        SAR_CUDA(cudaEventRecord(q.max_ready[slot], rt->stream));
+        if (int rc = sar_runtime_max_async(rt, 0, 0, cs)) return rc;
+        SAR_CUDA(cudaMemcpyAsync(&q.h_max[slot], &rt->scal->max, sizeof(uint32_t), cudaMemcpyDeviceToHost, cs));
+        SAR_CUDA(cudaEventRecord(q.max_ready[slot], cs));
         if (f >= nd) if (int rc = colourise(f - (uint32_t)nd)) return rc;       // the device's previous frame, one behind
     }
     for (uint32_t g = n_frames > nd ? n_frames - (uint32_t)nd : 0; g < n_frames; ++g)
