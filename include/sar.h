@@ -320,8 +320,13 @@ int sar_render_seeded_async(const sar_config *cfg, sar_runtime *rt, uint64_t see
 int sar_render_device_async(const sar_config *cfg, sar_runtime *rt, const double *d_init_xyz,
                             uint64_t first_job, uint64_t n_jobs, uint32_t threads, void *stream);
 int sar_runtime_reset_async(sar_runtime *rt, void *stream);
-/* Recompute Runtime.max (lib.rs:643) and the Depth min/max over rows
- * [row0,row0+rows) (rows=0: whole image) into the runtime's device scalars. */
+/* Bring Runtime.max (lib.rs:643) up to date in the runtime's device scalars, over
+ * rows [row0,row0+rows) (rows=0: whole image).  The render kernel keeps a running
+ * max like lib.rs:813-815 does, so for a whole image whose counts all came from
+ * render calls since the last reset this is a one-thread kernel (it folds the NaN
+ * debt of pixel (0,0) in); otherwise a reduction over the accumulators.  The Depth
+ * min/max (lib.rs:877-882) is reduced by the colourise calls when a Depth image is
+ * asked for. */
 int sar_runtime_max_async(sar_runtime *rt, uint32_t row0, uint32_t rows, void *stream);
 /* Read back / force Runtime.max (synchronises `stream`). */
 int sar_runtime_get_max(sar_runtime *rt, uint32_t *max_out, void *stream);

@@ -65,6 +65,9 @@ struct sar_runtime {
     uint64_t job_base = 0;
     uint32_t host_max = 0;           // Runtime.max as last read back / forced by the host ...
     bool host_max_valid = false;     // ... valid until the accumulators change
+    bool max_tracked = false;        // every count change since the last reset came from the iterate kernel, which keeps
+                                     // scal->max current: the max "reduction" is then one thread (launch_fold_max)
+    bool depth_valid = false;        // scal->zmax_key / zmin_key (Depth fold, lib.rs:877-882) match the accumulators
     int sm_count = 148;
     // lazily allocated scratch
     double *d_init = nullptr; size_t d_init_cap = 0;
@@ -418,6 +421,8 @@ int sar_runtime_reset_async(sar_runtime *rt, void *stream)
     SAR_CUDA(cudaGetLastError());
     rt->job_base = 0;
     rt->host_max_valid = false;
+    rt->max_tracked = true;
+    rt->depth_valid = false;
     return SAR_OK;
 }
 int sar_runtime_reset(sar_runtime *rt)
@@ -494,6 +499,8 @@ int sar_runtime_upload(sar_runtime *rt, const uint32_t *count, const double *ste
     SAR_CUDA(cudaGetLastError());
     SAR_CUDA(cudaStreamSynchronize(rt->stream));
     rt->host_max_valid = false;
+    rt->max_tracked = false;
+    rt->depth_valid = false;
     if (rt->job_base == 0) rt->job_base = 1;   // uploaded records carry job key 0: they keep every future tie
     return SAR_OK;
 }
@@ -520,6 +527,8 @@ int sar_runtime_merge(sar_runtime *dst, const sar_runtime *src)
     launch_merge(dst->fast, dst->rec, dst->scal, sfast, srec, sscal, dst->npix, dst->slots, dst->stream);
     SAR_CUDA(cudaGetLastError());
     dst->host_max_valid = false;
+    dst->max_tracked = false;
+    dst->depth_valid = false;
     SAR_CUDA(cudaStreamSynchronize(dst->stream));
     if (src->job_base > dst->job_base) dst->job_base = src->job_base;
     return SAR_OK;
@@ -546,6 +555,7 @@ static int render_launch(const sar_config *cfg, sar_runtime *rt, const double *d
     launch_iterate(p, threads ? threads : default_lanes(rt), s);
     SAR_CUDA(cudaGetLastError());
     rt->host_max_valid = false;
+    rt->depth_valid = false;
     rt->job_base += n_jobs;
     return SAR_OK;
 }
@@ -670,6 +680,19 @@ int sar_autoframe(const sar_config *cfg, int device, uint64_t seed, const double
 }
 
 // ---- max / colorize ----------------------------------------------------------------------------
+// Full reduction: Runtime.max and the Depth fold over a row range, from the accumulators.
+static int runtime_max_full(sar_runtime *rt, uint32_t row0, uint32_t rows, cudaStream_t s)
+{
+    const unsigned int init[3] = {0u, ZKEY_ZERO, ZKEY_FLT_MAX};   // max, zmax_key, zmin_key (fold seed lib.rs:882)
+    SAR_CUDA(cudaMemcpyAsync(&rt->scal->max, init, sizeof init, cudaMemcpyHostToDevice, s));
+    launch_max(rt->fast, rt->rec, rt->scal, (size_t)row0 * rt->w, (size_t)rows * rt->w, rt->slots, s);
+    SAR_CUDA(cudaGetLastError());
+    const bool whole = row0 == 0 && rows == rt->h;
+    rt->max_tracked = whole;          // a whole-image reduction is a valid starting point for the render's own tracking
+    rt->depth_valid = whole;
+    return SAR_OK;
+}
+
 int sar_runtime_max_async(sar_runtime *rt, uint32_t row0, uint32_t rows, void *stream)
 {
     if (!rt) return fail(SAR_ERR_INVALID, "runtime is NULL");
@@ -677,12 +700,21 @@ int sar_runtime_max_async(sar_runtime *rt, uint32_t row0, uint32_t rows, void *s
     if ((uint64_t)row0 + rows > rt->h) return fail(SAR_ERR_INVALID, "rows [%u,%u) outside image height %u", row0, row0 + rows, rt->h);
     SAR_CUDA(cudaSetDevice(rt->device));
     cudaStream_t s = pick(rt, stream);
-    const unsigned int init[3] = {0u, ZKEY_ZERO, ZKEY_FLT_MAX};   // max, zmax_key, zmin_key (fold seed lib.rs:882)
-    SAR_CUDA(cudaMemcpyAsync(&rt->scal->max, init, sizeof init, cudaMemcpyHostToDevice, s));
-    launch_max(rt->fast, rt->rec, rt->scal, (size_t)row0 * rt->w, (size_t)rows * rt->w, rt->slots, s);
-    SAR_CUDA(cudaGetLastError());
     rt->host_max_valid = false;
-    return SAR_OK;
+    if (rt->max_tracked && row0 == 0 && rows == rt->h) {
+        // the iterate kernel kept scal->max current (lib.rs:813-815 is a running max): only the NaN debt is left to fold.
+        // The Depth fold is not touched here; the colourise calls compute it when a Depth image is asked for.
+        launch_fold_max(rt->fast, rt->scal, rt->slots, s);
+        SAR_CUDA(cudaGetLastError());
+        return SAR_OK;
+    }
+    return runtime_max_full(rt, row0, rows, s);
+}
+// Depth images need the min/max of the touched z values (lib.rs:877-882): reduce them if they are stale.
+static int ensure_depth_fold(const sar_config *cfg, sar_runtime *rt, cudaStream_t s)
+{
+    if (cfg->render_kind != SAR_RENDER_DEPTH || rt->depth_valid) return SAR_OK;
+    return runtime_max_full(rt, 0, rt->h, s);
 }
 int sar_runtime_get_max(sar_runtime *rt, uint32_t *max_out, void *stream)
 {
@@ -713,6 +745,7 @@ int sar_colorize_rows_async(const sar_config *cfg, sar_runtime *rt, uint32_t row
     if ((uint64_t)row0 + rows > rt->h) return fail(SAR_ERR_INVALID, "rows [%u,%u) outside image height %u", row0, row0 + rows, rt->h);
     if (dst && (dst->w != rt->w || dst->h != rt->h)) return fail(SAR_ERR_DIMS, "peer image is %ux%u, runtime %ux%u", dst->w, dst->h, rt->w, rt->h);
     SAR_CUDA(cudaSetDevice(rt->device));
+    if (int rc = ensure_depth_fold(cfg, rt, pick(rt, stream))) return rc;
     ColorParams cp;
     make_color_params(cfg, rt, cp, row0, rows, rt->host_max_valid ? &rt->host_max : nullptr);
     launch_colorize(cp, rt->fast, rt->rec, rt->scal, dst ? dst->image : rt->image, nullptr, pick(rt, stream));
@@ -741,6 +774,7 @@ int sar_colorize(const sar_config *cfg, const sar_runtime *crt, uint16_t *rgba_u
     if (int rc = check_config(cfg, rt)) return rc;
     SAR_CUDA(cudaSetDevice(rt->device));
     if (int rc = sar_runtime_max_async(rt, 0, 0, nullptr)) return rc;
+    if (int rc = ensure_depth_fold(cfg, rt, rt->stream)) return rc;
     float *d_f32 = nullptr;
     if (rgba_f32) {
         if (int rc = ensure_scratch(rt, rt->npix * 4 * sizeof(float))) return rc;
@@ -844,6 +878,8 @@ int sar_runtime_merge_peers_async(sar_runtime *rt, sar_peer *const *peers, int n
     launch_merge_peers(rt->fast, rt->rec, rt->scal, pl, (size_t)row0 * rt->w, (size_t)rows * rt->w, rt->slots, pick(rt, stream));
     SAR_CUDA(cudaGetLastError());
     rt->host_max_valid = false;
+    rt->max_tracked = false;
+    rt->depth_valid = false;
     return SAR_OK;
 }
 
@@ -884,6 +920,8 @@ int sar_frame_reset_async(sar_runtime *rt, int n_ranks, uint32_t epoch, void *st
     SAR_CUDA(cudaGetLastError());
     rt->job_base = 0;
     rt->host_max_valid = false;
+    rt->max_tracked = false;          // the frame protocol reduces its stripe maxima itself
+    rt->depth_valid = false;
     return SAR_OK;
 }
 
@@ -908,6 +946,8 @@ int sar_frame_merge_async(sar_runtime *rt, sar_peer *const *peers_by_rank, int n
     launch_frame_merge(rt->fast, rt->rec, rt->cnt, rt->scal, pl, (size_t)row0 * rt->w, (size_t)rows * rt->w, rt->slots, S, pick(rt, stream));
     SAR_CUDA(cudaGetLastError());
     rt->host_max_valid = false;
+    rt->max_tracked = false;
+    rt->depth_valid = false;
     return SAR_OK;
 }
 
@@ -1134,6 +1174,7 @@ int sar_render_parallel(sar_renderer *r, const sar_config *cfg_in, uint64_t jobs
     }
     rt0->job_base = total_jobs;
     if (int rc = sar_runtime_max_async(rt0, 0, 0, nullptr)) return rc;
+    if (int rc = ensure_depth_fold(&cfg, rt0, rt0->stream)) return rc;
     uint32_t host_max = 0;
     if (int rc = sar_runtime_get_max(rt0, &host_max, nullptr)) return rc;
     // colorize (lib.rs:1080) stripe by stripe, each stripe's copy to the host starting as soon as it is coloured
@@ -1407,6 +1448,7 @@ static int sequence_core(sar_renderer *r, const sar_config *cfg_in, const double
             if (int rc = render_launch(&cfg, rt, nullptr, seed, (uint64_t)f * jobs[d], jobs[d], lanes[d], cs)) return rc;
         }
         if (int rc = sar_runtime_max_async(rt, 0, 0, cs)) return rc;
+        if (int rc = ensure_depth_fold(&cfg, rt, cs)) return rc;
         SAR_CUDA(cudaMemcpyAsync(&q.h_max[slot], &rt->scal->max, sizeof(uint32_t), cudaMemcpyDeviceToHost, cs));
         SAR_CUDA(cudaEventRecord(q.max_ready[slot], cs));
         if (f >= nd) if (int rc = colourise(f - (uint32_t)nd)) return rc;       // the device's previous frame, one behind

@@ -66,7 +66,8 @@ enum SyncKind {                       // what a flag announces (see sar_runtime_
 
 struct Scalars {                      // device-resident scalar state of a Runtime
     unsigned long long nan_sink;      // iterations of NaN trajectories, owed to count[(0,0)]
-    unsigned int max;                 // Runtime.max (lib.rs:643), valid after launch_max()
+    unsigned int max;                 // Runtime.max (lib.rs:643): kept current by the iterate kernel (without the NaN debt);
+                                      // final after launch_fold_max() / launch_max()
     unsigned int zmax_key, zmin_key;  // Depth colourise fold (lib.rs:877-882)
     unsigned int pad;
     // Cross-GPU synchronisation over peer memory (one process per GPU).  flag[k][r] is
@@ -139,6 +140,7 @@ void launch_reset(unsigned long long *fast, ulonglong2 *rec, Scalars *scal, size
 void launch_iterate(const IterParams &p, unsigned int lanes, cudaStream_t s);
 // the warm-up alone (lib.rs:748-752): start points -> states after p.warmup steps, out[3*job..]
 void launch_warm(const IterParams &p, double *out, cudaStream_t s);
+void launch_fold_max(const unsigned long long *fast, Scalars *scal, SlotMap slots, cudaStream_t s);
 void launch_max(const unsigned long long *fast, const ulonglong2 *rec, Scalars *scal, size_t pix0, size_t npix, SlotMap slots, cudaStream_t s);
 void launch_colorize(const ColorParams &cp, const unsigned long long *fast, const ulonglong2 *rec, const Scalars *scal,
                      uint16_t *rgba_u16, float *rgba_f32, cudaStream_t s);

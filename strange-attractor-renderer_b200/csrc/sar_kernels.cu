@@ -284,6 +284,7 @@ iterate_kernel(const __grid_constant__ IterParams P)
 {
     const unsigned long long nthreads = (unsigned long long)gridDim.x * blockDim.x;
     const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t cmax = 0u;                                                       // greatest count this thread's hits produced (lib.rs:813-815)
     for (unsigned long long job0 = tid; job0 < P.n_jobs; job0 += nthreads * NT) {
         double x[NT], y[NT], z[NT];
         uint32_t job_inv[NT];
@@ -373,7 +374,7 @@ iterate_kernel(const __grid_constant__ IterParams P)
                 }
                 unsigned long long *slot = P.fast + slot_of(c[k].idx, P.slots);
                 if (MODE == 0 || MODE == 4) {
-                    if (!hit) c[k].key = 0u;                                  // nothing recorded: nothing to test
+                    if (!hit) { c[k].key = 0u; c[k].idx = IDX_RARE; }         // nothing recorded: nothing to test, `old` stays undefined
                     c[k].old = atom_inc_if(hit, slot);
                 } else {
                     c[k].old = ~0ull;
@@ -388,12 +389,17 @@ iterate_kernel(const __grid_constant__ IterParams P)
         // depth test (lib.rs:821) on the returned hints; the winning branch inline (in the loop) or as a call (loop exits)
         auto test = [&](Cand (&c)[NT], auto inl) {
 #pragma unroll
-            for (int k = 0; k < NT; ++k)
+            for (int k = 0; k < NT; ++k) {
+                if (MODE == 0 && c[k].idx != IDX_RARE) {                      // count after this hit; the running max of lib.rs:813-815
+                    const uint32_t now = (uint32_t)c[k].old + 1u;
+                    cmax = now > cmax ? now : cmax;
+                }
                 if (c[k].key >= (uint32_t)(c[k].old >> 32) && c[k].key != 0u) {      // may beat zbuf
                     if (MODE != 0) { if (c[k].idx == 0xFFFFFFF0u) P.scal->pad = c[k].key; }   // diagnostics: keep the returned value live
                     else if (decltype(inl)::value) record_win(P, c[k].idx, c[k].key, job_inv[k], c[k].old, c[k].dx, c[k].dy, c[k].dz, c[k].sx, c[k].sy, c[k].sz);
                     else record_win_call(&P, c[k].idx, c[k].key, job_inv[k], c[k].old, c[k].dx, c[k].dy, c[k].dz, c[k].sx, c[k].sy, c[k].sz);
                 }
+            }
         };
         using inl_t = std::integral_constant<bool, true>;
         using call_t = std::integral_constant<bool, false>;
@@ -423,6 +429,13 @@ iterate_kernel(const __grid_constant__ IterParams P)
                 arith(A); scatter(A, it); test(A, inl_t{});
             }
         }
+    }
+    // Runtime.max, kept current by the render itself: one reduction per warp (lanes leave the job loop together,
+    // except NaN jobs, hence the active mask), not 132 608 same-address atomics
+    {
+        const unsigned int m = __activemask();
+        const uint32_t wmax = __reduce_max_sync(m, cmax);
+        if (wmax && (threadIdx.x & 31u) == (unsigned int)(__ffs(m) - 1)) atomicMax(&P.scal->max, wmax);
     }
 }
 
@@ -651,6 +664,18 @@ __global__ void max_kernel(const unsigned long long *fast, const ulonglong2 *rec
         atomicMax(&scal->zmax_key, zmx);
         atomicMin(&scal->zmin_key, zmn);
     }
+}
+// When the iterate kernel has kept scal->max current (every count change since the last reset came from it), all
+// that is left of the reduction is the NaN debt owed to pixel (0,0): one thread.
+__global__ void fold_max_kernel(const unsigned long long *fast, Scalars *scal, SlotMap slots)
+{
+    const uint32_t c0 = pixel_count(fast, scal, 0, slots);
+    if (c0 > scal->max) scal->max = c0;
+}
+void launch_fold_max(const unsigned long long *fast, Scalars *scal, SlotMap slots, cudaStream_t s)
+{
+    fold_max_kernel<<<1, 1, 0, s>>>(fast, scal, slots);
+    ++g_launches;
 }
 void launch_max(const unsigned long long *fast, const ulonglong2 *rec, Scalars *scal, size_t pix0, size_t npix, SlotMap slots, cudaStream_t s)
 {
