@@ -222,6 +222,9 @@ static void make_iter_params(const sar_config *cfg, sar_runtime *rt, IterParams 
     p.slots = rt->slots;
     p.iterations = cfg->iterations;
     p.warmup = SAR_WARMUP_ITERATIONS;                                            // lib.rs:750
+#ifdef SAR_DIAGNOSTICS
+    p.diag_hot = (unsigned int)get_diag_hot(); p.diag_tab_entries = 2048;
+#endif
 }
 
 static void make_color_params(const sar_config *cfg, const sar_runtime *rt, ColorParams &c, uint32_t row0, uint32_t rows,
@@ -272,9 +275,12 @@ int sar_set_option(const char *name, int64_t value)
         if (!set_pipeline((int)value)) return fail(SAR_ERR_INVALID, "pipeline must be 0 or 1");
         return SAR_OK;
     }
+#ifdef SAR_DIAGNOSTICS
+    if (strcmp(name, "diag_hot") == 0) { set_diag_hot((int)value); return SAR_OK; }
+#endif
     if (strcmp(name, "diagnostic_mode") == 0) {
 #ifdef SAR_DIAGNOSTICS
-        if (!set_mode((int)value)) return fail(SAR_ERR_INVALID, "diagnostic_mode must be 0, 1, 2 or 4");
+        if (!set_mode((int)value)) return fail(SAR_ERR_INVALID, "diagnostic_mode must be 0, 1, 2, 4 or 5");
         return SAR_OK;
 #else
         if (value == 0) return SAR_OK;

@@ -105,6 +105,9 @@ struct IterParams {                   // everything the iterate kernel reads; li
     unsigned int ct_kind;
     unsigned int attractor_kind;
     SlotMap slots;                    // pixel -> slot map of the fast array
+#ifdef SAR_DIAGNOSTICS
+    unsigned int diag_hot, diag_tab_entries;   // MODE 5 cost model: hot fraction (per 1024) and table entries per block
+#endif
     unsigned int warmup;              // unrecorded steps before the recorded ones: 1000 (lib.rs:750), or 0 when `init` holds warmed states
 };
 
@@ -172,6 +175,10 @@ void launch_wait(Scalars *mine, int kind, int n_ranks, unsigned int epoch, cudaS
 void set_sync_timeout_ms(long long ms);
 unsigned long long launch_count();
 bool set_mode(int mode);     // SAR_DIAGNOSTICS builds only: 0 = product path; 1, 2, 4 = roofline experiments (incomplete results)
+#ifdef SAR_DIAGNOSTICS
+void set_diag_hot(int per_1024);
+int get_diag_hot();
+#endif
 bool set_pipeline(int on);          // tuning: depth test one iteration behind its atomic (0/1); never changes results
 bool set_traj_per_thread(int nt);   // tuning: trajectories carried per thread (1, 2 or 4); never changes results
 

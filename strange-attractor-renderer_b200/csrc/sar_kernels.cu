@@ -373,6 +373,26 @@ iterate_kernel(const __grid_constant__ IterParams P)
                     }
                 }
                 unsigned long long *slot = P.fast + slot_of(c[k].idx, P.slots);
+#ifdef SAR_DIAGNOSTICS
+                if (MODE == 5) {
+                    // cost model of a per-SM shared-memory table for hot pixels: a pseudo-random P.diag_hot / 1024 of the
+                    // hits pay a tag load + two shared-memory atomics instead of the L2 atomic (results are meaningless)
+                    extern __shared__ unsigned int s_tab[];
+                    const unsigned int h = c[k].idx * 0x9E3779B1u;
+                    const unsigned int e = (h >> 8) % (unsigned int)(P.diag_tab_entries);
+                    const unsigned int tag = *((volatile unsigned int *)&s_tab[3 * e]);
+                    const bool hot = hit && ((h >> 22) < P.diag_hot) && tag != 0xDEADBEEFu;
+                    if (!hit) { c[k].key = 0u; c[k].idx = IDX_RARE; }
+                    if (hot) {
+                        const unsigned int cnt = atomicAdd(&s_tab[3 * e + 1], 1u);
+                        const unsigned int zm = atomicMax(&s_tab[3 * e + 2], c[k].key);
+                        c[k].old = ((unsigned long long)(zm | 0x80000000u) << 32) | cnt;
+                        c[k].key = 0u;
+                    } else {
+                        c[k].old = atom_inc_if(hit, slot);
+                    }
+                } else
+#endif
                 if (MODE == 0 || MODE == 4) {
                     if (!hit) { c[k].key = 0u; c[k].idx = IDX_RARE; }         // nothing recorded: nothing to test, `old` stays undefined
                     c[k].old = atom_inc_if(hit, slot);
@@ -390,12 +410,12 @@ iterate_kernel(const __grid_constant__ IterParams P)
         auto test = [&](Cand (&c)[NT], auto inl) {
 #pragma unroll
             for (int k = 0; k < NT; ++k) {
-                if (MODE == 0 && c[k].idx != IDX_RARE) {                      // count after this hit; the running max of lib.rs:813-815
+                if ((MODE == 0 || MODE == 5) && c[k].idx != IDX_RARE) {       // count after this hit; the running max of lib.rs:813-815
                     const uint32_t now = (uint32_t)c[k].old + 1u;
                     cmax = now > cmax ? now : cmax;
                 }
                 if (c[k].key >= (uint32_t)(c[k].old >> 32) && c[k].key != 0u) {      // may beat zbuf
-                    if (MODE != 0) { if (c[k].idx == 0xFFFFFFF0u) P.scal->pad = c[k].key; }   // diagnostics: keep the returned value live
+                    if (MODE != 0 && MODE != 5) { if (c[k].idx == 0xFFFFFFF0u) P.scal->pad = c[k].key; }   // diagnostics: keep the returned value live
                     else if (decltype(inl)::value) record_win(P, c[k].idx, c[k].key, job_inv[k], c[k].old, c[k].dx, c[k].dy, c[k].dz, c[k].sx, c[k].sy, c[k].sz);
                     else record_win_call(&P, c[k].idx, c[k].key, job_inv[k], c[k].old, c[k].dx, c[k].dy, c[k].dz, c[k].sx, c[k].sy, c[k].sz);
                 }
@@ -550,10 +570,13 @@ bool set_pipeline(int on)
     return true;
 }
 #ifdef SAR_DIAGNOSTICS
+static std::atomic<int> g_diag_hot{0};
+void set_diag_hot(int per_1024) { g_diag_hot = per_1024; }
+int get_diag_hot() { return g_diag_hot.load(); }
 static std::atomic<int> g_mode{0};
 bool set_mode(int m)
 {
-    if (m != 0 && m != 1 && m != 2 && m != 4) return false;
+    if (m != 0 && m != 1 && m != 2 && m != 4 && m != 5) return false;
     g_mode = m;
     return true;
 }
@@ -564,6 +587,11 @@ bool set_mode(int m) { return m == 0; }
 template <int MODE>
 static void launch_iterate_mode(const IterParams &p, unsigned long long want, cudaStream_t s)
 {
+#ifdef SAR_DIAGNOSTICS
+    const size_t smem = MODE == 5 ? (size_t)p.diag_tab_entries * 12 : 0;
+#else
+    const size_t smem = 0;
+#endif
     // `want` lanes; NT lanes per thread; narrow blocks so that the grid stays a multiple of the SM
     // count at the default 896 lanes per SM (7 blocks per SM) and small launches spread over the SMs
     const int nt = g_nt.load();
@@ -572,20 +600,20 @@ static void launch_iterate_mode(const IterParams &p, unsigned long long want, cu
     const unsigned int grid = (unsigned int)((threads + block - 1) / block);
     if (p.attractor_kind == 1u) {            // the cubic family: one instantiation (the knobs above are tuned for AK 0)
         const unsigned int blk = want >= 148ull * 128ull ? 128u : 32u;
-        iterate_kernel<1, MODE, 0, 1><<<(unsigned int)((want + blk - 1) / blk), blk, 0, s>>>(p);
+        iterate_kernel<1, MODE, 0, 1><<<(unsigned int)((want + blk - 1) / blk), blk, smem, s>>>(p);
         return;
     }
     if (g_pipe.load()) {
         switch (nt) {
-        case 1: iterate_kernel<1, MODE, 1, 0><<<grid, block, 0, s>>>(p); break;
-        case 2: iterate_kernel<2, MODE, 1, 0><<<grid, block, 0, s>>>(p); break;
-        default: iterate_kernel<4, MODE, 1, 0><<<grid, block, 0, s>>>(p); break;
+        case 1: iterate_kernel<1, MODE, 1, 0><<<grid, block, smem, s>>>(p); break;
+        case 2: iterate_kernel<2, MODE, 1, 0><<<grid, block, smem, s>>>(p); break;
+        default: iterate_kernel<4, MODE, 1, 0><<<grid, block, smem, s>>>(p); break;
         }
     } else {
         switch (nt) {
-        case 1: iterate_kernel<1, MODE, 0, 0><<<grid, block, 0, s>>>(p); break;
-        case 2: iterate_kernel<2, MODE, 0, 0><<<grid, block, 0, s>>>(p); break;
-        default: iterate_kernel<4, MODE, 0, 0><<<grid, block, 0, s>>>(p); break;
+        case 1: iterate_kernel<1, MODE, 0, 0><<<grid, block, smem, s>>>(p); break;
+        case 2: iterate_kernel<2, MODE, 0, 0><<<grid, block, smem, s>>>(p); break;
+        default: iterate_kernel<4, MODE, 0, 0><<<grid, block, smem, s>>>(p); break;
         }
     }
 }
@@ -599,6 +627,7 @@ void launch_iterate(const IterParams &p, unsigned int lanes, cudaStream_t s)
     case 1: launch_iterate_mode<1>(p, want, s); break;
     case 2: launch_iterate_mode<2>(p, want, s); break;
     case 4: launch_iterate_mode<4>(p, want, s); break;
+    case 5: launch_iterate_mode<5>(p, want, s); break;
     default: launch_iterate_mode<0>(p, want, s); break;
     }
 #else

@@ -29,7 +29,9 @@ ITERS = int(float(os.environ.get("SWEEP_ITERS", "1e9")))
 SMS = torch.cuda.get_device_properties(0).multi_processor_count
 shapes = os.environ.get("SWEEP_SHAPES", "poisson:2048x2048,solar:1800x2000,poisson:4096x4096").split(",")
 modes = [int(m) for m in os.environ.get("SWEEP_MODES", "0,1,4" if DIAG else "0").split(",")]
-NAMES = {0: "product", 1: "arithmetic only", 2: "RED only", 4: "no win path"}
+NAMES = {0: "product", 1: "arithmetic only", 2: "RED only", 4: "no win path", 5: "hot-pixel table cost model"}
+if DIAG and os.environ.get("SWEEP_HOT"):
+    N.check(L.sar_set_option(b"diag_hot", int(os.environ["SWEEP_HOT"])))
 for shape in shapes:
     preset, wh = shape.split(":")
     W, H = (int(v) for v in wh.split("x"))
