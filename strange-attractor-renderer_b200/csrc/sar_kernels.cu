@@ -259,8 +259,10 @@ __device__ __noinline__ unsigned long long classify_rare(const IterParams *Pp, d
 //
 // MODE (only in SAR_DIAGNOSTICS builds; the product library holds MODE 0 alone): 1 = arithmetic
 // only (no memory traffic); 2 = count with a fire-and-forget reduction, no depth test; 4 = the
-// product's atomic with the win path removed.  Modes != 0 leave the Runtime in a state that is
-// only good for timing (tools/sweep_iterate.py).
+// product's atomic with the win path removed; 5 = cost model of a per-SM shared-memory table for
+// hot pixels (a pseudo-random fraction of the hits pays a tag load + two shared-memory atomics
+// instead of the L2 atomic).  Modes != 0 leave the Runtime in a state that is only good for timing
+// (tools/sweep_iterate.py, profiles/r2_iterate_variants.md).
 // ---------------------------------------------------------------------------------------------
 constexpr unsigned int IDX_RARE = 0xFFFFFFFFu;   // candidate that needs classify_rare (W*H <= 2^31, so never a pixel)
 
