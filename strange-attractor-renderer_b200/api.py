@@ -326,7 +326,7 @@ def render(config, runtime: Runtime, initial_points=None) -> None:
     which case it is n successive render() calls, one per point."""
     c = _pod(config)
     n_pts = 1 if initial_points is None else int(np.asarray(initial_points).size // 3)
-    if c.iterations * max(n_pts, 1) >= 1_000_000 and n_pts < 1024:
+    if c.iterations >= 1_000_000 and n_pts < 1024:
         # the reference's render() is ONE serial trajectory (lib.rs:769-837): on a GPU that is one lane out of
         # ~130 000, slower than a CPU core.  Exact, but almost never what a port wants: say so once per process.
         global _warned_serial
