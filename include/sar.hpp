@@ -10,6 +10,8 @@
 //   sar::Runtime::{Runtime(config), reset, merge}                                          lib.rs:660, 682, 708
 //   sar::render(config, runtime), sar::colorize(config, runtime) -> FinalImage             lib.rs:747, 841
 //   sar::ParallelRenderer::{ParallelRenderer(), shutdown}, sar::render_parallel(...)       lib.rs:919, 1020, 1051
+//   sar::PixelFormat, Container, encode_image(runtime, ...), write_image(...)              src/bin/main.rs:40-100
+//   sar::autoframe(config, ...) -> AutoFrame                                               lib.rs:326-334 (the author's TODO)
 #pragma once
 #include <array>
 #include <cstdint>
@@ -175,6 +177,45 @@ inline FinalImage render_parallel(ParallelRenderer &renderer, const Config &conf
     FinalImage img{config.width, config.height, std::vector<uint16_t>(size_t(config.width) * config.height * 4)};
     check(sar_render_parallel(renderer.handle(), &c, jobs_per_thread, seed, nullptr, img.raw.data()));
     return img;
+}
+
+// ---- output conversion + raw encoders (src/bin/main.rs:40-100) ----------------------------------
+enum class PixelFormat { Rgba16 = SAR_PIX_RGBA16, Rgb16 = SAR_PIX_RGB16, Rgba8 = SAR_PIX_RGBA8, Rgb8 = SAR_PIX_RGB8 };
+enum class Container { Raw = SAR_FILE_RAW, Pam = SAR_FILE_PAM, Bmp = SAR_FILE_BMP };
+// the match at main.rs:52-57
+inline PixelFormat pixel_format(bool transparent, bool eight_bit) {
+    return transparent ? (eight_bit ? PixelFormat::Rgba8 : PixelFormat::Rgba16) : (eight_bit ? PixelFormat::Rgb8 : PixelFormat::Rgb16);
+}
+// The image of the last colorize() on `runtime`, converted on the device and wrapped in the container.
+inline std::vector<uint8_t> encode_image(const Runtime &runtime, uint32_t width, uint32_t height, PixelFormat fmt, Container cont) {
+    const size_t n = sar_encoded_size(width, height, uint32_t(fmt), uint32_t(cont));
+    if (n == 0) throw Error(SAR_ERR_UNSUPPORTED, "this pixel format cannot be written in this container (BMP is 8-bit only)");
+    std::vector<uint8_t> out(n);
+    check(sar_runtime_encode(runtime.handle(), uint32_t(fmt), uint32_t(cont), out.data(), out.size(), nullptr));
+    return out;
+}
+inline void write_image(const Runtime &runtime, const Config &config, const std::string &path, bool eight_bit, Container cont) {
+    const auto bytes = encode_image(runtime, config.width, config.height, pixel_format(config.transparent, eight_bit), cont);
+    check(sar_write_file(path.c_str(), bytes.data(), bytes.size()));
+}
+
+// ---- auto-framing first pass (lib.rs:326-334) ----------------------------------------------------
+struct AutoFrame {
+    std::array<double, 6> box;      // screen-space xmin, xmax, ymin, ymax, zmin, zmax (the table of lib.rs:329-333)
+    Vec3 center_camera;
+    double scale;
+    uint64_t diverged, n_jobs;
+    void apply(Config &config) const { config.view.center_camera = center_camera; config.view.scale = scale; }
+};
+inline AutoFrame autoframe(const Config &config, uint64_t n_jobs = 4096, uint64_t iterations = 20'000, uint64_t seed = 0, int device = 0) {
+    const sar_config c = config.to_pod();
+    sar_autoframe_result r;
+    check(sar_autoframe(&c, device, seed, nullptr, n_jobs, iterations, &r));
+    AutoFrame a;
+    for (int i = 0; i < 6; ++i) a.box[i] = r.box[i];
+    a.center_camera = {r.center_camera[0], r.center_camera[1], r.center_camera[2]};
+    a.scale = r.scale; a.diverged = r.diverged; a.n_jobs = r.n_jobs;
+    return a;
 }
 
 }  // namespace sar

@@ -7,13 +7,13 @@
 
 #include "sar.hpp"
 
-static unsigned long long fnv(const std::vector<uint16_t> &v)
+static unsigned long long fnv_bytes(const unsigned char *p, size_t n)
 {
     unsigned long long h = 1469598103934665603ull;
-    const unsigned char *p = reinterpret_cast<const unsigned char *>(v.data());
-    for (size_t i = 0; i < v.size() * 2; ++i) { h ^= p[i]; h *= 1099511628211ull; }
+    for (size_t i = 0; i < n; ++i) { h ^= p[i]; h *= 1099511628211ull; }
     return h;
 }
+static unsigned long long fnv(const std::vector<uint16_t> &v) { return fnv_bytes(reinterpret_cast<const unsigned char *>(v.data()), v.size() * 2); }
 
 int main(int argc, char **argv)
 {
@@ -60,5 +60,17 @@ int main(int argc, char **argv)
     std::printf("PARALLEL threads=%llu hash=%llu px00=%u,%u,%u\n", (unsigned long long)renderer.num_threads(), fnv(img.raw),
                 img.pixel(0, 0)[0], img.pixel(0, 0)[1], img.pixel(0, 0)[2]);
     renderer.shutdown();
+
+    // write_image_matches (main.rs:40-100) and the auto-framing first pass (lib.rs:326-334)
+    cfg.angle = 0.0; cfg.transparent = false;
+    render(cfg, runtime);
+    (void)colorize(cfg, runtime);
+    const std::vector<uint8_t> pam = encode_image(runtime, cfg.width, cfg.height, pixel_format(cfg.transparent, false), Container::Pam);
+    const std::vector<uint8_t> bmp = encode_image(runtime, cfg.width, cfg.height, pixel_format(cfg.transparent, true), Container::Bmp);
+    std::printf("ENCODED pam=%llu bmp=%llu\n", fnv_bytes(pam.data(), pam.size()), fnv_bytes(bmp.data(), bmp.size()));
+    try { (void)encode_image(runtime, cfg.width, cfg.height, PixelFormat::Rgb16, Container::Bmp); std::puts("BMP16_DID_NOT_FAIL"); return 6; }
+    catch (const Error &e) { std::printf("BMP16 code=%d\n", e.code); }
+    const AutoFrame af = autoframe(Config::poisson_saturne(), 1024, 2000, /*seed=*/3);
+    std::printf("AUTOFRAME xmin=%.17g ymax=%.17g diverged=%llu\n", af.box[0], af.box[3], (unsigned long long)af.diverged);
     return 0;
 }

@@ -70,3 +70,14 @@ def test_cpp_mirror_matches_python_api(exe):
     assert lines["PARALLEL"][0]["threads"] == "256"
     assert str(_fnv(img)) == lines["PARALLEL"][0]["hash"]
     pr.shutdown()
+    # encoders and auto-framing through the C++ mirror == through api.py
+    cfg.angle, cfg.transparent = 0.0, False
+    S.render(cfg, rt)
+    S.colorize(cfg, rt)
+    pam = S.encode_image(rt, S.PixelFormat.of(False, False), S.Container.Pam)
+    bmp = S.encode_image(rt, S.PixelFormat.of(False, True), S.Container.Bmp)
+    assert lines["ENCODED"][0] == {"pam": str(_fnv(pam)), "bmp": str(_fnv(bmp))}
+    assert lines["BMP16"][0]["code"] == str(S._native.SAR_ERR_UNSUPPORTED)
+    af = S.autoframe(S.Config.poisson_saturne(), n_jobs=1024, iterations=2000, seed=3)
+    assert float(lines["AUTOFRAME"][0]["xmin"]) == af.box[0] and float(lines["AUTOFRAME"][0]["ymax"]) == af.box[3]
+    assert lines["AUTOFRAME"][0]["diverged"] == str(af.diverged)
