@@ -274,9 +274,17 @@ int  sar_render_sequence(sar_renderer *r, const sar_config *cfg, const double *a
  *                 + samples, 16-bit ones most significant byte first
  *   SAR_FILE_BMP  8-bit formats only (the reference's BmpEncoder panics on a
  *                 16-bit image): BITMAPINFOHEADER 24 bpp / BITMAPV4HEADER 32 bpp
- *                 BI_BITFIELDS, B,G,R[,A], rows bottom-up padded to 4 bytes */
+ *                 BI_BITFIELDS, B,G,R[,A], rows bottom-up padded to 4 bytes
+ *   SAR_FILE_PNG  a complete PNG (main.rs:78-89) WITHOUT the compressor: IHDR, one
+ *                 IDAT whose zlib stream holds the filter-type-0 scanlines in
+ *                 "stored" deflate blocks, IEND.  Decodes to exactly the pixels
+ *                 the reference's PNG decodes to; the file is as large as the raw
+ *                 image (the reference deflates with CompressionType::Default —
+ *                 feed SAR_FILE_RAW bytes to a PNG encoder for that).  Scanline
+ *                 packing and per-chunk CRC-32 / Adler-32 partial sums run on the
+ *                 device; the host folds the sums into the 20 trailing bytes. */
 enum { SAR_PIX_RGBA16 = 0, SAR_PIX_RGB16 = 1, SAR_PIX_RGBA8 = 2, SAR_PIX_RGB8 = 3 };
-enum { SAR_FILE_RAW = 0, SAR_FILE_PAM = 1, SAR_FILE_BMP = 2 };
+enum { SAR_FILE_RAW = 0, SAR_FILE_PAM = 1, SAR_FILE_BMP = 2, SAR_FILE_PNG = 3 };
 /* bytes of one encoded image (header + pixels); 0 for an unsupported combination */
 size_t sar_encoded_size(uint32_t width, uint32_t height, uint32_t pixel_format, uint32_t container);
 /* the container header alone (host only, no GPU); out may be NULL to query header_bytes */

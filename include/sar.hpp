@@ -181,7 +181,7 @@ inline FinalImage render_parallel(ParallelRenderer &renderer, const Config &conf
 
 // ---- output conversion + raw encoders (src/bin/main.rs:40-100) ----------------------------------
 enum class PixelFormat { Rgba16 = SAR_PIX_RGBA16, Rgb16 = SAR_PIX_RGB16, Rgba8 = SAR_PIX_RGBA8, Rgb8 = SAR_PIX_RGB8 };
-enum class Container { Raw = SAR_FILE_RAW, Pam = SAR_FILE_PAM, Bmp = SAR_FILE_BMP };
+enum class Container { Raw = SAR_FILE_RAW, Pam = SAR_FILE_PAM, Bmp = SAR_FILE_BMP, Png = SAR_FILE_PNG };
 // the match at main.rs:52-57
 inline PixelFormat pixel_format(bool transparent, bool eight_bit) {
     return transparent ? (eight_bit ? PixelFormat::Rgba8 : PixelFormat::Rgba16) : (eight_bit ? PixelFormat::Rgb8 : PixelFormat::Rgb16);

@@ -572,8 +572,65 @@ void orc_config_solar_sail(sar_config *c)      /* lib.rs:355-386 */
  *   BMP: 8-bit only; Rgb8 -> BITMAPINFOHEADER (40), Rgba8 -> BITMAPV4HEADER (108) BI_BITFIELDS; BGR(A), bottom-up, rows padded to 4. */
 static size_t put_u16le(uint8_t *p, uint32_t v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); return 2; }
 static size_t put_u32le(uint8_t *p, uint32_t v) { put_u16le(p, v & 0xFFFFu); put_u16le(p + 2, v >> 16); return 4; }
+/* PNG (main.rs:78-89) with the compressor left out: signature, IHDR, one IDAT = zlib stream of "stored" deflate
+ * blocks (RFC 1950 / 1951) around the filter-type-0 scanlines (16-bit samples big-endian, PNG spec), IEND.  CRC-32
+ * and Adler-32 by their bitwise / bytewise definitions. */
+static uint32_t png_crc(const uint8_t *p, size_t n)
+{
+    uint32_t c = 0xFFFFFFFFu;
+    for (size_t i = 0; i < n; ++i) {
+        c ^= p[i];
+        for (int k = 0; k < 8; ++k) c = (c & 1u) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
+    }
+    return c ^ 0xFFFFFFFFu;
+}
+static void be32(uint8_t *p, uint32_t v) { p[0] = (uint8_t)(v >> 24); p[1] = (uint8_t)(v >> 16); p[2] = (uint8_t)(v >> 8); p[3] = (uint8_t)v; }
+static size_t png_encode(const uint16_t *rgba, uint32_t w, uint32_t h, int wide, int alpha, uint8_t *out)
+{
+    const size_t nch = alpha ? 4 : 3, bpp = nch * (wide ? 2 : 1), raw_row = 1 + (size_t)w * bpp, raw_len = raw_row * h;
+    const size_t n_blocks = (raw_len + 65534) / 65535, zlen = 2 + raw_len + 5 * n_blocks + 4;
+    const size_t total = 8 + 25 + 12 + zlen + 12;
+    if (!out) return total;
+    uint8_t *raw = (uint8_t *)malloc(raw_len ? raw_len : 1);
+    for (uint32_t y = 0; y < h; ++y) {
+        uint8_t *r = raw + (size_t)y * raw_row;
+        *r++ = 0;                                              /* filter type 0 */
+        for (uint32_t x = 0; x < w; ++x)
+            for (size_t c = 0; c < nch; ++c) {
+                const uint16_t v = rgba[4 * ((size_t)y * w + x) + c];
+                if (wide) { *r++ = (uint8_t)(v >> 8); *r++ = (uint8_t)v; }
+                else *r++ = (uint8_t)(((uint32_t)v + 128u) / 257u);
+            }
+    }
+    uint8_t *p = out;
+    static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
+    memcpy(p, sig, 8); p += 8;
+    be32(p, 13); memcpy(p + 4, "IHDR", 4); be32(p + 8, w); be32(p + 12, h);
+    p[16] = wide ? 16 : 8; p[17] = alpha ? 6 : 2; p[18] = 0; p[19] = 0; p[20] = 0;
+    be32(p + 21, png_crc(p + 4, 17)); p += 25;
+    be32(p, (uint32_t)zlen); memcpy(p + 4, "IDAT", 4);
+    uint8_t *z = p + 8;
+    z[0] = 0x78; z[1] = 0x01;
+    uint8_t *q = z + 2;
+    uint32_t a = 1, b = 0;
+    for (size_t blk = 0; blk < n_blocks; ++blk) {
+        const size_t first = blk * 65535, len = raw_len - first < 65535 ? raw_len - first : 65535;
+        q[0] = blk + 1 == n_blocks; q[1] = (uint8_t)len; q[2] = (uint8_t)(len >> 8); q[3] = (uint8_t)~len; q[4] = (uint8_t)(~len >> 8);
+        memcpy(q + 5, raw + first, len);
+        q += 5 + len;
+    }
+    for (size_t i = 0; i < raw_len; ++i) { a = (a + raw[i]) % 65521u; b = (b + a) % 65521u; }
+    be32(q, (b << 16) | a); q += 4;
+    be32(q, png_crc(p + 4, 4 + zlen)); q += 4;
+    be32(q, 0); memcpy(q + 4, "IEND", 4); be32(q + 8, png_crc(q + 4, 4));
+    free(raw);
+    return total;
+}
+
 size_t orc_encode(const uint16_t *rgba, uint32_t w, uint32_t h, uint32_t fmt, uint32_t container, uint8_t *out)
 {
+    if (container == SAR_FILE_PNG)
+        return png_encode(rgba, w, h, fmt == SAR_PIX_RGBA16 || fmt == SAR_PIX_RGB16, fmt == SAR_PIX_RGBA16 || fmt == SAR_PIX_RGBA8, out);
     const int wide = fmt == SAR_PIX_RGBA16 || fmt == SAR_PIX_RGB16, alpha = fmt == SAR_PIX_RGBA16 || fmt == SAR_PIX_RGBA8;
     const size_t nch = alpha ? 4 : 3, bpp = nch * (wide ? 2 : 1);
     size_t stride = (size_t)w * bpp, n = 0;

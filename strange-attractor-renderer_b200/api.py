@@ -481,6 +481,7 @@ class Container(enum.Enum):
     Raw = N.SAR_FILE_RAW        # the converted image.as_bytes() alone (feed it to a PNG encoder)
     Pam = N.SAR_FILE_PAM        # --pam, main.rs:62-68
     Bmp = N.SAR_FILE_BMP        # --bmp, main.rs:70-76 (8-bit formats only)
+    Png = N.SAR_FILE_PNG        # the default branch, main.rs:78-89, without the compressor (stored deflate blocks)
 
 
 def encode_image(runtime: Runtime, pixel_format: PixelFormat, container: Container = Container.Raw) -> np.ndarray:
@@ -497,7 +498,7 @@ def encode_image(runtime: Runtime, pixel_format: PixelFormat, container: Contain
 def write_image(runtime: Runtime, path: str, transparent: bool, eight_bit: bool, container: Container) -> str:
     """write_image_matches (main.rs:40-100) for the PAM / BMP branches: convert, set the extension, write."""
     data = encode_image(runtime, PixelFormat.of(transparent, eight_bit), container)
-    ext = {Container.Pam: ".pam", Container.Bmp: ".bmp", Container.Raw: ".raw"}[container]
+    ext = {Container.Pam: ".pam", Container.Bmp: ".bmp", Container.Raw: ".raw", Container.Png: ".png"}[container]
     path = os.path.splitext(path)[0] + ext                       # name.set_extension(..), main.rs:63, 71
     N.check(N.lib().sar_write_file(path.encode(), data.ctypes.data_as(N._u8p), data.size))
     return path

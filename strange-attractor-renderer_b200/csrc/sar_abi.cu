@@ -92,8 +92,10 @@ struct seq_device {                  // per-device pipeline state of sar_render_
                                                     // colourised with ITS max read back by the host and copied out
     uint8_t *stage[2] = {nullptr, nullptr};         // pinned host staging (when the caller gives no frame array)
     size_t stage_bytes = 0;
-    uint8_t *enc[2] = {nullptr, nullptr};           // device: converted pixels (formats other than RGBA16 native)
+    uint8_t *enc[2] = {nullptr, nullptr};           // device: converted pixels (formats other than RGBA16 native) [+ PNG partial sums]
     size_t enc_bytes = 0;
+    uint8_t *h_sums[2] = {nullptr, nullptr};        // pinned: PNG partial checksums of the frame in each slot
+    size_t sums_cap = 0;
     uint32_t *h_max = nullptr;                      // pinned: Runtime.max of the frame in each slot
     cudaEvent_t max_ready[2] = {nullptr, nullptr}, rendered[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr};
     cudaStream_t copy_stream = nullptr;
@@ -1036,6 +1038,7 @@ static void seq_release(sar_renderer *r, size_t d)
     for (int k = 0; k < 2; ++k) {
         sar_runtime_free(q.rt[k]);
         if (q.stage[k]) cudaFreeHost(q.stage[k]);
+        if (q.h_sums[k]) cudaFreeHost(q.h_sums[k]);
         cudaFree(q.enc[k]);
         if (q.max_ready[k]) cudaEventDestroy(q.max_ready[k]);
         if (q.rendered[k]) cudaEventDestroy(q.rendered[k]);
@@ -1212,13 +1215,80 @@ int sar_render_parallel(sar_renderer *r, const sar_config *cfg_in, uint64_t jobs
 struct OutSpec {
     uint32_t fmt = SAR_PIX_RGBA16, container = SAR_FILE_RAW;
     uint32_t order = ORDER_NATIVE;
-    size_t row_stride = 0, payload = 0, header = 0, total = 0;
+    size_t row_stride = 0, payload = 0, header = 0, trailer = 0, total = 0;
     uint8_t head[160] = {0};
+    // PNG only: the raw (filtered scanline) stream, its stored blocks and the partial-checksum chunks
+    size_t raw_row = 0, raw_len = 0, n_blocks = 0, n_crc = 0, n_adler = 0, sums_bytes = 0;
 };
+
+// ---- CRC-32 (PNG / zlib polynomial, reflected) and Adler-32 folding of the device's partial sums -----------
+static uint32_t g_crc_table[256];
+static uint32_t g_crc_shift_chunk[32];          // operator: CRC register after PNG_CHUNK zero bytes, per input bit
+static std::once_flag g_crc_once;
+static uint32_t crc_zero_byte(uint32_t c) { return g_crc_table[c & 0xFFu] ^ (c >> 8); }
+static uint32_t gf2_apply(const uint32_t *mat, uint32_t v)
+{
+    uint32_t r = 0;
+    for (int i = 0; v; v >>= 1, ++i) if (v & 1u) r ^= mat[i];
+    return r;
+}
+static void crc_init()
+{
+    for (uint32_t n = 0; n < 256; ++n) {
+        uint32_t c = n;
+        for (int k = 0; k < 8; ++k) c = (c & 1u) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
+        g_crc_table[n] = c;
+    }
+    uint32_t m[32], sq[32];
+    for (int i = 0; i < 32; ++i) m[i] = crc_zero_byte(1u << i);          // one zero byte
+    for (size_t len = 1; len < PNG_CHUNK; len <<= 1) {                     // square up to PNG_CHUNK (a power of two) zero bytes
+        for (int i = 0; i < 32; ++i) sq[i] = gf2_apply(m, m[i]);
+        memcpy(m, sq, sizeof m);
+    }
+    memcpy(g_crc_shift_chunk, m, sizeof m);
+}
+static uint32_t crc_bytes(uint32_t c, const uint8_t *p, size_t n)          // register update, no pre/post conditioning
+{
+    for (size_t i = 0; i < n; ++i) c = g_crc_table[(c ^ p[i]) & 0xFFu] ^ (c >> 8);
+    return c;
+}
+static void put_be32(uint8_t *p, uint32_t v) { p[0] = (uint8_t)(v >> 24); p[1] = (uint8_t)(v >> 16); p[2] = (uint8_t)(v >> 8); p[3] = (uint8_t)v; }
+// the 20 bytes after the IDAT payload: Adler-32 of the raw stream, CRC-32 of the IDAT chunk, the IEND chunk
+static void png_trailer(const OutSpec &o, const uint8_t *sums, uint8_t *out)
+{
+    std::call_once(g_crc_once, crc_init);
+    const uint32_t *crc_part = reinterpret_cast<const uint32_t *>(sums);
+    const unsigned long long *ad = reinterpret_cast<const unsigned long long *>(sums + align_up(o.n_crc * 4, 8));
+    // Adler-32 (zlib): a = 1 + sum d, b = sum of the running a, both mod 65521
+    unsigned long long a = 1, b = 0;
+    for (size_t i = 0; i < o.n_adler; ++i) {
+        const size_t len = (i + 1) * PNG_CHUNK <= o.raw_len ? PNG_CHUNK : o.raw_len - i * PNG_CHUNK;
+        b = (b + (unsigned long long)len * a + ad[2 * i + 1]) % 65521ull;
+        a = (a + ad[2 * i]) % 65521ull;
+    }
+    const uint32_t adler = (uint32_t)((b << 16) | a);
+    // CRC-32 over "IDAT" + zlib header + payload + Adler-32: linear in (register, data), so the register is advanced over
+    // each chunk with the precomputed zero-bytes operator and the chunk's own contribution is XORed in
+    const uint8_t pre[6] = {'I', 'D', 'A', 'T', 0x78, 0x01};
+    uint32_t c = crc_bytes(0xFFFFFFFFu, pre, 6);
+    for (size_t i = 0; i < o.n_crc; ++i) {
+        const size_t len = (i + 1) * PNG_CHUNK <= o.payload ? PNG_CHUNK : o.payload - i * PNG_CHUNK;
+        if (len == PNG_CHUNK) c = gf2_apply(g_crc_shift_chunk, c);
+        else for (size_t k = 0; k < len; ++k) c = crc_zero_byte(c);
+        c ^= crc_part[i];
+    }
+    uint8_t ab[4];
+    put_be32(ab, adler);
+    c = crc_bytes(c, ab, 4) ^ 0xFFFFFFFFu;
+    memcpy(out, ab, 4);
+    put_be32(out + 4, c);
+    const uint8_t iend[12] = {0, 0, 0, 0, 'I', 'E', 'N', 'D', 0xAE, 0x42, 0x60, 0x82};
+    memcpy(out + 8, iend, 12);
+}
 static int make_outspec(uint32_t w, uint32_t h, uint32_t fmt, uint32_t container, OutSpec &o)
 {
     if (fmt > SAR_PIX_RGB8) return fail(SAR_ERR_INVALID, "pixel_format %u", fmt);
-    if (container > SAR_FILE_BMP) return fail(SAR_ERR_INVALID, "container %u", container);
+    if (container > SAR_FILE_PNG) return fail(SAR_ERR_INVALID, "container %u", container);
     const bool wide = fmt == SAR_PIX_RGBA16 || fmt == SAR_PIX_RGB16, alpha = fmt == SAR_PIX_RGBA16 || fmt == SAR_PIX_RGBA8;
     const size_t bpp = (alpha ? 4 : 3) * (wide ? 2 : 1);
     o.fmt = fmt; o.container = container;
@@ -1254,7 +1324,35 @@ static int make_outspec(uint32_t w, uint32_t h, uint32_t fmt, uint32_t container
         o.header = (size_t)(p - o.head);
     }
     o.payload = o.row_stride * h;
-    o.total = o.header + o.payload;
+    o.trailer = 0;
+    if (container == SAR_FILE_PNG) {
+        // signature, IHDR, then ONE IDAT chunk holding a zlib stream of stored blocks (no compression)
+        std::call_once(g_crc_once, crc_init);
+        o.order = wide ? ORDER_BIG_ENDIAN : ORDER_NATIVE;
+        o.raw_row = 1 + (size_t)w * bpp;
+        o.raw_len = o.raw_row * h;
+        o.n_blocks = (o.raw_len + 65534) / 65535;
+        o.payload = o.raw_len + 5 * o.n_blocks;
+        if (2 + o.payload + 4 > 0x7FFFFFFFull) return fail(SAR_ERR_INVALID, "image too large for one IDAT chunk");
+        o.n_crc = (o.payload + PNG_CHUNK - 1) / PNG_CHUNK;
+        o.n_adler = (o.raw_len + PNG_CHUNK - 1) / PNG_CHUNK;
+        o.sums_bytes = align_up(o.n_crc * 4, 8) + o.n_adler * 16;
+        uint8_t *p = o.head;
+        const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
+        memcpy(p, sig, 8); p += 8;
+        put_be32(p, 13); p += 4;
+        uint8_t *ihdr = p;
+        memcpy(p, "IHDR", 4); p += 4;
+        put_be32(p, w); p += 4; put_be32(p, h); p += 4;
+        *p++ = wide ? 16 : 8; *p++ = alpha ? 6 : 2; *p++ = 0; *p++ = 0; *p++ = 0;      // bit depth, colour type, deflate, adaptive, no interlace
+        put_be32(p, crc_bytes(0xFFFFFFFFu, ihdr, 17) ^ 0xFFFFFFFFu); p += 4;
+        put_be32(p, (uint32_t)(2 + o.payload + 4)); p += 4;
+        memcpy(p, "IDAT", 4); p += 4;
+        *p++ = 0x78; *p++ = 0x01;                                                       // zlib header: deflate, 32 K window, no dictionary
+        o.header = (size_t)(p - o.head);
+        o.trailer = 20;
+    }
+    o.total = o.header + o.payload + o.trailer;
     return SAR_OK;
 }
 
@@ -1287,12 +1385,24 @@ int sar_runtime_encode(sar_runtime *rt, uint32_t pixel_format, uint32_t containe
     if (out_bytes < o.total) return fail(SAR_ERR_INVALID, "output needs %zu bytes (got %zu)", o.total, out_bytes);
     SAR_CUDA(cudaSetDevice(rt->device));
     cudaStream_t s = pick(rt, stream);
-    if (int rc = ensure_scratch(rt, o.payload)) return rc;
-    launch_convert(rt->image, (uint8_t *)rt->d_scratch, rt->w, rt->h, o.fmt, o.order, o.row_stride, s);
-    SAR_CUDA(cudaGetLastError());
+    const size_t sums_off = align_up(o.payload, 256);
+    if (int rc = ensure_scratch(rt, sums_off + o.sums_bytes)) return rc;
+    uint8_t *d_pay = (uint8_t *)rt->d_scratch;
+    std::vector<uint8_t> sums(o.sums_bytes);
+    if (o.container == SAR_FILE_PNG) {
+        launch_png_pack(rt->image, d_pay, rt->w, rt->h, o.fmt, o.raw_row, o.raw_len, o.n_blocks, s);
+        launch_png_sums(d_pay, o.payload, o.raw_len, (uint32_t *)(d_pay + sums_off),
+                        (unsigned long long *)(d_pay + sums_off + align_up(o.n_crc * 4, 8)), o.n_crc, o.n_adler, s);
+        SAR_CUDA(cudaGetLastError());
+        SAR_CUDA(cudaMemcpyAsync(sums.data(), d_pay + sums_off, o.sums_bytes, cudaMemcpyDeviceToHost, s));
+    } else {
+        launch_convert(rt->image, d_pay, rt->w, rt->h, o.fmt, o.order, o.row_stride, s);
+        SAR_CUDA(cudaGetLastError());
+    }
     memcpy(out, o.head, o.header);
-    SAR_CUDA(cudaMemcpyAsync(out + o.header, rt->d_scratch, o.payload, cudaMemcpyDeviceToHost, s));
+    SAR_CUDA(cudaMemcpyAsync(out + o.header, d_pay, o.payload, cudaMemcpyDeviceToHost, s));
     SAR_CUDA(cudaStreamSynchronize(s));
+    if (o.container == SAR_FILE_PNG) png_trailer(o, sums.data(), out + o.header + o.payload);
     return SAR_OK;
 }
 
@@ -1330,11 +1440,17 @@ static int seq_prepare(sar_renderer *r, size_t d, const sar_config &cfg, bool ne
             q.stage[k] = nullptr;
             SAR_CUDA(cudaHostAlloc((void **)&q.stage[k], o.total, cudaHostAllocPortable));
         }
-        const bool convert = !(o.fmt == SAR_PIX_RGBA16 && o.order == ORDER_NATIVE);
-        if (convert && (!q.enc[k] || q.enc_bytes < o.payload)) {
+        const bool convert = !(o.fmt == SAR_PIX_RGBA16 && o.order == ORDER_NATIVE) || o.container == SAR_FILE_PNG;
+        const size_t enc_need = align_up(o.payload, 256) + o.sums_bytes;
+        if (convert && (!q.enc[k] || q.enc_bytes < enc_need)) {
             cudaFree(q.enc[k]);
             q.enc[k] = nullptr;
-            SAR_CUDA(cudaMalloc((void **)&q.enc[k], o.payload));
+            SAR_CUDA(cudaMalloc((void **)&q.enc[k], enc_need));
+        }
+        if (o.sums_bytes && (!q.h_sums[k] || q.sums_cap < o.sums_bytes)) {
+            if (q.h_sums[k]) cudaFreeHost(q.h_sums[k]);
+            q.h_sums[k] = nullptr;
+            SAR_CUDA(cudaHostAlloc((void **)&q.h_sums[k], o.sums_bytes, cudaHostAllocPortable));
         }
         if (!q.max_ready[k]) SAR_CUDA(cudaEventCreateWithFlags(&q.max_ready[k], cudaEventDisableTiming));
         if (!q.rendered[k]) SAR_CUDA(cudaEventCreateWithFlags(&q.rendered[k], cudaEventDisableTiming));
@@ -1342,7 +1458,9 @@ static int seq_prepare(sar_renderer *r, size_t d, const sar_config &cfg, bool ne
     }
     // capacities of what was (re)allocated above
     if (need_stage && q.stage_bytes < o.total) q.stage_bytes = o.total;
-    if (!(o.fmt == SAR_PIX_RGBA16 && o.order == ORDER_NATIVE) && q.enc_bytes < o.payload) q.enc_bytes = o.payload;
+    if ((!(o.fmt == SAR_PIX_RGBA16 && o.order == ORDER_NATIVE) || o.container == SAR_FILE_PNG) &&
+        q.enc_bytes < align_up(o.payload, 256) + o.sums_bytes) q.enc_bytes = align_up(o.payload, 256) + o.sums_bytes;
+    if (o.sums_bytes && q.sums_cap < o.sums_bytes) q.sums_cap = o.sums_bytes;
     return SAR_OK;
 }
 
@@ -1354,7 +1472,8 @@ static int sequence_core(sar_renderer *r, const sar_config *cfg_in, const double
     if (!r || !cfg_in || (!angles_rad && n_frames)) return fail(SAR_ERR_INVALID, "NULL argument");
     if (!frames_out && !cb16 && !cb8) return fail(SAR_ERR_INVALID, "need a frame array or a callback");
     uint8_t *const rgba_frames = frames_out;
-    const bool convert = !(o.fmt == SAR_PIX_RGBA16 && o.order == ORDER_NATIVE);
+    const bool png = o.container == SAR_FILE_PNG;
+    const bool convert = !(o.fmt == SAR_PIX_RGBA16 && o.order == ORDER_NATIVE) || png;
     if (jobs_per_thread == 0) return fail(SAR_ERR_INVALID, "jobs_per_thread must be non-zero");
     if (flags & ~SAR_SEQ_SHARED_POINTS) return fail(SAR_ERR_INVALID, "unknown flags 0x%x", flags);
     if (int rc = check_config(cfg_in, nullptr)) return rc;
@@ -1393,7 +1512,8 @@ static int sequence_core(sar_renderer *r, const sar_config *cfg_in, const double
         const int slot = (int)((g / nd) % 2);
         SAR_CUDA(cudaSetDevice(r->devices[d]));
         SAR_CUDA(cudaEventSynchronize(r->seq[d].copied[slot]));
-        const uint8_t *bytes = rgba_frames ? rgba_frames + (size_t)g * frame_u16 : r->seq[d].stage[slot];
+        uint8_t *bytes = rgba_frames ? rgba_frames + (size_t)g * frame_u16 : r->seq[d].stage[slot];
+        if (png) png_trailer(o, r->seq[d].h_sums[slot], bytes + o.header + o.payload);   // Adler-32, IDAT CRC, IEND
         if (cb16) cb16(user, g, reinterpret_cast<const uint16_t *>(bytes));
         if (cb8) cb8(user, g, bytes, o.total);
         return SAR_OK;
@@ -1421,7 +1541,13 @@ static int sequence_core(sar_renderer *r, const sar_config *cfg_in, const double
         SAR_CUDA(cudaStreamWaitEvent(cs, q.copied[slot], 0));                   // the slot's previous image has left the device
         launch_colorize(cp, rt->fast, rt->rec, rt->scal, rt->image, nullptr, cs);           // colorize, lib.rs:1080
         SAR_CUDA(cudaGetLastError());
-        if (convert) {                                                          // main.rs:52-57 on the device
+        const size_t sums_off = align_up(o.payload, 256);
+        if (png) {                                                              // main.rs:78-89 minus the compressor
+            launch_png_pack(rt->image, q.enc[slot], rt->w, rt->h, o.fmt, o.raw_row, o.raw_len, o.n_blocks, cs);
+            launch_png_sums(q.enc[slot], o.payload, o.raw_len, (uint32_t *)(q.enc[slot] + sums_off),
+                            (unsigned long long *)(q.enc[slot] + sums_off + align_up(o.n_crc * 4, 8)), o.n_crc, o.n_adler, cs);
+            SAR_CUDA(cudaGetLastError());
+        } else if (convert) {                                                   // main.rs:52-57 on the device
             launch_convert(rt->image, q.enc[slot], rt->w, rt->h, o.fmt, o.order, o.row_stride, cs);
             SAR_CUDA(cudaGetLastError());
         }
@@ -1434,6 +1560,7 @@ static int sequence_core(sar_renderer *r, const sar_config *cfg_in, const double
         memcpy(dst, o.head, o.header);
         SAR_CUDA(cudaMemcpyAsync(dst + o.header, convert ? (const void *)q.enc[slot] : (const void *)rt->image, o.payload,
                                  cudaMemcpyDeviceToHost, q.copy_stream));
+        if (png) SAR_CUDA(cudaMemcpyAsync(q.h_sums[slot], q.enc[slot] + sums_off, o.sums_bytes, cudaMemcpyDeviceToHost, q.copy_stream));
         SAR_CUDA(cudaEventRecord(q.copied[slot], q.copy_stream));
         return SAR_OK;
     };

@@ -138,6 +138,13 @@ void launch_convert(const uint16_t *rgba, uint8_t *out, unsigned int W, unsigned
 struct BBoxAccum { unsigned long long lo[3], hi[3], diverged; };
 void launch_bbox(const IterParams &p, BBoxAccum *acc, cudaStream_t s);
 
+// PNG with stored deflate blocks: payload writer and per-chunk partial checksums (sar_kernels.cu)
+constexpr size_t PNG_CHUNK = 4096;
+void launch_png_pack(const uint16_t *rgba, uint8_t *out, unsigned int W, unsigned int H, unsigned int fmt, size_t raw_row,
+                     size_t raw_len, size_t n_blocks, cudaStream_t s);
+void launch_png_sums(const uint8_t *payload, size_t payload_len, size_t raw_len, uint32_t *crc, unsigned long long *adler,
+                     size_t n_crc, size_t n_adler, cudaStream_t s);
+
 // launchers (sar_kernels.cu); every one bumps the launch counter
 void launch_reset(unsigned long long *fast, ulonglong2 *rec, Scalars *scal, size_t npix, size_t nslots, cudaStream_t s);
 void launch_iterate(const IterParams &p, unsigned int lanes, cudaStream_t s);

@@ -999,6 +999,94 @@ void launch_convert(const uint16_t *rgba, uint8_t *out, unsigned int W, unsigned
 }
 
 // ---------------------------------------------------------------------------------------------
+// PNG (main.rs:78-89) without the compressor: the converted image as filter-type-0 scanlines inside
+// zlib "stored" deflate blocks — a valid PNG any decoder reads back to the same pixels; the
+// reference's encoder additionally deflates (png::CompressionType::Default), which stays on the host.
+// The device writes the IDAT payload (block headers + scanlines, 16-bit samples big-endian) and the
+// per-chunk partial checksums the host folds into the zlib Adler-32 and the chunk CRC-32.
+//   raw stream  : for each row  [0x00 filter byte][W * bpp sample bytes]
+//   payload     : raw stream cut into blocks of <= 65535 bytes, each behind [BFINAL, LEN lo, hi, ~LEN lo, hi]
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ inline size_t png_payload_offset(size_t k) { return k + 5 * (k / 65535 + 1); }
+
+__global__ void png_pack_kernel(const ushort4 *__restrict__ img, uint8_t *__restrict__ out, unsigned int W, unsigned int H,
+                                unsigned int fmt, size_t raw_row, size_t raw_len, size_t n_blocks)
+{
+    const size_t npix = (size_t)W * H;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const bool wide = fmt == PIX_RGBA16 || fmt == PIX_RGB16, alpha = fmt == PIX_RGBA16 || fmt == PIX_RGBA8;
+    const unsigned int nch = alpha ? 4u : 3u, bpp = nch * (wide ? 2u : 1u);
+    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += stride) {
+        const ushort4 v = img[p];
+        const unsigned int y = (unsigned int)(p / W), x = (unsigned int)(p - (size_t)y * W);
+        const uint16_t c[4] = {v.x, v.y, v.z, v.w};
+        size_t k = (size_t)y * raw_row;
+        if (x == 0) out[png_payload_offset(k)] = 0;                          // filter type 0 (None)
+        k += 1 + (size_t)x * bpp;
+        for (unsigned int ch = 0; ch < nch; ++ch) {
+            if (wide) {
+                out[png_payload_offset(k)] = (uint8_t)(c[ch] >> 8); ++k;    // most significant byte first
+                out[png_payload_offset(k)] = (uint8_t)c[ch]; ++k;
+            } else {
+                out[png_payload_offset(k)] = (uint8_t)narrow_u16(c[ch]); ++k;
+            }
+        }
+        if (p < n_blocks) {                                                  // the stored-block headers
+            const size_t first = p * 65535;
+            const size_t len = raw_len - first < 65535 ? raw_len - first : 65535;
+            uint8_t *hd = out + first + 5 * p;
+            hd[0] = p + 1 == n_blocks ? 1 : 0;
+            hd[1] = (uint8_t)len; hd[2] = (uint8_t)(len >> 8); hd[3] = (uint8_t)~len; hd[4] = (uint8_t)(~len >> 8);
+        }
+    }
+}
+// Partial checksums over chunks of PNG_CHUNK bytes: crc[i] = CRC-32 register after chunk i of the PAYLOAD starting
+// from register 0 (no pre/post conditioning: the linear part, combined on the host); adler[i] = (sum d, sum (len - j) d_j)
+// over chunk i of the RAW stream.
+__global__ void png_sums_kernel(const uint8_t *__restrict__ payload, size_t payload_len, size_t raw_len,
+                                uint32_t *__restrict__ crc, unsigned long long *__restrict__ adler, size_t n_crc, size_t n_adler)
+{
+    __shared__ uint32_t table[256];
+    for (unsigned int n = threadIdx.x; n < 256; n += blockDim.x) {
+        uint32_t c = n;
+        for (int k = 0; k < 8; ++k) c = (c & 1u) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
+        table[n] = c;
+    }
+    __syncthreads();
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n_crc) {
+        const size_t lo = t * PNG_CHUNK, hi = lo + PNG_CHUNK < payload_len ? lo + PNG_CHUNK : payload_len;
+        uint32_t c = 0;
+        for (size_t i = lo; i < hi; ++i) c = table[(c ^ payload[i]) & 0xFFu] ^ (c >> 8);
+        crc[t] = c;
+    }
+    if (t < n_adler) {
+        const size_t lo = t * PNG_CHUNK, hi = lo + PNG_CHUNK < raw_len ? lo + PNG_CHUNK : raw_len;
+        unsigned long long a = 0, b = 0;
+        for (size_t k = lo; k < hi; ++k) { a += payload[png_payload_offset(k)]; b += a; }   // b = sum over j of (hi - lo - j) d_j
+        adler[2 * t] = a; adler[2 * t + 1] = b;
+    }
+}
+void launch_png_pack(const uint16_t *rgba, uint8_t *out, unsigned int W, unsigned int H, unsigned int fmt, size_t raw_row,
+                     size_t raw_len, size_t n_blocks, cudaStream_t s)
+{
+    const size_t npix = (size_t)W * H;
+    if (npix == 0) return;
+    const unsigned int block = 256;
+    size_t g = (npix + block - 1) / block;
+    png_pack_kernel<<<(unsigned int)(g > 148u * 16u ? 148u * 16u : g), block, 0, s>>>(reinterpret_cast<const ushort4 *>(rgba), out, W, H, fmt, raw_row, raw_len, n_blocks);
+    ++g_launches;
+}
+void launch_png_sums(const uint8_t *payload, size_t payload_len, size_t raw_len, uint32_t *crc, unsigned long long *adler,
+                     size_t n_crc, size_t n_adler, cudaStream_t s)
+{
+    const size_t n = n_crc > n_adler ? n_crc : n_adler;
+    if (n == 0) return;
+    png_sums_kernel<<<(unsigned int)((n + 127) / 128), 128, 0, s>>>(payload, payload_len, raw_len, crc, adler, n_crc, n_adler);
+    ++g_launches;
+}
+
+// ---------------------------------------------------------------------------------------------
 // layout conversion to / from the reference's three textures (lib.rs:633-639)
 // ---------------------------------------------------------------------------------------------
 __global__ void unpack_kernel(const unsigned long long *fast, const ulonglong2 *rec, const Scalars *scal, size_t npix, SlotMap slots,

@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 
 FORMATS = [0, 1, 2, 3]           # SAR_PIX_RGBA16, RGB16, RGBA8, RGB8
-CONTAINERS = [0, 1, 2]           # SAR_FILE_RAW, PAM, BMP
+CONTAINERS = [0, 1, 2, 3]        # SAR_FILE_RAW, PAM, BMP, PNG (stored deflate)
 
 
 def test_headers_and_sizes_match_the_oracle(oracle):
@@ -20,7 +20,7 @@ def test_headers_and_sizes_match_the_oracle(oracle):
 
     L = N.lib()
     rng = np.random.default_rng(5)
-    for (w, h) in [(1, 1), (3, 2), (5, 7), (450, 501), (2048, 2048)]:
+    for (w, h) in [(1, 1), (3, 2), (5, 7), (450, 501), (2048, 2048), (9000, 3)]:
         img = rng.integers(0, 65536, (h, w, 4), dtype=np.uint16) if w * h < 10_000 else np.zeros((h, w, 4), np.uint16)
         for fmt in FORMATS:
             for cont in CONTAINERS:
@@ -42,6 +42,33 @@ def test_headers_and_sizes_match_the_oracle(oracle):
     N.check(L.sar_encode_header(12, 34, 1, 1, buf.ctypes.data_as(N._u8p), 160, C.byref(hb)))
     assert bytes(buf[:hb.value]) == b"P7\nWIDTH 12\nHEIGHT 34\nDEPTH 3\nMAXVAL 65535\nTUPLTYPE RGB\nENDHDR\n"
     assert L.sar_encoded_size(12, 34, 9, 0) == 0 and L.sar_encoded_size(0, 4, 0, 0) == 0
+
+
+def test_oracle_png_decodes_to_the_converted_pixels(oracle):
+    """The stored-deflate PNG (oracle side) is a valid PNG: Pillow / zlib read back exactly the converted samples."""
+    import io
+    import zlib
+
+    from PIL import Image
+
+    rng = np.random.default_rng(7)
+    img = rng.integers(0, 65536, (37, 53, 4), dtype=np.uint16)
+    for fmt, mode, nch in ((2, "RGBA", 4), (3, "RGB", 3)):
+        png = oracle.encode(img, fmt, 3)
+        got = np.asarray(Image.open(io.BytesIO(png.tobytes())).convert(mode))
+        want = ((img[..., :nch].astype(np.uint32) + 128) // 257).astype(np.uint8)
+        assert np.array_equal(got, want)
+    # 16-bit: Pillow has no 16-bit RGB(A) mode, so inflate the IDAT by hand and compare the big-endian scanlines
+    for fmt, nch in ((0, 4), (1, 3)):
+        png = oracle.encode(img, fmt, 3).tobytes()
+        assert png[:8] == b"\x89PNG\r\n\x1a\n" and png[12:16] == b"IHDR" and png[24] == 16 and png[25] == (6 if nch == 4 else 2)
+        n = int.from_bytes(png[33:37], "big")
+        assert png[37:41] == b"IDAT" and zlib.crc32(png[37:41 + n]) == int.from_bytes(png[41 + n:45 + n], "big")
+        raw = zlib.decompress(png[41:41 + n])
+        rows = np.frombuffer(raw, np.uint8).reshape(37, 1 + 53 * nch * 2)
+        assert (rows[:, 0] == 0).all()
+        assert np.array_equal(rows[:, 1:].reshape(37, 53, nch, 2).astype(np.uint16) @ np.array([256, 1], np.uint16), img[..., :nch])
+        assert png[-12:] == b"\x00\x00\x00\x00IEND\xaeB`\x82"
 
 
 def test_u16_to_u8_rule_is_round_to_nearest(oracle):
@@ -75,6 +102,18 @@ def test_device_conversion_matches_oracle_bytes(oracle):
                     continue
                 got = S.encode_image(rt, fmt, cont)
                 assert np.array_equal(got, ref), (fmt, cont, int((got != ref).sum()))
+    # a frame wider than one stored deflate block (65 535 bytes): PNG scanlines straddle block boundaries
+    wide = S.Config.poisson_saturne()
+    wide.width, wide.height, wide.iterations = 8300, 5, 2_000
+    wrt = S.Runtime.new(wide)
+    S.render(wide, wrt, initial_points=S.seed_points(2, 0, 64))
+    wimg = S.colorize(wide, wrt)
+    assert np.array_equal(S.encode_image(wrt, S.PixelFormat.Rgba16, S.Container.Png), oracle.encode(wimg, 0, 3))
+    import io
+    from PIL import Image
+    png8 = S.encode_image(rt, S.PixelFormat.Rgba8, S.Container.Png)
+    assert np.array_equal(np.asarray(Image.open(io.BytesIO(png8.tobytes())).convert("RGBA")),
+                          ((S.colorize(cfg, rt).astype(np.uint32) + 128) // 257).astype(np.uint8))
     # known answer of the reference's published image: pixel (0,0), RGB16 big-endian in a PAM
     cfg.transparent = False
     S.colorize(cfg, rt)
@@ -93,7 +132,8 @@ def test_encoded_sequence_equals_per_frame_encoding(oracle, tmp_path):
     angles = S.angle_iter(0.0, 60.0, 20.0)
     r = S.ParallelRenderer.new(threads=128)
     plain = S.render_sequence(r, cfg, angles, 1, seed=3)
-    for fmt, cont in ((S.PixelFormat.Rgb8, S.Container.Bmp), (S.PixelFormat.Rgba16, S.Container.Pam), (S.PixelFormat.Rgb16, S.Container.Raw)):
+    for fmt, cont in ((S.PixelFormat.Rgb8, S.Container.Bmp), (S.PixelFormat.Rgba16, S.Container.Pam), (S.PixelFormat.Rgb16, S.Container.Raw),
+                      (S.PixelFormat.Rgba16, S.Container.Png), (S.PixelFormat.Rgb8, S.Container.Png)):
         enc = S.render_sequence_encoded(r, cfg, angles, 1, fmt, cont, seed=3)
         seen = []
         S.render_sequence_encoded(r, cfg, angles, 1, fmt, cont, seed=3, callback=lambda f, b: seen.append((f, b.copy())))
