@@ -1268,6 +1268,9 @@ __global__ void frame_export_kernel(const unsigned long long *fast, Scalars *sca
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += stride)
         cnt[i] = pixel_count(fast, scal, i, slots);
+    // the iterate kernel left this rank's own running max here; the merge reduces the max of the MERGED stripe
+    // into the same word, so start it from 0 (the local value is a lower bound of the merged one, but be exact by construction)
+    if (blockIdx.x == 0 && threadIdx.x == 0) scal->max = 0u;
     if (frame_last_block(&scal->done_counter[0])) frame_signal(S, SYNC_RENDER_DONE, true, -1);
 }
 void launch_frame_export(const unsigned long long *fast, Scalars *scal, uint32_t *cnt, size_t npix, SlotMap slots,
