@@ -23,6 +23,7 @@ PY
 }
 for n in 1 2 4 8; do run $n weak; done
 for n in 2 4 8; do run $n strong --scaling strong --no-parity; done
-for n in 4 8; do run $n strong_halflanes --scaling strong --no-parity --lanes 66304; done
 # BASELINE configs[3]: poisson-saturne, 8e9 iterations, 4096x4096, 8 GPUs row-striped
 run 8 cfg3_4096 --size 4096x4096 --no-parity
+# BASELINE configs[4]: 360-frame solar-sail sweep, 1e8 iterations per frame, frames round-robin over the GPUs of one process
+timeout 300 python tools/seq_bench.py 360 2>&1 | grep cfg4
