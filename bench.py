@@ -192,7 +192,7 @@ def parity_frame(world, rank, local, group, preset="solar", depth=False, per_gpu
         ocfg = cfg.to_pod()
         ocfg.iterations = frame.iterations_per_job
         ort = O.Runtime(w, h)
-        O.render_jobs_mt(ocfg, ort, O.seed_points(seed, 0, lanes * jpt * world))
+        O.render_jobs_mt(ocfg, ort, O.seed_points(seed, 0, frame.lanes * jpt * world))
         oimg = O.colorize(ocfg, ort)
         d = np.abs(img.astype(np.int32) - oimg.astype(np.int32))
         checks = {
@@ -204,7 +204,7 @@ def parity_frame(world, rank, local, group, preset="solar", depth=False, per_gpu
             "image": bool(d.max() == 0) if ort.max + 1 < (1 << 20) else bool(d.max() <= 1 and (d > 0).mean() < 1e-4),
             "image_exact": bool(d.max() == 0),
             "vs": "oracle",
-            "frame": f"{preset}{' depth' if depth else ''} {w}x{h}, {world} rank(s) x {lanes * jpt} jobs x {frame.iterations_per_job} iterations",
+            "frame": f"{preset}{' depth' if depth else ''} {w}x{h}, {world} rank(s) x {frame.lanes * jpt} jobs x {frame.iterations_per_job} iterations",
             "recorded": int(ort.count.sum(dtype=np.uint64)), "max": int(ort.max),
         }
     if rank == 0:
