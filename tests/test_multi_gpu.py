@@ -30,6 +30,17 @@ def test_n_rank_frame_equals_oracle(preset, kind, world):
     assert r.returncode == 0 and "DIST_CHECK_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
 
 
+def test_baseline_cfg3_full_size_8_ranks_equals_oracle():
+    """BASELINE configs[3] itself: poisson-saturne, 8e9 iterations, 4096x4096, 8 ranks row-striped — count, zbuf, steps and
+    image against the oracle (about a minute of host time for the oracle's 9e9 steps)."""
+    if _gpu_count() < 8:
+        pytest.skip("needs 8 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "8", "--master-addr", "127.0.0.1",
+           "--master-port", "29547", os.path.join(ROOT, "tools", "dist_check.py"), "poisson", "gas", "full"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0 and "DIST_CHECK_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
 def test_in_process_two_device_renderer_equals_one_device():
     """ParallelRenderer over two devices in ONE process (frames' jobs split by device, merged by
     peer copy) gives the image and buffers of one device running the same num_threads."""
