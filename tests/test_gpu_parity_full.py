@@ -91,3 +91,26 @@ def test_more_than_2_pow_23_pixels_layout(S, oracle):
     n, per_job, st, count, mx = _check_frame(S, oracle, cfg, seed=99)
     # the frame is wider than tall, so part of the attractor falls outside it (lib.rs:789)
     assert 0.5 * n * per_job < st.recorded == int(count.sum(dtype=np.uint64)) < n * per_job
+
+
+def test_baseline_cfg4_sequence_frames_full_size(S, oracle):
+    """BASELINE configs[4]: frames of the solar-sail angle sweep at full size (1e8 iterations per frame, 2048x2048,
+    default lanes, fresh start points per frame as the reference draws them) through sar_render_sequence — every
+    frame's RGBA16 image equals the oracle's colorize bit for bit although max (the NaN sink) is far beyond the
+    host-libm ln table."""
+    cfg = S.Config.solar_sail()
+    cfg.width, cfg.height, cfg.iterations, cfg.transparent = 2048, 2048, 100_000_000, True
+    angles = S.angle_iter(0.0, 360.0, 120.0)                      # 0, 120, 240 degrees of the 360-frame sweep
+    r = S.ParallelRenderer.new()
+    n, per_job = r.plan(cfg.iterations, 1)
+    frames = S.render_sequence(r, cfg, angles, 1, seed=7)
+    ocfg = cfg.to_pod()
+    ocfg.iterations = per_job
+    for f, a in enumerate(angles):
+        ocfg.angle = a
+        ort = oracle.Runtime(2048, 2048)
+        oracle.render_jobs_mt(ocfg, ort, oracle.seed_points(7, f * n, n))
+        assert ort.max >= (1 << 20)
+        d = frames[f].astype(np.int32) - oracle.colorize(ocfg, ort).astype(np.int32)
+        assert not d.any(), f"frame {f}: {(d != 0).sum()} values differ"
+    r.shutdown()
