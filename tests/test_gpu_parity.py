@@ -493,3 +493,38 @@ def test_sequence_frames_are_exact_beyond_the_ln_table(S, oracle):
         d = np.abs(frames[f].astype(np.int32) - oracle.colorize(ocfg, ort).astype(np.int32))
         assert d.max() == 0, f"frame {f}: {(d > 0).sum()} values differ"
     r.shutdown()
+
+
+def test_cross_gpu_wait_times_out_instead_of_hanging(S):
+    """A rank whose peers never signal (a dead process) must cost a timeout, not a hung GPU or a frame computed from
+    half-delivered data: the wait records sync_error, later protocol kernels of that Runtime do nothing,
+    and the error can be read and cleared."""
+    L = S._native.lib()
+    cfg = _small(S.Config.poisson_saturne(), 64, 64, 100)
+    rt = S.Runtime.new(cfg)
+    err = C.c_uint32(7)
+    S._native.check(L.sar_runtime_sync_error(rt._h, C.byref(err), 0))
+    assert err.value == 0
+    S._native.check(L.sar_set_option(b"sync_timeout_ms", 50))
+    try:
+        S._native.check(L.sar_frame_image_wait_async(rt._h, 2, 5, None))      # waits for IMAGE_DONE(5) from 2 ranks: never comes
+        S._native.check(L.sar_stream_synchronize(rt._h, None))
+        S._native.check(L.sar_runtime_sync_error(rt._h, C.byref(err), 0))
+        assert err.value == 1 + 3, "IMAGE_DONE is event kind 3"
+        # a later kernel of the protocol on this Runtime is a no-op: the accumulators stay as they are
+        S.render(cfg, rt, initial_points=S.seed_points(1, 0, 8))
+        before = rt.download()[0].copy()
+        assert before.sum() == 8 * 100
+        S._native.check(L.sar_frame_reset_async(rt._h, 1, 6, None))            # would zero the accumulators
+        S._native.check(L.sar_stream_synchronize(rt._h, None))
+        assert np.array_equal(rt.download()[0], before), "a protocol kernel ran on a Runtime whose wait had failed"
+        S._native.check(L.sar_runtime_sync_error(rt._h, C.byref(err), 1))      # read and clear
+        assert err.value == 4
+        S._native.check(L.sar_runtime_sync_error(rt._h, C.byref(err), 0))
+        assert err.value == 0
+    finally:
+        S._native.check(L.sar_set_option(b"sync_timeout_ms", 10_000))
+    # with the error cleared the protocol works again (a 1-rank frame: reset waits for nothing new)
+    S._native.check(L.sar_frame_reset_async(rt._h, 1, 1, None))
+    S._native.check(L.sar_stream_synchronize(rt._h, None))
+    assert rt.download()[0].sum() == 0
