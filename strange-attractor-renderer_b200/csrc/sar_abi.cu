@@ -273,6 +273,10 @@ int sar_set_option(const char *name, int64_t value)
         set_sync_timeout_ms(value);
         return SAR_OK;
     }
+    if (strcmp(name, "tile_scatter") == 0) {
+        if (!set_tile_scatter((int)value)) return fail(SAR_ERR_INVALID, "tile_scatter must be 0 or 1");
+        return SAR_OK;
+    }
     if (strcmp(name, "pipeline") == 0) {
         if (!set_pipeline((int)value)) return fail(SAR_ERR_INVALID, "pipeline must be 0 or 1");
         return SAR_OK;
@@ -560,7 +564,7 @@ static int render_launch(const sar_config *cfg, sar_runtime *rt, const double *d
         return fail(SAR_ERR_INVALID, "job order keys exhausted (%llu jobs since the last reset, 2^32 at most): reset or "
                     "download/upload the Runtime", (unsigned long long)rt->job_base);
     p.job_key0 = (unsigned int)rt->job_base;
-    launch_iterate(p, threads ? threads : default_lanes(rt), s);
+    if (launch_iterate(p, threads ? threads : default_lanes(rt), s)) rt->max_tracked = false;   // tile path: max by reduction
     SAR_CUDA(cudaGetLastError());
     rt->host_max_valid = false;
     rt->depth_valid = false;

@@ -54,6 +54,9 @@ constexpr uint32_t ZKEY_FLT_MAX  = 0xFF7FFFFFu;   // zkey(f32::MAX)
 constexpr unsigned long long FAST_RESET = (unsigned long long)(ZKEY_SENTINEL + 1u) << 32;  // count 0, hint just above the sentinel
 constexpr unsigned long long REC_HI_RESET = ((unsigned long long)ZKEY_SENTINEL << 32) | 0xFFFFFFFFull;
 
+constexpr unsigned int TILE_BLOCK = 896;                 // lanes of a tile-path block (one block per SM)
+constexpr size_t TILE_SMEM_MAX = 200 * 1024;             // shared memory a tile may take: W*H*8 bytes -> up to 25 600 pixels
+
 constexpr int SYNC_MAX_RANKS = 16;
 enum SyncKind {                       // what a flag announces (see sar_runtime_signal_async)
     SYNC_RENDER_DONE = 0,             // rank r's trajectories of this frame are all in its accumulators
@@ -147,7 +150,8 @@ void launch_png_sums(const uint8_t *payload, size_t payload_len, size_t raw_len,
 
 // launchers (sar_kernels.cu); every one bumps the launch counter
 void launch_reset(unsigned long long *fast, ulonglong2 *rec, Scalars *scal, size_t npix, size_t nslots, cudaStream_t s);
-void launch_iterate(const IterParams &p, unsigned int lanes, cudaStream_t s);
+// returns true when the shared-memory tile path ran (small images; Runtime.max then needs the full reduction)
+bool launch_iterate(const IterParams &p, unsigned int lanes, cudaStream_t s);
 // the warm-up alone (lib.rs:748-752): start points -> states after p.warmup steps, out[3*job..]
 void launch_warm(const IterParams &p, double *out, cudaStream_t s);
 void launch_fold_max(const unsigned long long *fast, Scalars *scal, SlotMap slots, cudaStream_t s);
@@ -186,6 +190,7 @@ bool set_mode(int mode);     // SAR_DIAGNOSTICS builds only: 0 = product path; 1
 void set_diag_hot(int per_1024);
 int get_diag_hot();
 #endif
+bool set_tile_scatter(int on);      // 1 (default): images that fit a shared-memory tile use per-block private histograms
 bool set_pipeline(int on);          // tuning: depth test one iteration behind its atomic (0/1); never changes results
 bool set_traj_per_thread(int nt);   // tuning: trajectories carried per thread (1, 2 or 4); never changes results
 

@@ -185,7 +185,7 @@ __device__ __forceinline__ double transform_ds(const IterParams &P, double dx, d
 // are ordered with rec_order(), which folds the two zeros again.
 __device__ __forceinline__ void record_win(const IterParams &P, unsigned int idx, uint32_t key, uint32_t job_inv,
                                            unsigned long long old, double dx, double dy, double dz,
-                                           double sx, double sy, double sz)
+                                           double sx, double sy, double sz, bool raise_hint = true)
 {
     unsigned long long hi = ((unsigned long long)key << 32) | job_inv;
     if (key == ZKEY_ZERO) {
@@ -205,7 +205,7 @@ __device__ __forceinline__ void record_win(const IterParams &P, unsigned int idx
     // Best-effort raise of the hint so later candidates below this z skip this path: one
     // compare-and-swap against the value our own atomic produced, result ignored.  If other hits
     // landed in between it fails and the hint stays low, which only costs a later visit here.
-    {
+    if (raise_hint) {
         const unsigned long long expect = old + 1ull;
         const unsigned long long want = ((unsigned long long)key << 32) | (expect & 0xFFFFFFFFull);
         if ((uint32_t)(expect >> 32) < key) (void)atomicCAS(P.fast + slot_of(idx, P.slots), expect, want);
@@ -221,9 +221,9 @@ __device__ __forceinline__ void record_win(const IterParams &P, unsigned int idx
 
 __device__ __noinline__ void record_win_call(const IterParams *Pp, unsigned int idx, uint32_t key, uint32_t job_inv,
                                              unsigned long long old, double dx, double dy, double dz,
-                                             double sx, double sy, double sz)
+                                             double sx, double sy, double sz, bool raise_hint)
 {
-    record_win(*Pp, idx, key, job_inv, old, dx, dy, dz, sx, sy, sz);
+    record_win(*Pp, idx, key, job_inv, old, dx, dy, dz, sx, sy, sz, raise_hint);
 }
 
 // Everything that is not a plain in-view hit: out of view, non-finite coordinates, and the
@@ -280,10 +280,29 @@ struct Cand {
 // other warps alone — with NT lanes per thread there are only 3-4 warps per scheduler.  Within a
 // lane tests still retire in iteration order and before the next atomic is issued, so exact z ties
 // keep resolving to the earlier iteration.
-template <int NT, int MODE, int PIPE, int AK>
-__global__ void __launch_bounds__(128 / NT, (NT == 1 && AK == 0) ? (PIPE ? 5 : 7) : (NT == 1 ? 4 : 8))   // register budgets: 7 x 128 / 5 x 128 / 8 x 64 / 8 x 32 threads per SM
+//
+// TILE = 1 — the north star's "per-block count tiles in shared memory before a global atomicAdd reduction", for
+// images that FIT a tile (W*H*8 bytes of shared memory, i.e. up to 25 600 pixels: thumbnails and previews; one block of
+// 896 lanes per SM).  Every block keeps a private (count u32, z max u32) pair per pixel in shared memory, seeded with
+// the pixel's global depth hint; a hit is two shared-memory atomics (ATOMS.ADD + ATOMS.MAX) instead of one L2 atomic
+// — on such small images the L2 path serialises on a few thousand addresses (64x64: 30 G it/s) —, a hit that reaches
+// the block's running max is a depth-test candidate and goes through the same exact record path (128-bit CAS on
+// (zkey, ~job)), and at the end the block adds its counts and max-es its hints into the global arrays.  Exact for the
+// same reasons as the L2 path: counts commute; a hit that is the global winner of its pixel is >= every earlier hit
+// of its own block, so it always reaches the record path, which alone decides.
+template <int NT, int MODE, int PIPE, int AK, int TILE>
+__global__ void __launch_bounds__(TILE ? TILE_BLOCK : 128 / NT, TILE ? 1 : ((NT == 1 && AK == 0) ? (PIPE ? 5 : 7) : (NT == 1 ? 4 : 8)))   // register budgets: 7 x 128 / 5 x 128 / 8 x 64 / 8 x 32 threads per SM
 iterate_kernel(const __grid_constant__ IterParams P)
 {
+    extern __shared__ unsigned int s_tile[];                                  // TILE: count[npix] | zmax[npix]
+    const unsigned int npix = P.W * P.H;
+    if (TILE) {
+        for (unsigned int p = threadIdx.x; p < npix; p += blockDim.x) {
+            s_tile[p] = 0u;
+            s_tile[npix + p] = (uint32_t)(P.fast[slot_of(p, P.slots)] >> 32);   // the pixel's current hint (canonical key)
+        }
+        __syncthreads();
+    }
     const unsigned long long nthreads = (unsigned long long)gridDim.x * blockDim.x;
     const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t cmax = 0u;                                                       // greatest count this thread's hits produced (lib.rs:813-815)
@@ -375,6 +394,14 @@ iterate_kernel(const __grid_constant__ IterParams P)
                     }
                 }
                 unsigned long long *slot = P.fast + slot_of(c[k].idx, P.slots);
+                if (TILE) {
+                    if (!hit) { c[k].key = 0u; c[k].idx = IDX_RARE; c[k].old = ~0ull; }
+                    else {
+                        const unsigned int before = atomicAdd(&s_tile[c[k].idx], 1u);                 // count += 1, lib.rs:811
+                        const unsigned int zbefore = atomicMax(&s_tile[npix + c[k].idx], c[k].key);   // the block's running z max
+                        c[k].old = ((unsigned long long)zbefore << 32) | before;
+                    }
+                } else
 #ifdef SAR_DIAGNOSTICS
                 if (MODE == 5) {
                     // cost model of a per-SM shared-memory table for hot pixels: a pseudo-random P.diag_hot / 1024 of the
@@ -412,14 +439,14 @@ iterate_kernel(const __grid_constant__ IterParams P)
         auto test = [&](Cand (&c)[NT], auto inl) {
 #pragma unroll
             for (int k = 0; k < NT; ++k) {
-                if ((MODE == 0 || MODE == 5) && c[k].idx != IDX_RARE) {       // count after this hit; the running max of lib.rs:813-815
+                if ((MODE == 0 || MODE == 5) && !TILE && c[k].idx != IDX_RARE) {   // count after this hit; the running max of lib.rs:813-815
                     const uint32_t now = (uint32_t)c[k].old + 1u;
                     cmax = now > cmax ? now : cmax;
                 }
                 if (c[k].key >= (uint32_t)(c[k].old >> 32) && c[k].key != 0u) {      // may beat zbuf
                     if (MODE != 0 && MODE != 5) { if (c[k].idx == 0xFFFFFFF0u) P.scal->pad = c[k].key; }   // diagnostics: keep the returned value live
-                    else if (decltype(inl)::value) record_win(P, c[k].idx, c[k].key, job_inv[k], c[k].old, c[k].dx, c[k].dy, c[k].dz, c[k].sx, c[k].sy, c[k].sz);
-                    else record_win_call(&P, c[k].idx, c[k].key, job_inv[k], c[k].old, c[k].dx, c[k].dy, c[k].dz, c[k].sx, c[k].sy, c[k].sz);
+                    else if (decltype(inl)::value) record_win(P, c[k].idx, c[k].key, job_inv[k], c[k].old, c[k].dx, c[k].dy, c[k].dz, c[k].sx, c[k].sy, c[k].sz, !TILE);
+                    else record_win_call(&P, c[k].idx, c[k].key, job_inv[k], c[k].old, c[k].dx, c[k].dy, c[k].dz, c[k].sx, c[k].sy, c[k].sz, !TILE);
                 }
             }
         };
@@ -451,6 +478,21 @@ iterate_kernel(const __grid_constant__ IterParams P)
                 arith(A); scatter(A, it); test(A, inl_t{});
             }
         }
+    }
+    if (TILE) {
+        // the block's tile -> the global arrays: one 32-bit add on the count half and one 32-bit max on the hint half of
+        // every pixel this block touched (the hint stays <= the recorded key: every hit that raised the block's max went
+        // through record_win first)
+        __syncthreads();
+        for (unsigned int p = threadIdx.x; p < npix; p += blockDim.x) {
+            const unsigned int c = s_tile[p];
+            if (c) {
+                unsigned int *w = reinterpret_cast<unsigned int *>(P.fast + slot_of(p, P.slots));
+                atomicAdd(w, c);
+                atomicMax(w + 1, s_tile[npix + p]);
+            }
+        }
+        return;                                       // Runtime.max: the host runs the full reduction after a tile launch
     }
     // Runtime.max, kept current by the render itself: one reduction per warp (lanes leave the job loop together,
     // except NaN jobs, hence the active mask), not 132 608 same-address atomics
@@ -586,14 +628,39 @@ bool set_mode(int m)
 bool set_mode(int m) { return m == 0; }
 #endif
 
+static std::atomic<int> g_tile{1};
+bool set_tile_scatter(int on)
+{
+    if (on != 0 && on != 1) return false;
+    g_tile = on;
+    return true;
+}
+// a tile launch needs the whole image in one block's shared memory and at least one full block of lanes
+static bool tile_fits(const IterParams &p, unsigned long long want)
+{
+    return g_tile.load() && (size_t)p.W * p.H * 8 <= TILE_SMEM_MAX && want >= TILE_BLOCK;
+}
+
 template <int MODE>
-static void launch_iterate_mode(const IterParams &p, unsigned long long want, cudaStream_t s)
+static bool launch_iterate_mode(const IterParams &p, unsigned long long want, cudaStream_t s)
 {
 #ifdef SAR_DIAGNOSTICS
     const size_t smem = MODE == 5 ? (size_t)p.diag_tab_entries * 12 : 0;
 #else
     const size_t smem = 0;
 #endif
+    if (MODE == 0 && tile_fits(p, want)) {       // the image fits a shared-memory tile: per-block private histograms
+        const size_t tsm = (size_t)p.W * p.H * 8;
+        const unsigned int grid = (unsigned int)((want + TILE_BLOCK - 1) / TILE_BLOCK);
+        if (p.attractor_kind == 1u) {
+            cudaFuncSetAttribute(iterate_kernel<1, 0, 0, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM_MAX);
+            iterate_kernel<1, 0, 0, 1, 1><<<grid, TILE_BLOCK, tsm, s>>>(p);
+        } else {
+            cudaFuncSetAttribute(iterate_kernel<1, 0, 0, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM_MAX);
+            iterate_kernel<1, 0, 0, 0, 1><<<grid, TILE_BLOCK, tsm, s>>>(p);
+        }
+        return true;
+    }
     // `want` lanes; NT lanes per thread; narrow blocks so that the grid stays a multiple of the SM
     // count at the default 896 lanes per SM (7 blocks per SM) and small launches spread over the SMs
     const int nt = g_nt.load();
@@ -602,40 +669,44 @@ static void launch_iterate_mode(const IterParams &p, unsigned long long want, cu
     const unsigned int grid = (unsigned int)((threads + block - 1) / block);
     if (p.attractor_kind == 1u) {            // the cubic family: one instantiation (the knobs above are tuned for AK 0)
         const unsigned int blk = want >= 148ull * 128ull ? 128u : 32u;
-        iterate_kernel<1, MODE, 0, 1><<<(unsigned int)((want + blk - 1) / blk), blk, smem, s>>>(p);
-        return;
+        iterate_kernel<1, MODE, 0, 1, 0><<<(unsigned int)((want + blk - 1) / blk), blk, smem, s>>>(p);
+        return false;
     }
     if (g_pipe.load()) {
         switch (nt) {
-        case 1: iterate_kernel<1, MODE, 1, 0><<<grid, block, smem, s>>>(p); break;
-        case 2: iterate_kernel<2, MODE, 1, 0><<<grid, block, smem, s>>>(p); break;
-        default: iterate_kernel<4, MODE, 1, 0><<<grid, block, smem, s>>>(p); break;
+        case 1: iterate_kernel<1, MODE, 1, 0, 0><<<grid, block, smem, s>>>(p); break;
+        case 2: iterate_kernel<2, MODE, 1, 0, 0><<<grid, block, smem, s>>>(p); break;
+        default: iterate_kernel<4, MODE, 1, 0, 0><<<grid, block, smem, s>>>(p); break;
         }
     } else {
         switch (nt) {
-        case 1: iterate_kernel<1, MODE, 0, 0><<<grid, block, smem, s>>>(p); break;
-        case 2: iterate_kernel<2, MODE, 0, 0><<<grid, block, smem, s>>>(p); break;
-        default: iterate_kernel<4, MODE, 0, 0><<<grid, block, smem, s>>>(p); break;
+        case 1: iterate_kernel<1, MODE, 0, 0, 0><<<grid, block, smem, s>>>(p); break;
+        case 2: iterate_kernel<2, MODE, 0, 0, 0><<<grid, block, smem, s>>>(p); break;
+        default: iterate_kernel<4, MODE, 0, 0, 0><<<grid, block, smem, s>>>(p); break;
         }
     }
+    return false;
 }
 
-void launch_iterate(const IterParams &p, unsigned int lanes, cudaStream_t s)
+// returns true when the launch used the shared-memory tile path (Runtime.max is then not tracked by the kernel)
+bool launch_iterate(const IterParams &p, unsigned int lanes, cudaStream_t s)
 {
-    if (p.n_jobs == 0) return;
+    if (p.n_jobs == 0) return false;
     const unsigned long long want = p.n_jobs < lanes ? p.n_jobs : lanes;
+    bool tile = false;
 #ifdef SAR_DIAGNOSTICS
     switch (g_mode.load()) {
-    case 1: launch_iterate_mode<1>(p, want, s); break;
-    case 2: launch_iterate_mode<2>(p, want, s); break;
-    case 4: launch_iterate_mode<4>(p, want, s); break;
-    case 5: launch_iterate_mode<5>(p, want, s); break;
-    default: launch_iterate_mode<0>(p, want, s); break;
+    case 1: tile = launch_iterate_mode<1>(p, want, s); break;
+    case 2: tile = launch_iterate_mode<2>(p, want, s); break;
+    case 4: tile = launch_iterate_mode<4>(p, want, s); break;
+    case 5: tile = launch_iterate_mode<5>(p, want, s); break;
+    default: tile = launch_iterate_mode<0>(p, want, s); break;
     }
 #else
-    launch_iterate_mode<0>(p, want, s);
+    tile = launch_iterate_mode<0>(p, want, s);
 #endif
     ++g_launches;
+    return tile;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -528,3 +528,68 @@ def test_cross_gpu_wait_times_out_instead_of_hanging(S):
     S._native.check(L.sar_frame_reset_async(rt._h, 1, 1, None))
     S._native.check(L.sar_stream_synchronize(rt._h, None))
     assert rt.download()[0].sum() == 0
+
+
+def test_tile_scatter_path_is_bit_exact(S, oracle):
+    """Images that fit a shared-memory tile (W*H <= 25 600 pixels) with at least one full block of lanes take the
+    per-block privatised histogram path (the north star's scatter).  Same bar as the L2 path: count,
+    zbuf, steps and image equal the oracle's — incl. NaN trajectories, out-of-view points, a 1x1 image, Depth, a
+    progressive mix of tile and L2 launches on one Runtime, and the cubic attractor."""
+    L = S._native.lib()
+    cases = [
+        (S.Config.poisson_saturne(), 64, 64, 400, 2000, {}),
+        (S.Config.solar_sail(), 120, 100, 300, 3000, {"angle": 220.0 * math.pi / 180.0}),      # NaN sink
+        (S.Config.poisson_saturne(), 1, 1, 50, 1000, {}),
+        (S.Config.poisson_saturne(), 160, 160, 200, 1500, {"scale": 5.0}),                     # the largest tile; mostly out of view
+        (S.Config.solar_sail(), 97, 131, 250, 1000, {"depth": True}),
+    ]
+    for base, w, h, iters, jobs, opt in cases:
+        cfg = _small(base, w, h, iters)
+        cfg.angle = opt.get("angle", 0.3)
+        if "scale" in opt:
+            cfg.view.scale = opt["scale"]
+        if opt.get("depth"):
+            cfg.render = S.RenderKind.Depth
+        pts = S.seed_points(40 + w, 0, jobs)
+        rt = S.Runtime.new(cfg)
+        S.render(cfg, rt, initial_points=pts)
+        ort, st = _oracle_state(oracle, cfg, pts)
+        _assert_state_equal(rt.download(), ort)
+        img, f32 = S.colorize(cfg, rt, want_f32=True)
+        oimg, of64 = oracle.colorize(cfg.to_pod(), ort, want_f64=True)
+        _assert_image_close(img, f32, oimg, of64)
+        # the knob: the L2 path on the same job list gives the same bytes
+        S._native.check(L.sar_set_option(b"tile_scatter", 0))
+        try:
+            rt2 = S.Runtime.new(cfg)
+            S.render(cfg, rt2, initial_points=pts)
+            for a, b in zip(rt.download()[:3], rt2.download()[:3]):
+                assert np.array_equal(a.view(np.uint8), b.view(np.uint8))
+        finally:
+            S._native.check(L.sar_set_option(b"tile_scatter", 1))
+    # progressive: tile launch, then a small launch (L2 path: fewer than 896 jobs), then a tile launch again; max tracked across them
+    cfg = _small(S.Config.poisson_saturne(), 100, 80, 300)
+    a, b, c = S.seed_points(1, 0, 1200), S.seed_points(2, 0, 40), S.seed_points(3, 0, 900)
+    rt = S.Runtime.new(cfg)
+    for pts in (a, b, c):
+        S.render(cfg, rt, initial_points=pts)
+    ort, _ = _oracle_state(oracle, cfg, np.concatenate([a, b, c]))
+    _assert_state_equal(rt.download(), ort)
+    assert np.array_equal(S.colorize(cfg, rt), oracle.colorize(cfg.to_pod(), ort))
+    # just above the tile limit: 161 x 160 pixels go the L2 way (and still match)
+    cfg = _small(S.Config.poisson_saturne(), 161, 160, 100)
+    pts = S.seed_points(9, 0, 1000)
+    rt = S.Runtime.new(cfg)
+    S.render(cfg, rt, initial_points=pts)
+    ort, _ = _oracle_state(oracle, cfg, pts)
+    _assert_state_equal(rt.download(), ort)
+    # the cubic attractor kind has a tile instantiation too
+    base = S.Config.poisson_saturne()
+    cfg = _small(S.Config.poisson_saturne(), 90, 90, 200)
+    cfg.attractor = S.attractors.PolynomialSprott3Degree(base.attractor.x, base.attractor.y, base.attractor.z,
+                                                         [-0.05] + [0.0] * 9, [0.0] * 10, [0.0] * 9 + [-0.05])
+    pts = S.seed_points(4, 0, 1000)
+    rt = S.Runtime.new(cfg)
+    S.render(cfg, rt, initial_points=pts)
+    ort, _ = _oracle_state(oracle, cfg, pts)
+    _assert_state_equal(rt.download(), ort)
