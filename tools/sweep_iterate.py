@@ -3,7 +3,7 @@
     python tools/sweep_iterate.py            # product library
     SWEEP_DIAG=1 python tools/sweep_iterate.py   # libsar_b200_diag.so: also mode 1 (arithmetic only) and 4 (no win path)
 
-env: SWEEP_NT=1,2,4  SWEEP_PIPE=0,1  SWEEP_LANES=768,896,1024  SWEEP_SHAPES=poisson:2048x2048,solar:1800x2000,poisson:4096x4096
+env: SWEEP_NT=1,2,4  SWEEP_PIPE=0,1  SWEEP_TILE=0|1 (shared-memory tile scatter for small images off / on)  SWEEP_LANES=768,896,1024  SWEEP_SHAPES=poisson:2048x2048,solar:1800x2000,poisson:4096x4096
      SWEEP_ITERS=1e9  SWEEP_MODES=0,1,4 (diag only)
 Prints the median of 3 launches as G recorded iterations/s (warm-up steps excluded)."""
 import ctypes as C
@@ -30,6 +30,8 @@ SMS = torch.cuda.get_device_properties(0).multi_processor_count
 shapes = os.environ.get("SWEEP_SHAPES", "poisson:2048x2048,solar:1800x2000,poisson:4096x4096").split(",")
 modes = [int(m) for m in os.environ.get("SWEEP_MODES", "0,1,4" if DIAG else "0").split(",")]
 NAMES = {0: "product", 1: "arithmetic only", 2: "RED only", 4: "no win path", 5: "hot-pixel table cost model"}
+if os.environ.get("SWEEP_TILE"):
+    N.check(L.sar_set_option(b"tile_scatter", int(os.environ["SWEEP_TILE"])))
 if DIAG and os.environ.get("SWEEP_HOT"):
     N.check(L.sar_set_option(b"diag_hot", int(os.environ["SWEEP_HOT"])))
 for shape in shapes:
