@@ -123,7 +123,10 @@ int         sar_default_threads(int device, uint32_t *threads);
 /* Options.  Tuning knobs of the iterate kernel that never change results
  * (DESIGN.md §5): "traj_per_thread" (1, 2 or 4) — how many trajectories one GPU
  * thread carries side by side; "pipeline" (0 / 1) — make the depth test of an
- * iteration after the arithmetic of the next one.  "diagnostic_mode": the product library accepts only 0;
+ * iteration after the arithmetic of the next one; "tile_scatter" (0 / 1, default
+ * 1) — images of at most 25 600 pixels accumulate in per-block shared-memory
+ * tiles that are added into the global buffers at the end of the launch;
+ * "sync_timeout_ms" — see the frame protocol below.  "diagnostic_mode": the product library accepts only 0;
  * the roofline-experiment variants of the iterate kernel (incomplete results by
  * design) exist only in the separately built libsar_b200_diag.so
  * (-DSAR_DIAGNOSTICS, tools/sweep_iterate.py) — SAR_ERR_UNSUPPORTED here. */

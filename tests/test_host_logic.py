@@ -114,6 +114,8 @@ def test_product_library_has_no_diagnostic_kernels():
     assert L.sar_set_option(b"traj_per_thread", 1) == 0
     assert L.sar_set_option(b"pipeline", 1) == 0 and L.sar_set_option(b"pipeline", 2) == N.SAR_ERR_INVALID
     assert L.sar_set_option(b"pipeline", 0) == 0
+    assert L.sar_set_option(b"tile_scatter", 0) == 0 and L.sar_set_option(b"tile_scatter", 2) == N.SAR_ERR_INVALID
+    assert L.sar_set_option(b"tile_scatter", 1) == 0
     syms = subprocess.run(["cuobjdump", "-symbols", N.LIB_PATH], capture_output=True, text=True).stdout
     kernels = sorted({w for line in syms.splitlines() if "STO_ENTRY" in line for w in line.split() if "iterate_kernel" in w})
     assert kernels and all("ELi0ELi" in k for k in kernels)   # iterate_kernel<NT, MODE = 0, PIPE>, kernels
