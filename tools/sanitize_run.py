@@ -30,6 +30,13 @@ for nt, pipe in ((1, 0), (2, 1), (4, 0)):
                 pass
 S._native.check(L.sar_set_option(b"traj_per_thread", 1))
 S._native.check(L.sar_set_option(b"pipeline", 0))
+# the shared-memory tile path: an image that fits a tile, more than one block of jobs, NaN trajectories included
+tcfg = S.Config.solar_sail()
+tcfg.width, tcfg.height, tcfg.iterations, tcfg.angle = 120, 100, 400, 1.0
+trt = S.Runtime.new(tcfg)
+S.render(tcfg, trt, initial_points=S.seed_points(8, 0, 2500))
+S.colorize(tcfg, trt)
+tile_hits = int(trt.download()[0].sum())
 af = S.autoframe(cfg, n_jobs=500, iterations=500, seed=2)
 r = S.ParallelRenderer.new(threads=128)
 cfg.iterations = 600_000
@@ -44,4 +51,4 @@ rt = S.Runtime.new(base)
 S.render(base, rt, initial_points=S.seed_points(1, 0, 100))
 S.colorize(base, rt)
 r.shutdown()
-print("sanitize tour done", int(count.sum()), af.diverged, frames.shape, enc.shape, one.shape)
+print("sanitize tour done", tile_hits, int(count.sum()), af.diverged, frames.shape, enc.shape, one.shape)
