@@ -593,3 +593,39 @@ def test_tile_scatter_path_is_bit_exact(S, oracle):
     S.render(cfg, rt, initial_points=pts)
     ort, _ = _oracle_state(oracle, cfg, pts)
     _assert_state_equal(rt.download(), ort)
+
+
+def test_randomised_tile_configs_bit_exact(S, oracle):
+    """The randomised sweep of test_randomised_configs_bit_exact on images that fit a shared-memory tile with enough
+    jobs to take the tile path (>= 896): shapes, scale, camera, angle, rotation, transforms, palettes, perturbed
+    coefficients (some diverge), Depth — state and RGBA16 image must equal the oracle's."""
+    rng = np.random.default_rng(20261018)
+    for case in range(10):
+        base = S.Config.poisson_saturne() if case % 2 == 0 else S.Config.solar_sail()
+        w = int(rng.integers(1, 161))
+        h = int(rng.integers(1, max(2, min(161, 25_600 // w + 1))))
+        assert w * h <= 25_600
+        cfg = _small(base, w, h, int(rng.integers(1, 400)))
+        cfg.angle = float(rng.uniform(-7.0, 7.0))
+        cfg.view.scale = float(rng.choice([0.3, 1.0, 1.7, 4.0]))
+        cfg.view.center_camera.x += float(rng.normal(0, 0.05))
+        cfg.view.rotation.rotation = float(rng.uniform(0, 6.3))
+        cfg.transparent = bool(rng.integers(0, 2))
+        if case % 3 == 0:
+            cfg.color_transform = S.color_transforms.AdjustedVelocity(offset=float(rng.uniform(-0.2, 0.5)), factor=float(rng.uniform(0.5, 3.0)))
+        if case % 4 == 1:
+            cfg.color_transform = S.color_transforms.ScreenBlend([float(v) for v in rng.uniform(-1, 1, 4)], offset=0.3, factor=0.8)
+        if case >= 5:
+            for lst in (cfg.attractor.x, cfg.attractor.y, cfg.attractor.z):
+                lst[int(rng.integers(0, 10))] += float(rng.normal(0, 0.02))
+        if case == 9:
+            cfg.render = S.RenderKind.Depth
+        pts = S.seed_points(2000 + case, 0, int(rng.integers(896, 2500)))
+        rt = S.Runtime.new(cfg)
+        S.render(cfg, rt, initial_points=pts)
+        ort, _ = _oracle_state(oracle, cfg, pts)
+        _assert_state_equal(rt.download(), ort)
+        img, f32 = S.colorize(cfg, rt, want_f32=True)
+        oimg, of64 = oracle.colorize(cfg.to_pod(), ort, want_f64=True)
+        _assert_image_close(img, f32, oimg, of64)
+        rt.close()
