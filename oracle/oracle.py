@@ -1,7 +1,8 @@
 """ctypes loader for the CPU oracle (oracle/sar_oracle.c).  TEST INFRASTRUCTURE ONLY.
 
-Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
-legs may import this module.  The product package never does.
+Only tests/, __graft_entry__.smoke() and bench.py (cpu_baseline / --impl reference legs, and the
+N-rank parity frames it checks outside every timed region) may import this module.  The product
+package never does.
 """
 from __future__ import annotations
 

@@ -1,9 +1,10 @@
 /* sar_oracle.h — CPU restatement of the reference's render path.  TEST INFRASTRUCTURE ONLY.
  *
  * This is the oracle the CUDA path is checked against.  It is NOT part of the
- * product: only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
- * `--impl reference` legs may build, load or call it.  libsar_b200.so never
- * links or calls anything in this directory.
+ * product: only tests/, __graft_entry__.smoke() and bench.py — its cpu_baseline /
+ * `--impl reference` legs and the N-rank parity frames it checks outside every
+ * timed region — may build, load or call it.  libsar_b200.so never links or
+ * calls anything in this directory.
  *
  * It restates, function by function, `src/lib.rs` of Icelk/strange-attractor-
  * renderer @ e571d19 (citations below are into that file), with Rust's
