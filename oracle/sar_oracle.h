@@ -19,18 +19,21 @@
  * no lockfile).  Every entry point therefore takes the start point(s)
  * explicitly.
  *
- * Pinning (see oracle/README.md, tests/test_oracle_golden.py): the reference's
- * own tests hold no numeric vector for this path (one doctest that only builds
- * a Config, lib.rs:9-15).  The oracle is pinned against the reference's
- * published material instead: the bounding-box known-answer comment
- * (lib.rs:329-333), pixel (0,0) of the two solar-sail PNGs (exact values of the
- * NaN path), and block-level correlation with the three media PNG images.
- * The Rust toolchain is absent here, so `oracle/_ref` (the compiled reference)
- * cannot be built and the reference cannot be run on seeded inputs: in the strict
- * sense this oracle is "parity unpinned" by reference-run outputs.  What pins it
- * is the reference's PUBLISHED outputs (the three images its README commands
- * produced — statistically, their seeds being unknown), two exact known answers,
- * and a second independent restatement (tests/pyref.py) that agrees bit for bit.
+ * Pinning (see oracle/README.md, tests/test_reference_images.py, tests/test_oracle_golden.py): the
+ * reference's own tests hold no numeric vector for this path (one doctest that only builds a
+ * Config, lib.rs:9-15), the Rust toolchain is absent here (no `oracle/_ref`), and the reference
+ * seeds itself from the OS, so it cannot be run on given inputs at all.  What it does publish is
+ * three output images (the PNGs under media, README.md:72-77), and the oracle is pinned on those pixel by
+ * pixel: colorize is inverted on every fully informative pixel (2 133 250), recovering integer
+ * count, palette position and Runtime.max such that lib.rs:853-868 returns the PNG's 16-bit channels
+ * EXACTLY (orc_colorize gives the sampled pixels back bit for bit); the recovered count field equals
+ * the oracle's own 1e9-iteration render at Poisson noise per pixel (chi-square 0.99-1.01; one pixel
+ * of shift: > 60), the recovered palette positions equal the oracle's `steps` (median 1e-5), and
+ * solar-sail's max is k x (1e9/12/12), the render_parallel decomposition feeding the NaN sink.
+ * In the strict sense of "reference run here on seeded inputs" the oracle remains unpinned — the
+ * reference has no seeded mode; a `>` vs `>=` on a z tie is below the noise floor of its outputs.
+ * Also: the bounding-box known answer (lib.rs:329-333), and a second independent restatement
+ * (tests/pyref.py) that agrees bit for bit.
  */
 #ifndef SAR_ORACLE_H
 #define SAR_ORACLE_H

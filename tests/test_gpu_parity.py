@@ -629,3 +629,31 @@ def test_randomised_tile_configs_bit_exact(S, oracle):
         oimg, of64 = oracle.colorize(cfg.to_pod(), ort, want_f64=True)
         _assert_image_close(img, f32, oimg, of64)
         rt.close()
+
+
+@pytest.mark.parametrize("name", ["poisson_saturne", "solar_sail", "solar_sail_220"])
+def test_gpu_colorize_reproduces_the_reference_s_published_pixels(S, name):
+    """Not GPU-vs-oracle: GPU vs the REFERENCE's own output.  tests/golden/media_inverse.npz holds, for 50 000 pixels of
+    each media/*.png, the (count, steps) and the image's Runtime.max recovered by inverting colorize (lib.rs:853-874) such
+    that the formula returns the PNG's 16-bit channels exactly (tests/test_reference_images.py).  Uploaded as a 1-row
+    Runtime, sar_colorize must give those bytes back — solar-sail's max (k x 6 944 444) is far beyond the ln table, so
+    this is also the host-ln(max+1) path.  Pixels the pre-clamp revision coloured from a negative position are skipped."""
+    import os
+
+    import test_reference_images as T
+
+    inv = np.load(os.path.join(T.ROOT, "tests", "golden", "media_inverse.npz"))
+    count, steps, zbuf, mx = T.strip_runtime_arrays(inv, name)
+    preset, off, _ = T.IMAGES[name]
+    cfg = getattr(S.Config, preset)()
+    cfg.width, cfg.height, cfg.transparent = count.shape[1], 1, False
+    cfg.colors.brighness.offset = off
+    rt = S.Runtime.new(cfg)
+    rt.upload(count, steps, zbuf)
+    c2, s2, z2, gmax = rt.download()
+    assert gmax == mx and np.array_equal(c2, count) and np.array_equal(s2, steps)
+    img = S.colorize(cfg, rt)[0, 1:, :]
+    head = inv[name + "_v"] >= 0
+    assert head.sum() > 30_000
+    assert np.array_equal(img[head, :3], inv[name + "_rgb"][head]), "GPU colourise differs from the reference's published pixels"
+    assert (img[:, 3] == 65535).all()

@@ -1,0 +1,180 @@
+"""Pin the oracle on the reference's own published OUTPUT, pixel by pixel (not block statistics).
+
+tests/golden/make_inverse_fixtures.py inverts `colorize` (lib.rs:853-874) on media/*.png: for every pixel
+whose three channels are neither 0 nor 65535 it recovers the integer count, the palette position (`steps`) and
+— once per image — `Runtime.max`, such that the formula gives back the PNG's 16-bit channels EXACTLY.  The
+system is over-determined (3 integers from 1 integer + 1 real), so this only works if formula, constants,
+cast, logs and max are the reference's.  All 2 133 250 such pixels of the three images are solvable.
+
+What that buys, per SURVEY §8 row:
+  a11/a12  colourise: the oracle (and, in tests/test_gpu_parity.py, the GPU) reproduces sampled reference pixels bit for bit
+  a6       count scatter + max: the recovered count field equals the oracle's render at Poisson-noise level, PIXEL by
+           pixel (chi-square per pixel ~ 1; a one-pixel shift gives > 20), and the hottest pixel agrees within 5 sigma
+  a7/a8    depth test + colour transforms: recovered palette positions equal the oracle's `steps` (median ~ 1e-5)
+  a15      decomposition: solar-sail's max is k * (1e9 / 12 / 12), lib.rs:1058 (12 threads x 12 jobs, k diverging jobs)
+  §0.5     NaN sink: the diverging fraction k/144 is inside the oracle's binomial range
+Two documented differences between the images and lib.rs @ HEAD (the oracle follows HEAD, the tests show both):
+the images predate the `value < 0 -> 0` clamp of lib.rs:443-444 (negative positions extrapolate the first palette
+segment), and the solar-sail images used AdjustedVelocity { offset: -0.2, factor: 0.8 } where HEAD's preset has
+the two values swapped (lib.rs:381-384).
+"""
+import math
+import os
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PER_JOB = 1_000_000_000 // 12 // 12
+IMAGES = {  # name -> (preset, brightness offset, view angle) of README.md:72-77
+    "poisson_saturne": ("poisson_saturne", -0.25, 0.0),
+    "solar_sail": ("solar_sail", -0.1, 0.0),
+    "solar_sail_220": ("solar_sail", -0.15, 220.0 * math.pi / 180.0),
+}
+
+
+@pytest.fixture(scope="module")
+def inverse():
+    return np.load(os.path.join(ROOT, "tests", "golden", "media_inverse.npz"))
+
+
+def _config(O, name, w, h):
+    preset, off, angle = IMAGES[name]
+    cfg = getattr(O, preset)()
+    cfg.width, cfg.height, cfg.transparent, cfg.bright_offset, cfg.angle = w, h, 0, off, angle
+    if preset == "solar_sail":
+        # The published solar-sail images were coloured with AdjustedVelocity { offset: -0.2, factor: 0.8 }: the recovered
+        # positions are (|dp| - 0.2) * 0.8 to 8e-5.  HEAD's preset has the two numbers the other way round
+        # (lib.rs:381-384: factor -0.2, offset 0.8 -> every position negative -> one flat colour after the clamp);
+        # the oracle's preset follows HEAD, the comparison below uses the images' values.  Counts do not depend on it.
+        cfg.ct_offset, cfg.ct_factor = -0.2, 0.8
+    return cfg
+
+
+def strip_runtime_arrays(inv, name):
+    """A 1-row frame: pixel 0 holds Runtime.max, pixels 1..K the recovered (count, steps) of the sampled pixels."""
+    n, v, mx = inv[name + "_n"], inv[name + "_v"].astype(np.float64), int(inv[name + "_max"])
+    count = np.concatenate([[mx], n]).astype(np.uint32)[None, :]
+    steps = np.concatenate([[0.0], v])[None, :]
+    return count, steps, np.full(count.shape, -1.0, np.float32), mx
+
+
+def unclamped_pixel(n, v, mx, off):
+    """colorize of one pixel with lib.rs:443-444 removed (negative `as usize` saturates to segment 0, `%` keeps the sign)."""
+    pal = [(1, 1, .5), (.5, 1, .5), (1, .5, .5), (.5, 1, 1), (.5, .5, 1), (1, .5, 1), (1, .5, 1)]
+    val = v * 6.0
+    s = int(math.floor(val)) if val >= 0.0 else 0
+    t = math.fmod(val, 1.0)
+    factor = math.log(float(n + 1)) / math.log(float(mx + 1))
+    out = []
+    for c in range(3):
+        x = (math.sqrt(pal[s + 1][c] * t + pal[s][c] * (1.0 - t)) * factor + off) * (5.0 / 3.0) * 65535.0
+        out.append(0 if x <= 0 else (65535 if x >= 65535 else int(x)))
+    return out
+
+
+@pytest.mark.parametrize("name", list(IMAGES))
+def test_oracle_colorize_reproduces_reference_pixels_exactly(oracle, inverse, name):
+    count, steps, zbuf, mx = strip_runtime_arrays(inverse, name)
+    cfg = _config(oracle, name, count.shape[1], 1)
+    rt = oracle.Runtime(count.shape[1], 1)
+    rt.load(count, steps, zbuf)
+    assert rt.max == mx
+    img = oracle.colorize(cfg, rt)[0, 1:, :3]
+    ref, v = inverse[name + "_rgb"], inverse[name + "_v"]
+    head = v >= 0
+    assert head.sum() > 30_000
+    assert np.array_equal(img[head], ref[head]), "oracle colourise differs from the reference's published pixels"
+    # pixels the pre-clamp revision coloured from a negative palette position: HEAD (and the oracle) clamp to 0
+    neg = np.flatnonzero(~head)
+    if name != "poisson_saturne":
+        assert len(neg) > 5_000
+    n = inverse[name + "_n"]
+    for i in neg[:2000]:
+        assert unclamped_pixel(int(n[i]), float(v[i]), mx, IMAGES[name][1]) == list(ref[i])
+    if len(neg):
+        strip0 = steps.copy()
+        strip0[0, 1:][~head] = 0.0
+        rt.load(count, strip0, zbuf)
+        assert np.array_equal(oracle.colorize(cfg, rt)[0, 1:, :3][~head], img[~head])
+    # the stats the generator recorded: every fully informative pixel of the image was solved
+    full, solved = inverse[name + "_stats"][:2]
+    assert full == solved
+
+
+def test_recovered_max_is_the_decomposition_of_render_parallel(inverse):
+    """lib.rs:1058: iterations / threads / jobs_per_thread, integer division; a diverged job adds all of its
+    iterations to pixel (0,0), so max = k * per_job."""
+    for name, k in (("solar_sail", 58), ("solar_sail_220", 54)):
+        assert int(inverse[name + "_max"]) == k * PER_JOB
+    assert int(inverse["poisson_saturne_max"]) == 95_125
+
+
+@pytest.fixture(scope="module")
+def oracle_renders(oracle):
+    """One 1e9-iteration oracle render per published image, decomposed like the author's run (12 x 12 jobs)."""
+    cache = {}
+
+    def get(name):
+        if name not in cache:
+            w, h = (1920, 1080) if name == "poisson_saturne" else (1800, 2000)
+            cfg = _config(oracle, name, w, h)
+            cfg.iterations = 1_000_000_000
+            pts = oracle.seed_points(1234, 0, 144)
+            img, rt = oracle.render_parallel(cfg, 12, 12, pts, want_runtime=True)
+            cache[name] = (img, rt.count.copy().ravel(), rt.steps.copy().ravel(), rt.max)
+        return cache[name]
+
+    return get
+
+
+def _chi2(x, y, s=1.0):
+    """mean over pixels of (x - s y)^2 / (x + s^2 y): ~1 when x and s*y are Poisson draws of the same field."""
+    x, y = x.astype(np.float64), y.astype(np.float64)
+    return float((((x - s * y) ** 2) / np.maximum(x + s * s * y, 1.0)).mean())
+
+
+@pytest.mark.slow
+@pytest.mark.parametrize("name", list(IMAGES))
+def test_reference_count_field_equals_oracle_at_poisson_noise(oracle_renders, inverse, name):
+    img, count, steps, omax = oracle_renders(name)
+    idx, n = inverse[name + "_idx"].astype(np.int64), inverse[name + "_n"]
+    w, h = inverse[name + "_stats"][4:6]
+    rmax = int(inverse[name + "_max"])
+    if name == "poisson_saturne":
+        s = 1.0
+        assert abs(rmax - omax) < 5.0 * math.sqrt(rmax), (rmax, omax)       # hottest pixel: 95 125 vs oracle +- 308
+    else:
+        # max is the NaN sink: diverging jobs x per_job.  Binomial(144, ~0.39): within 4 sigma of each other
+        k_ref, k_orc = rmax / PER_JOB, omax / PER_JOB
+        assert abs(k_orc - round(k_orc)) < 1e-3, "oracle's NaN sink is not a whole number of jobs"
+        assert abs(k_ref - k_orc) < 4.0 * math.sqrt(144 * 0.39 * 0.61) * math.sqrt(2.0), (k_ref, k_orc)
+        s = (144.0 - k_ref) / (144.0 - k_orc)                                # recorded (bounded) jobs: ref / oracle
+    c = count[idx]
+    chi = _chi2(n, c, s)
+    assert 0.85 < chi < 1.25, chi
+    # power of the test: the same field one pixel off is nowhere near
+    for shift in (1, -1, int(w), -int(w)):
+        assert _chi2(n, count[np.clip(idx + shift, 0, len(count) - 1)], s) > 15.0
+    # total mass over the sampled pixels
+    assert abs(float(n.sum()) / (s * float(c.sum())) - 1.0) < 2e-3
+
+
+@pytest.mark.slow
+@pytest.mark.parametrize("name", list(IMAGES))
+def test_reference_palette_positions_equal_oracle_steps(oracle_renders, inverse, name):
+    """`steps` of a pixel = colour transform of the hit with the greatest z (lib.rs:818-833).  The last palette
+    segment is constant (lib.rs:418 duplicates the last colour), positions there cannot be recovered: excluded."""
+    img, count, steps, omax = oracle_renders(name)
+    idx, v = inverse[name + "_idx"].astype(np.int64), inverse[name + "_v"].astype(np.float64)
+    o = steps[idx]
+    keep = (v < 5.0 / 6.0 - 1e-3) & (o < 5.0 / 6.0 - 1e-3) & (count[idx] > 0)
+    assert keep.sum() > 20_000
+    d = np.abs(v[keep] - o[keep])
+    assert np.median(d) < 1e-4, np.median(d)
+    assert np.quantile(d, 0.9) < 1e-3, np.quantile(d, 0.9)
+    if name != "poisson_saturne":
+        # AdjustedVelocity (lib.rs:511-516) is NOT clamped by the transform: negative positions on both sides
+        neg = v < -1e-3
+        assert neg.sum() > 5_000 and np.median(np.abs(v[neg] - o[neg])) < 1e-4
+        assert (o[neg] < 0).mean() > 0.99
