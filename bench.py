@@ -128,7 +128,10 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "width": WIDTH, "height": HEIGHT, "iterations_per_step": iters,
+        # same workload keys and values as the GPU arm's `config`; the bounded sample a step runs is `iterations_per_step`
+        "config": {"workload": WORKLOAD, "width": WIDTH, "height": HEIGHT, "iterations_per_gpu": ITERATIONS,
+                   "iterations_per_frame": ITERATIONS, "seed": SEED, "iterations_per_step": iters,
+                   "l2": "n/a (host arm: private 16 B/px buffers per thread, 64 MiB each, far beyond the CPU caches)",
                    "note": "reference is Rust; no rustc/cargo in this image, so the CPU arm is the C restatement (oracle/) of lib.rs:747-1082"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
