@@ -297,6 +297,18 @@ int  sar_encode_header(uint32_t width, uint32_t height, uint32_t pixel_format, u
  * on it) and copy header + pixels to `out` (sar_encoded_size bytes).  Blocking. */
 int  sar_runtime_encode(sar_runtime *rt, uint32_t pixel_format, uint32_t container,
                         uint8_t *out, size_t out_bytes, void *stream);
+/* A complete, COMPRESSED PNG of the Runtime's device-resident image — what the reference's PngEncoder
+ * (main.rs:78-89, CompressionType::Default, adaptive filter) is for: a file of a few MB instead of the raw image.
+ * The compressor runs on the device (csrc/sar_deflate.cu): Sub-filtered scanlines (so the untouched part of a frame is
+ * zeros), one deflate block per 16 KB with run-length matches and its own dynamic Huffman code, blocks made
+ * independently by one warp each and joined on byte boundaries; CRC-32 / Adler-32 partial sums on the device, folded
+ * by the host.  A deflate stream is specified by what it decodes to (RFC 1950/1951), not by its bytes: the file
+ * decodes to exactly the pixels of the reference's PNG; its size is within a few per cent of the reference's
+ * (reference poisson-saturne.png 3.63 MB, this 3.72 MB).  Pixel formats as above (16-bit samples big-endian).
+ * sar_png_bound: worst-case bytes for out_capacity (0 for an unsupported size); *out_bytes: bytes written.  Blocking. */
+size_t sar_png_bound(uint32_t width, uint32_t height, uint32_t pixel_format);
+int  sar_runtime_encode_png(sar_runtime *rt, uint32_t pixel_format, uint8_t *out, size_t out_capacity,
+                            size_t *out_bytes, void *stream);
 /* File::create(path) + write_all, main.rs:102-104 */
 int  sar_write_file(const char *path, const uint8_t *bytes, size_t n_bytes);
 /* sar_render_sequence with every frame converted on the device and handed over

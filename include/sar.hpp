@@ -10,7 +10,7 @@
 //   sar::Runtime::{Runtime(config), reset, merge}                                          lib.rs:660, 682, 708
 //   sar::render(config, runtime), sar::colorize(config, runtime) -> FinalImage             lib.rs:747, 841
 //   sar::ParallelRenderer::{ParallelRenderer(), shutdown}, sar::render_parallel(...)       lib.rs:919, 1020, 1051
-//   sar::PixelFormat, Container, encode_image(runtime, ...), write_image(...)              src/bin/main.rs:40-100
+//   sar::PixelFormat, Container, encode_image(runtime, ...), encode_png(...), write_image(...)  src/bin/main.rs:40-100
 //   sar::autoframe(config, ...) -> AutoFrame                                               lib.rs:326-334 (the author's TODO)
 #pragma once
 #include <array>
@@ -194,8 +194,19 @@ inline std::vector<uint8_t> encode_image(const Runtime &runtime, uint32_t width,
     check(sar_runtime_encode(runtime.handle(), uint32_t(fmt), uint32_t(cont), out.data(), out.size(), nullptr));
     return out;
 }
+// The same image as a complete, deflate-compressed PNG (main.rs:78-89; compressor on the device, sar.h: sar_runtime_encode_png).
+inline std::vector<uint8_t> encode_png(const Runtime &runtime, uint32_t width, uint32_t height, PixelFormat fmt) {
+    const size_t cap = sar_png_bound(width, height, uint32_t(fmt));
+    if (cap == 0) throw Error(SAR_ERR_UNSUPPORTED, "image too large for one IDAT chunk");
+    std::vector<uint8_t> out(cap);
+    size_t n = 0;
+    check(sar_runtime_encode_png(runtime.handle(), uint32_t(fmt), out.data(), out.size(), &n, nullptr));
+    out.resize(n);
+    return out;
+}
 inline void write_image(const Runtime &runtime, const Config &config, const std::string &path, bool eight_bit, Container cont) {
-    const auto bytes = encode_image(runtime, config.width, config.height, pixel_format(config.transparent, eight_bit), cont);
+    const auto bytes = cont == Container::Png ? encode_png(runtime, config.width, config.height, pixel_format(config.transparent, eight_bit))
+                                              : encode_image(runtime, config.width, config.height, pixel_format(config.transparent, eight_bit), cont);
     check(sar_write_file(path.c_str(), bytes.data(), bytes.size()));
 }
 

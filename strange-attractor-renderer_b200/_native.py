@@ -101,6 +101,8 @@ SYMBOLS = {
     "sar_encoded_size": (C.c_size_t, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]),
     "sar_encode_header": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _u8p, C.c_size_t, _P(C.c_size_t)]),
     "sar_runtime_encode": (C.c_int, [_vp, C.c_uint32, C.c_uint32, _u8p, C.c_size_t, _vp]),
+    "sar_png_bound": (C.c_size_t, [C.c_uint32, C.c_uint32, C.c_uint32]),
+    "sar_runtime_encode_png": (C.c_int, [_vp, C.c_uint32, _u8p, C.c_size_t, _P(C.c_size_t), _vp]),
     "sar_write_file": (C.c_int, [C.c_char_p, _u8p, C.c_size_t]),
     "sar_render_sequence_encoded": (C.c_int, [_vp, _cfgp, _f64p, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, _u8p, _vp, _vp]),
     "sar_render_seeded_async": (C.c_int, [_cfgp, _vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, _vp]),

@@ -495,9 +495,25 @@ def encode_image(runtime: Runtime, pixel_format: PixelFormat, container: Contain
     return out
 
 
-def write_image(runtime: Runtime, path: str, transparent: bool, eight_bit: bool, container: Container) -> str:
-    """write_image_matches (main.rs:40-100) for the PAM / BMP branches: convert, set the extension, write."""
-    data = encode_image(runtime, PixelFormat.of(transparent, eight_bit), container)
+def encode_png(runtime: Runtime, pixel_format: PixelFormat) -> np.ndarray:
+    """The image of the last colorize() on `runtime` as a complete COMPRESSED PNG (main.rs:78-89): filter, deflate and
+    checksums on the device (include/sar.h: sar_runtime_encode_png).  uint8 array of the file's bytes."""
+    cap = N.lib().sar_png_bound(runtime.width, runtime.height, pixel_format.value)
+    if cap == 0:
+        raise SarError(N.SAR_ERR_UNSUPPORTED, "image too large for one IDAT chunk")
+    out = np.empty(cap, dtype=np.uint8)
+    n = C.c_size_t()
+    N.check(N.lib().sar_runtime_encode_png(runtime._h, pixel_format.value, out.ctypes.data_as(N._u8p), cap, C.byref(n), None))
+    return out[:n.value].copy()
+
+
+def write_image(runtime: Runtime, path: str, transparent: bool, eight_bit: bool, container: Container, compress: bool = True) -> str:
+    """write_image_matches (main.rs:40-100): convert, set the extension, write.  The PNG branch (main.rs:78-89) writes a
+    deflate-compressed file like the reference's encoder unless compress=False (stored blocks, sar_runtime_encode)."""
+    if container is Container.Png and compress:
+        data = encode_png(runtime, PixelFormat.of(transparent, eight_bit))
+    else:
+        data = encode_image(runtime, PixelFormat.of(transparent, eight_bit), container)
     ext = {Container.Pam: ".pam", Container.Bmp: ".bmp", Container.Raw: ".raw", Container.Png: ".png"}[container]
     path = os.path.splitext(path)[0] + ext                       # name.set_extension(..), main.rs:63, 71
     N.check(N.lib().sar_write_file(path.encode(), data.ctypes.data_as(N._u8p), data.size))

@@ -10,8 +10,8 @@ CSRC = os.path.join(_HERE, "csrc")
 OUT = os.path.join(_HERE, "libsar_b200.so")
 # the same sources with -DSAR_DIAGNOSTICS: roofline-experiment variants of the iterate kernel, for tools/ only
 OUT_DIAG = os.path.join(_HERE, "libsar_b200_diag.so")
-SOURCES = ["sar_kernels.cu", "sar_abi.cu"]
-HEADERS = ["sar_device.cuh", os.path.join("..", "..", "include", "sar.h")]
+SOURCES = ["sar_kernels.cu", "sar_deflate.cu", "sar_abi.cu"]
+HEADERS = ["sar_device.cuh", "sar_deflate.cuh", os.path.join("..", "..", "include", "sar.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -5,6 +5,7 @@
 // every entry point that needs a GPU fails with SAR_ERR_CUDA when there is none.
 #include "../../include/sar.h"
 #include "sar_device.cuh"
+#include "sar_deflate.cuh"
 
 #include <cmath>
 #include <cstdarg>
@@ -1258,15 +1259,14 @@ static uint32_t crc_bytes(uint32_t c, const uint8_t *p, size_t n)          // re
 }
 static void put_be32(uint8_t *p, uint32_t v) { p[0] = (uint8_t)(v >> 24); p[1] = (uint8_t)(v >> 16); p[2] = (uint8_t)(v >> 8); p[3] = (uint8_t)v; }
 // the 20 bytes after the IDAT payload: Adler-32 of the raw stream, CRC-32 of the IDAT chunk, the IEND chunk
-static void png_trailer(const OutSpec &o, const uint8_t *sums, uint8_t *out)
+static void png_fold(const uint32_t *crc_part, size_t n_crc, size_t payload_len, const unsigned long long *ad, size_t n_adler,
+                     size_t raw_len, uint8_t *out)
 {
     std::call_once(g_crc_once, crc_init);
-    const uint32_t *crc_part = reinterpret_cast<const uint32_t *>(sums);
-    const unsigned long long *ad = reinterpret_cast<const unsigned long long *>(sums + align_up(o.n_crc * 4, 8));
     // Adler-32 (zlib): a = 1 + sum d, b = sum of the running a, both mod 65521
     unsigned long long a = 1, b = 0;
-    for (size_t i = 0; i < o.n_adler; ++i) {
-        const size_t len = (i + 1) * PNG_CHUNK <= o.raw_len ? PNG_CHUNK : o.raw_len - i * PNG_CHUNK;
+    for (size_t i = 0; i < n_adler; ++i) {
+        const size_t len = (i + 1) * PNG_CHUNK <= raw_len ? PNG_CHUNK : raw_len - i * PNG_CHUNK;
         b = (b + (unsigned long long)len * a + ad[2 * i + 1]) % 65521ull;
         a = (a + ad[2 * i]) % 65521ull;
     }
@@ -1275,8 +1275,8 @@ static void png_trailer(const OutSpec &o, const uint8_t *sums, uint8_t *out)
     // each chunk with the precomputed zero-bytes operator and the chunk's own contribution is XORed in
     const uint8_t pre[6] = {'I', 'D', 'A', 'T', 0x78, 0x01};
     uint32_t c = crc_bytes(0xFFFFFFFFu, pre, 6);
-    for (size_t i = 0; i < o.n_crc; ++i) {
-        const size_t len = (i + 1) * PNG_CHUNK <= o.payload ? PNG_CHUNK : o.payload - i * PNG_CHUNK;
+    for (size_t i = 0; i < n_crc; ++i) {
+        const size_t len = (i + 1) * PNG_CHUNK <= payload_len ? PNG_CHUNK : payload_len - i * PNG_CHUNK;
         if (len == PNG_CHUNK) c = gf2_apply(g_crc_shift_chunk, c);
         else for (size_t k = 0; k < len; ++k) c = crc_zero_byte(c);
         c ^= crc_part[i];
@@ -1288,6 +1288,11 @@ static void png_trailer(const OutSpec &o, const uint8_t *sums, uint8_t *out)
     put_be32(out + 4, c);
     const uint8_t iend[12] = {0, 0, 0, 0, 'I', 'E', 'N', 'D', 0xAE, 0x42, 0x60, 0x82};
     memcpy(out + 8, iend, 12);
+}
+static void png_trailer(const OutSpec &o, const uint8_t *sums, uint8_t *out)
+{
+    png_fold(reinterpret_cast<const uint32_t *>(sums), o.n_crc, o.payload,
+             reinterpret_cast<const unsigned long long *>(sums + align_up(o.n_crc * 4, 8)), o.n_adler, o.raw_len, out);
 }
 static int make_outspec(uint32_t w, uint32_t h, uint32_t fmt, uint32_t container, OutSpec &o)
 {
@@ -1407,6 +1412,71 @@ int sar_runtime_encode(sar_runtime *rt, uint32_t pixel_format, uint32_t containe
     SAR_CUDA(cudaMemcpyAsync(out + o.header, d_pay, o.payload, cudaMemcpyDeviceToHost, s));
     SAR_CUDA(cudaStreamSynchronize(s));
     if (o.container == SAR_FILE_PNG) png_trailer(o, sums.data(), out + o.header + o.payload);
+    return SAR_OK;
+}
+
+// ---- PNG with the compressor (main.rs:78-89): Sub-filtered scanlines, one run-length + dynamic-Huffman deflate block per
+// 16 KB, all on the device (sar_deflate.cu); the host patches the IDAT length and folds the checksums.
+struct PngPlan { OutSpec o; size_t n_chunks, pay_bound, n_crc_max, n_adler, off_chunks, off_sizes, off_offsets, off_pay, off_crc, off_adler, scratch; };
+static int png_plan(uint32_t w, uint32_t h, uint32_t fmt, PngPlan &p)
+{
+    if (int rc = check_dims(w, h)) return rc;
+    if (int rc = make_outspec(w, h, fmt, SAR_FILE_PNG, p.o)) return rc;
+    p.n_chunks = (p.o.raw_len + dfl::CHUNK - 1) / dfl::CHUNK;
+    p.pay_bound = p.o.raw_len + 5 * p.n_chunks;                       // every block at worst stored
+    if (2 + p.pay_bound + 4 > 0x7FFFFFFFull) return fail(SAR_ERR_INVALID, "image too large for one IDAT chunk");
+    p.n_crc_max = (p.pay_bound + PNG_CHUNK - 1) / PNG_CHUNK;
+    p.n_adler = (p.o.raw_len + PNG_CHUNK - 1) / PNG_CHUNK;
+    p.off_chunks = align_up(p.o.raw_len, 256);
+    p.off_sizes = p.off_chunks + align_up(p.n_chunks * dfl::CHUNK_CAP, 256);
+    p.off_offsets = p.off_sizes + align_up(p.n_chunks * sizeof(uint32_t), 256);
+    p.off_pay = p.off_offsets + align_up((p.n_chunks + 1) * sizeof(unsigned long long), 256);
+    p.off_crc = p.off_pay + align_up(p.pay_bound, 256);
+    p.off_adler = p.off_crc + align_up(p.n_crc_max * sizeof(uint32_t), 256);
+    p.scratch = p.off_adler + p.n_adler * 2 * sizeof(unsigned long long);
+    return SAR_OK;
+}
+
+size_t sar_png_bound(uint32_t width, uint32_t height, uint32_t pixel_format)
+{
+    PngPlan p;
+    if (png_plan(width, height, pixel_format, p)) return 0;
+    return p.o.header + p.pay_bound + 20;
+}
+
+int sar_runtime_encode_png(sar_runtime *rt, uint32_t pixel_format, uint8_t *out, size_t out_capacity, size_t *out_bytes, void *stream)
+{
+    if (!rt || !out || !out_bytes) return fail(SAR_ERR_INVALID, "NULL argument");
+    *out_bytes = 0;
+    PngPlan p;
+    if (int rc = png_plan(rt->w, rt->h, pixel_format, p)) return rc;
+    if (out_capacity < p.o.header + 20) return fail(SAR_ERR_INVALID, "output capacity %zu is below the fixed parts of a PNG", out_capacity);
+    SAR_CUDA(cudaSetDevice(rt->device));
+    cudaStream_t s = pick(rt, stream);
+    if (int rc = ensure_scratch(rt, p.scratch)) return rc;
+    uint8_t *base = (uint8_t *)rt->d_scratch;
+    unsigned long long *d_offsets = (unsigned long long *)(base + p.off_offsets);
+    launch_png_deflate(rt->image, rt->w, rt->h, p.o.fmt, p.o.raw_row, p.o.raw_len, base, base + p.off_chunks,
+                       (uint32_t *)(base + p.off_sizes), d_offsets, base + p.off_pay, (uint32_t *)(base + p.off_crc),
+                       (unsigned long long *)(base + p.off_adler), p.n_crc_max, p.n_adler, s);
+    SAR_CUDA(cudaGetLastError());
+    unsigned long long total = 0;
+    SAR_CUDA(cudaMemcpyAsync(&total, d_offsets + p.n_chunks, sizeof total, cudaMemcpyDeviceToHost, s));
+    SAR_CUDA(cudaStreamSynchronize(s));
+    if (total == 0 || total > p.pay_bound) return fail(SAR_ERR_CUDA, "deflate produced %llu bytes (bound %zu)", total, p.pay_bound);
+    const size_t need = p.o.header + (size_t)total + 20;
+    if (out_capacity < need) return fail(SAR_ERR_INVALID, "output needs %zu bytes (got %zu; sar_png_bound gives the worst case)", need, out_capacity);
+    const size_t n_crc = ((size_t)total + PNG_CHUNK - 1) / PNG_CHUNK;
+    std::vector<uint32_t> crc(n_crc);
+    std::vector<unsigned long long> adler(2 * p.n_adler);
+    memcpy(out, p.o.head, p.o.header);
+    put_be32(out + p.o.header - 10, (uint32_t)(2 + total + 4));      // IDAT length: zlib header + deflate stream + Adler-32
+    SAR_CUDA(cudaMemcpyAsync(out + p.o.header, base + p.off_pay, (size_t)total, cudaMemcpyDeviceToHost, s));
+    SAR_CUDA(cudaMemcpyAsync(crc.data(), base + p.off_crc, n_crc * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    SAR_CUDA(cudaMemcpyAsync(adler.data(), base + p.off_adler, adler.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    SAR_CUDA(cudaStreamSynchronize(s));
+    png_fold(crc.data(), n_crc, (size_t)total, adler.data(), p.n_adler, p.o.raw_len, out + p.o.header + (size_t)total);
+    *out_bytes = need;
     return SAR_OK;
 }
 

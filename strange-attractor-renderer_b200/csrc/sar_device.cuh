@@ -148,6 +148,12 @@ void launch_png_pack(const uint16_t *rgba, uint8_t *out, unsigned int W, unsigne
 void launch_png_sums(const uint8_t *payload, size_t payload_len, size_t raw_len, uint32_t *crc, unsigned long long *adler,
                      size_t n_crc, size_t n_adler, cudaStream_t s);
 
+// PNG with the compressor (sar_deflate.cu): filter, one deflate block per 16 KB, compaction, partial checksums
+void launch_png_deflate(const uint16_t *rgba, unsigned int W, unsigned int H, unsigned int fmt, size_t raw_row, size_t raw_len,
+                        uint8_t *raw, uint8_t *chunks, uint32_t *sizes, unsigned long long *offsets, uint8_t *pay,
+                        uint32_t *crc, unsigned long long *adler, size_t n_crc_max, size_t n_adler, cudaStream_t s);
+void bump_launches(unsigned int n);
+
 // launchers (sar_kernels.cu); every one bumps the launch counter
 void launch_reset(unsigned long long *fast, ulonglong2 *rec, Scalars *scal, size_t npix, size_t nslots, cudaStream_t s);
 // returns true when the shared-memory tile path ran (small images; Runtime.max then needs the full reduction)

@@ -22,6 +22,7 @@ namespace sar {
 
 static std::atomic<unsigned long long> g_launches{0};
 unsigned long long launch_count() { return g_launches.load(); }
+void bump_launches(unsigned int n) { g_launches += n; }
 
 // ---------------------------------------------------------------------------------------------
 // small device helpers

@@ -67,7 +67,9 @@ int main(int argc, char **argv)
     (void)colorize(cfg, runtime);
     const std::vector<uint8_t> pam = encode_image(runtime, cfg.width, cfg.height, pixel_format(cfg.transparent, false), Container::Pam);
     const std::vector<uint8_t> bmp = encode_image(runtime, cfg.width, cfg.height, pixel_format(cfg.transparent, true), Container::Bmp);
-    std::printf("ENCODED pam=%llu bmp=%llu\n", fnv_bytes(pam.data(), pam.size()), fnv_bytes(bmp.data(), bmp.size()));
+    const std::vector<uint8_t> png = encode_png(runtime, cfg.width, cfg.height, pixel_format(cfg.transparent, false));
+    std::printf("ENCODED pam=%llu bmp=%llu png=%llu\n", fnv_bytes(pam.data(), pam.size()), fnv_bytes(bmp.data(), bmp.size()),
+                fnv_bytes(png.data(), png.size()));
     try { (void)encode_image(runtime, cfg.width, cfg.height, PixelFormat::Rgb16, Container::Bmp); std::puts("BMP16_DID_NOT_FAIL"); return 6; }
     catch (const Error &e) { std::printf("BMP16 code=%d\n", e.code); }
     const AutoFrame af = autoframe(Config::poisson_saturne(), 1024, 2000, /*seed=*/3);

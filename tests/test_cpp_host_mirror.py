@@ -76,7 +76,8 @@ def test_cpp_mirror_matches_python_api(exe):
     S.colorize(cfg, rt)
     pam = S.encode_image(rt, S.PixelFormat.of(False, False), S.Container.Pam)
     bmp = S.encode_image(rt, S.PixelFormat.of(False, True), S.Container.Bmp)
-    assert lines["ENCODED"][0] == {"pam": str(_fnv(pam)), "bmp": str(_fnv(bmp))}
+    png = S.encode_png(rt, S.PixelFormat.of(False, False))      # deterministic: same bytes from both hosts
+    assert lines["ENCODED"][0] == {"pam": str(_fnv(pam)), "bmp": str(_fnv(bmp)), "png": str(_fnv(png))}
     assert lines["BMP16"][0]["code"] == str(S._native.SAR_ERR_UNSUPPORTED)
     af = S.autoframe(S.Config.poisson_saturne(), n_jobs=1024, iterations=2000, seed=3)
     assert float(lines["AUTOFRAME"][0]["xmin"]) == af.box[0] and float(lines["AUTOFRAME"][0]["ymax"]) == af.box[3]

@@ -149,3 +149,83 @@ def test_encoded_sequence_equals_per_frame_encoding(oracle, tmp_path):
     assert path.endswith("frame.bmp")
     assert np.array_equal(np.fromfile(path, dtype=np.uint8), oracle.encode(img, 3, 2))
     r.shutdown()
+
+
+def _png_rows(png: bytes, w: int, h: int, bpp: int):
+    """Structure checks of a one-IDAT PNG + inflate + undo the per-row filter (types 0 and 1) -> sample bytes [h, w*bpp]."""
+    import zlib
+
+    assert png[:8] == b"\x89PNG\r\n\x1a\n" and png[12:16] == b"IHDR"
+    assert int.from_bytes(png[16:20], "big") == w and int.from_bytes(png[20:24], "big") == h
+    assert zlib.crc32(png[12:29]) == int.from_bytes(png[29:33], "big")
+    n = int.from_bytes(png[33:37], "big")
+    assert png[37:41] == b"IDAT" and zlib.crc32(png[37:41 + n]) == int.from_bytes(png[41 + n:45 + n], "big")
+    assert png[45 + n:] == b"\x00\x00\x00\x00IEND\xaeB`\x82"
+    raw = zlib.decompress(png[41:41 + n])                       # checks the Adler-32 as well
+    rows = np.frombuffer(raw, np.uint8).reshape(h, 1 + w * bpp)
+    out = np.empty((h, w * bpp), np.uint8)
+    for y in range(h):
+        ft, line = int(rows[y, 0]), rows[y, 1:]
+        assert ft in (0, 1)
+        out[y] = line if ft == 0 else (np.cumsum(line.reshape(w, bpp).astype(np.uint32), axis=0) & 255).astype(np.uint8).reshape(-1)
+    return out, n
+
+
+@pytest.mark.gpu
+def test_device_png_deflate_decodes_to_the_reference_pixels(oracle):
+    """sar_runtime_encode_png (main.rs:78-89 with the compressor, on the device): a valid PNG whose pixels are exactly the
+    converted image — checked with zlib's inflate + CRC/Adler and with Pillow — and far smaller than the stored form."""
+    import io
+    import time
+
+    from PIL import Image
+
+    import strange_attractor_renderer_b200 as S
+
+    cfg = S.Config.solar_sail()
+    cfg.width, cfg.height, cfg.iterations, cfg.angle = 203, 97, 30_000, 220.0 * math.pi / 180.0
+    rt = S.Runtime.new(cfg)
+    S.render(cfg, rt, initial_points=S.seed_points(7, 0, 128))
+    for transparent in (True, False):
+        cfg.transparent = transparent
+        img = S.colorize(cfg, rt)
+        for fmt in S.PixelFormat:
+            wide, alpha = fmt in (S.PixelFormat.Rgba16, S.PixelFormat.Rgb16), fmt in (S.PixelFormat.Rgba16, S.PixelFormat.Rgba8)
+            nch = 4 if alpha else 3
+            bpp = nch * (2 if wide else 1)
+            png = S.encode_png(rt, fmt).tobytes()
+            assert png[24] == (16 if wide else 8) and png[25] == (6 if alpha else 2)
+            samples, n = _png_rows(png, 203, 97, bpp)
+            if wide:
+                want = img[..., :nch].astype(">u2").view(np.uint8).reshape(97, 203 * bpp)
+            else:
+                want = ((img[..., :nch].astype(np.uint32) + 128) // 257).astype(np.uint8).reshape(97, 203 * bpp)
+                pil = np.asarray(Image.open(io.BytesIO(png)).convert("RGBA" if alpha else "RGB"))
+                assert np.array_equal(pil.reshape(97, 203 * bpp), want)
+            assert np.array_equal(samples, want), fmt
+            assert len(png) < S._native.lib().sar_encoded_size(203, 97, fmt.value, 3)
+    # shapes around the block (16 KB) and lane (512 B) sizes, a 1x1 image, rows longer than a block
+    for w, h in ((1, 1), (2730, 1), (2731, 1), (85, 32), (8300, 5), (3, 1400)):
+        c2 = S.Config.poisson_saturne()
+        c2.width, c2.height, c2.iterations, c2.transparent = w, h, 3_000, False
+        r2 = S.Runtime.new(c2)
+        S.render(c2, r2, initial_points=S.seed_points(2, 0, 64))
+        im2 = S.colorize(c2, r2)
+        samples, _ = _png_rows(S.encode_png(r2, S.PixelFormat.Rgb16).tobytes(), w, h, 6)
+        assert np.array_equal(samples, im2[..., :3].astype(">u2").view(np.uint8).reshape(h, w * 6)), (w, h)
+    # a full-size frame: the README's poisson-saturne command at 1e8 iterations; size in the range of the reference's file
+    big = S.Config.poisson_saturne()
+    big.width, big.height, big.iterations, big.transparent = 1920, 1080, 100_000_000, False
+    big.colors.brighness.offset = -0.25
+    r = S.ParallelRenderer.new()
+    im = S.render_parallel(r, big, 1, seed=9)
+    S.encode_png(r.runtime(), S.PixelFormat.Rgb16)             # warm the scratch allocation
+    t0 = time.perf_counter()
+    png = S.encode_png(r.runtime(), S.PixelFormat.Rgb16).tobytes()
+    dt = time.perf_counter() - t0
+    samples, n = _png_rows(png, 1920, 1080, 6)
+    assert np.array_equal(samples, im[..., :3].astype(">u2").view(np.uint8).reshape(1080, 1920 * 6))
+    raw_len = 1080 * (1 + 1920 * 6)
+    print(f"\npng deflate 1920x1080 RGB16: {raw_len} -> {len(png)} bytes ({len(png) / raw_len:.3f}), {dt * 1e3:.2f} ms incl. copy-out")
+    assert len(png) < 0.45 * raw_len
+    r.shutdown()

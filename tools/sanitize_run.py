@@ -28,6 +28,7 @@ for nt, pipe in ((1, 0), (2, 1), (4, 0)):
                 S.encode_image(rt, fmt, cont)
             except S.SarError:
                 pass
+        S.encode_png(rt, fmt)
 S._native.check(L.sar_set_option(b"traj_per_thread", 1))
 S._native.check(L.sar_set_option(b"pipeline", 0))
 # the shared-memory tile path: an image that fits a tile, more than one block of jobs, NaN trajectories included
