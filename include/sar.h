@@ -287,7 +287,9 @@ int  sar_render_sequence(sar_renderer *r, const sar_config *cfg, const double *a
  *                 packing and per-chunk CRC-32 / Adler-32 partial sums run on the
  *                 device; the host folds the sums into the 20 trailing bytes. */
 enum { SAR_PIX_RGBA16 = 0, SAR_PIX_RGB16 = 1, SAR_PIX_RGBA8 = 2, SAR_PIX_RGB8 = 3 };
-enum { SAR_FILE_RAW = 0, SAR_FILE_PAM = 1, SAR_FILE_BMP = 2, SAR_FILE_PNG = 3 };
+/* SAR_FILE_PNG_DEFLATE: the compressed PNG of sar_runtime_encode_png as a frame format of sar_render_sequence_encoded
+ * (frames differ in size: callback only, frames_out must be NULL); the fixed-size entry points reject it. */
+enum { SAR_FILE_RAW = 0, SAR_FILE_PAM = 1, SAR_FILE_BMP = 2, SAR_FILE_PNG = 3, SAR_FILE_PNG_DEFLATE = 4 };
 /* bytes of one encoded image (header + pixels); 0 for an unsupported combination */
 size_t sar_encoded_size(uint32_t width, uint32_t height, uint32_t pixel_format, uint32_t container);
 /* the container header alone (host only, no GPU); out may be NULL to query header_bytes */

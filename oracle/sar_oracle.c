@@ -629,6 +629,7 @@ static size_t png_encode(const uint16_t *rgba, uint32_t w, uint32_t h, int wide,
 
 size_t orc_encode(const uint16_t *rgba, uint32_t w, uint32_t h, uint32_t fmt, uint32_t container, uint8_t *out)
 {
+    if (container > SAR_FILE_PNG) return 0;                     /* unknown / variable-size containers: unsupported here */
     if (container == SAR_FILE_PNG)
         return png_encode(rgba, w, h, fmt == SAR_PIX_RGBA16 || fmt == SAR_PIX_RGB16, fmt == SAR_PIX_RGBA16 || fmt == SAR_PIX_RGBA8, out);
     const int wide = fmt == SAR_PIX_RGBA16 || fmt == SAR_PIX_RGB16, alpha = fmt == SAR_PIX_RGBA16 || fmt == SAR_PIX_RGBA8;

@@ -16,7 +16,7 @@ SAR_CT_POISSON_SATURNE, SAR_CT_ADJUSTED_VELOCITY, SAR_CT_SCREEN_BLEND = 0, 1, 2
 SAR_ATTRACTOR_SPROTT2, SAR_ATTRACTOR_SPROTT3 = 0, 1
 SAR_SEQ_SHARED_POINTS = 1
 SAR_PIX_RGBA16, SAR_PIX_RGB16, SAR_PIX_RGBA8, SAR_PIX_RGB8 = 0, 1, 2, 3
-SAR_FILE_RAW, SAR_FILE_PAM, SAR_FILE_BMP, SAR_FILE_PNG = 0, 1, 2, 3
+SAR_FILE_RAW, SAR_FILE_PAM, SAR_FILE_BMP, SAR_FILE_PNG, SAR_FILE_PNG_DEFLATE = 0, 1, 2, 3, 4
 FRAME_BYTES_CALLBACK = C.CFUNCTYPE(None, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint8), C.c_size_t)
 FRAME_CALLBACK = C.CFUNCTYPE(None, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint16))
 

@@ -482,6 +482,7 @@ class Container(enum.Enum):
     Pam = N.SAR_FILE_PAM        # --pam, main.rs:62-68
     Bmp = N.SAR_FILE_BMP        # --bmp, main.rs:70-76 (8-bit formats only)
     Png = N.SAR_FILE_PNG        # the default branch, main.rs:78-89, without the compressor (stored deflate blocks)
+    PngDeflate = N.SAR_FILE_PNG_DEFLATE   # the same with the compressor (device deflate); frame sequences only — see encode_png()
 
 
 def encode_image(runtime: Runtime, pixel_format: PixelFormat, container: Container = Container.Raw) -> np.ndarray:
@@ -576,10 +577,19 @@ def render_sequence_encoded(renderer: ParallelRenderer, config, angles: Sequence
         seed = int.from_bytes(os.urandom(8), "little")
     ang = np.ascontiguousarray(angles, dtype=np.float64)
     n = int(ang.shape[0])
-    nb = N.lib().sar_encoded_size(c.width, c.height, pixel_format.value, container.value)
-    if nb == 0:
-        raise SarError(N.SAR_ERR_UNSUPPORTED, f"{pixel_format.name} cannot be written as {container.name}")
-    out = np.empty((n, nb), dtype=np.uint8) if callback is None else None
+    collected = None
+    if container is Container.PngDeflate:          # frames of different sizes: callback only; without one, collect copies
+        out = None
+        if callback is None:
+            collected = [None] * n
+
+            def callback(frame, data, _dst=collected):
+                _dst[frame] = data.copy()
+    else:
+        nb = N.lib().sar_encoded_size(c.width, c.height, pixel_format.value, container.value)
+        if nb == 0:
+            raise SarError(N.SAR_ERR_UNSUPPORTED, f"{pixel_format.name} cannot be written as {container.name}")
+        out = np.empty((n, nb), dtype=np.uint8) if callback is None else None
     cb_c = None
     if callback is not None:
         def _cb(_user, frame, ptr, nbytes):
@@ -591,4 +601,4 @@ def render_sequence_encoded(renderer: ParallelRenderer, config, angles: Sequence
         N.SAR_SEQ_SHARED_POINTS if shared_points else 0, pixel_format.value, container.value,
         out.ctypes.data_as(N._u8p) if out is not None else None,
         C.cast(cb_c, C.c_void_p) if cb_c is not None else None, None))
-    return out
+    return collected if collected is not None else out

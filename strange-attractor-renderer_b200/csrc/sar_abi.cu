@@ -100,6 +100,7 @@ struct seq_device {                  // per-device pipeline state of sar_render_
     uint32_t *h_max = nullptr;                      // pinned: Runtime.max of the frame in each slot
     cudaEvent_t max_ready[2] = {nullptr, nullptr}, rendered[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr};
     cudaStream_t copy_stream = nullptr;
+    cudaStream_t pay_stream = nullptr;              // compressed PNG: the exact-size copy of a finished frame's stream
     double *warm = nullptr; size_t warm_cap = 0;    // warmed states shared by all frames (SAR_SEQ_SHARED_POINTS)
     size_t img_bytes = 0;
 };
@@ -1040,6 +1041,7 @@ static void seq_release(sar_renderer *r, size_t d)
     seq_device &q = r->seq[d];
     cudaSetDevice(r->devices[d]);
     if (q.copy_stream) { cudaStreamSynchronize(q.copy_stream); cudaStreamDestroy(q.copy_stream); }
+    if (q.pay_stream) { cudaStreamSynchronize(q.pay_stream); cudaStreamDestroy(q.pay_stream); }
     for (int k = 0; k < 2; ++k) {
         sar_runtime_free(q.rt[k]);
         if (q.stage[k]) cudaFreeHost(q.stage[k]);
@@ -1224,6 +1226,10 @@ struct OutSpec {
     uint8_t head[160] = {0};
     // PNG only: the raw (filtered scanline) stream, its stored blocks and the partial-checksum chunks
     size_t raw_row = 0, raw_len = 0, n_blocks = 0, n_crc = 0, n_adler = 0, sums_bytes = 0;
+    // compressed PNG (SAR_FILE_PNG_DEFLATE / sar_runtime_encode_png): device scratch layout and bounds
+    bool deflate = false;
+    size_t n_chunks = 0, pay_bound = 0, n_crc_max = 0, off_chunks = 0, off_sizes = 0, off_offsets = 0, off_pay = 0, off_crc = 0,
+           off_adler = 0, scratch = 0;
 };
 
 // ---- CRC-32 (PNG / zlib polynomial, reflected) and Adler-32 folding of the device's partial sums -----------
@@ -1417,65 +1423,73 @@ int sar_runtime_encode(sar_runtime *rt, uint32_t pixel_format, uint32_t containe
 
 // ---- PNG with the compressor (main.rs:78-89): Sub-filtered scanlines, one run-length + dynamic-Huffman deflate block per
 // 16 KB, all on the device (sar_deflate.cu); the host patches the IDAT length and folds the checksums.
-struct PngPlan { OutSpec o; size_t n_chunks, pay_bound, n_crc_max, n_adler, off_chunks, off_sizes, off_offsets, off_pay, off_crc, off_adler, scratch; };
-static int png_plan(uint32_t w, uint32_t h, uint32_t fmt, PngPlan &p)
+static int png_plan(uint32_t w, uint32_t h, uint32_t fmt, OutSpec &o)
 {
     if (int rc = check_dims(w, h)) return rc;
-    if (int rc = make_outspec(w, h, fmt, SAR_FILE_PNG, p.o)) return rc;
-    p.n_chunks = (p.o.raw_len + dfl::CHUNK - 1) / dfl::CHUNK;
-    p.pay_bound = p.o.raw_len + 5 * p.n_chunks;                       // every block at worst stored
-    if (2 + p.pay_bound + 4 > 0x7FFFFFFFull) return fail(SAR_ERR_INVALID, "image too large for one IDAT chunk");
-    p.n_crc_max = (p.pay_bound + PNG_CHUNK - 1) / PNG_CHUNK;
-    p.n_adler = (p.o.raw_len + PNG_CHUNK - 1) / PNG_CHUNK;
-    p.off_chunks = align_up(p.o.raw_len, 256);
-    p.off_sizes = p.off_chunks + align_up(p.n_chunks * dfl::CHUNK_CAP, 256);
-    p.off_offsets = p.off_sizes + align_up(p.n_chunks * sizeof(uint32_t), 256);
-    p.off_pay = p.off_offsets + align_up((p.n_chunks + 1) * sizeof(unsigned long long), 256);
-    p.off_crc = p.off_pay + align_up(p.pay_bound, 256);
-    p.off_adler = p.off_crc + align_up(p.n_crc_max * sizeof(uint32_t), 256);
-    p.scratch = p.off_adler + p.n_adler * 2 * sizeof(unsigned long long);
+    if (int rc = make_outspec(w, h, fmt, SAR_FILE_PNG, o)) return rc;
+    o.deflate = true;
+    o.n_chunks = (o.raw_len + dfl::CHUNK - 1) / dfl::CHUNK;
+    o.pay_bound = o.raw_len + 5 * o.n_chunks;                         // every block at worst stored
+    if (2 + o.pay_bound + 4 > 0x7FFFFFFFull) return fail(SAR_ERR_INVALID, "image too large for one IDAT chunk");
+    o.n_crc_max = (o.pay_bound + PNG_CHUNK - 1) / PNG_CHUNK;
+    o.n_adler = (o.raw_len + PNG_CHUNK - 1) / PNG_CHUNK;
+    o.off_chunks = align_up(o.raw_len, 256);
+    o.off_sizes = o.off_chunks + align_up(o.n_chunks * dfl::CHUNK_CAP, 256);
+    o.off_offsets = o.off_sizes + align_up(o.n_chunks * sizeof(uint32_t), 256);
+    o.off_pay = o.off_offsets + align_up((o.n_chunks + 1) * sizeof(unsigned long long), 256);
+    o.off_crc = o.off_pay + align_up(o.pay_bound, 256);
+    o.off_adler = o.off_crc + align_up(o.n_crc_max * sizeof(uint32_t), 256);
+    o.scratch = o.off_adler + o.n_adler * 2 * sizeof(unsigned long long);
+    // sequence driver: what one frame needs on the host (header + worst-case stream + trailer) and the pinned sums block
+    // [total u64][crc partials][adler partials]
+    o.payload = o.pay_bound;
+    o.total = o.header + o.pay_bound + 20;
+    o.sums_bytes = 8 + align_up(o.n_crc_max * sizeof(uint32_t), 8) + o.n_adler * 2 * sizeof(unsigned long long);
     return SAR_OK;
+}
+static void png_deflate_launch(const sar_runtime *rt, const OutSpec &o, uint8_t *base, cudaStream_t s)
+{
+    launch_png_deflate(rt->image, rt->w, rt->h, o.fmt, o.raw_row, o.raw_len, base, base + o.off_chunks,
+                       (uint32_t *)(base + o.off_sizes), (unsigned long long *)(base + o.off_offsets), base + o.off_pay,
+                       (uint32_t *)(base + o.off_crc), (unsigned long long *)(base + o.off_adler), o.n_crc_max, o.n_adler, s);
 }
 
 size_t sar_png_bound(uint32_t width, uint32_t height, uint32_t pixel_format)
 {
-    PngPlan p;
-    if (png_plan(width, height, pixel_format, p)) return 0;
-    return p.o.header + p.pay_bound + 20;
+    OutSpec o;
+    if (png_plan(width, height, pixel_format, o)) return 0;
+    return o.total;
 }
 
 int sar_runtime_encode_png(sar_runtime *rt, uint32_t pixel_format, uint8_t *out, size_t out_capacity, size_t *out_bytes, void *stream)
 {
     if (!rt || !out || !out_bytes) return fail(SAR_ERR_INVALID, "NULL argument");
     *out_bytes = 0;
-    PngPlan p;
-    if (int rc = png_plan(rt->w, rt->h, pixel_format, p)) return rc;
-    if (out_capacity < p.o.header + 20) return fail(SAR_ERR_INVALID, "output capacity %zu is below the fixed parts of a PNG", out_capacity);
+    OutSpec o;
+    if (int rc = png_plan(rt->w, rt->h, pixel_format, o)) return rc;
+    if (out_capacity < o.header + 20) return fail(SAR_ERR_INVALID, "output capacity %zu is below the fixed parts of a PNG", out_capacity);
     SAR_CUDA(cudaSetDevice(rt->device));
     cudaStream_t s = pick(rt, stream);
-    if (int rc = ensure_scratch(rt, p.scratch)) return rc;
+    if (int rc = ensure_scratch(rt, o.scratch)) return rc;
     uint8_t *base = (uint8_t *)rt->d_scratch;
-    unsigned long long *d_offsets = (unsigned long long *)(base + p.off_offsets);
-    launch_png_deflate(rt->image, rt->w, rt->h, p.o.fmt, p.o.raw_row, p.o.raw_len, base, base + p.off_chunks,
-                       (uint32_t *)(base + p.off_sizes), d_offsets, base + p.off_pay, (uint32_t *)(base + p.off_crc),
-                       (unsigned long long *)(base + p.off_adler), p.n_crc_max, p.n_adler, s);
+    png_deflate_launch(rt, o, base, s);
     SAR_CUDA(cudaGetLastError());
     unsigned long long total = 0;
-    SAR_CUDA(cudaMemcpyAsync(&total, d_offsets + p.n_chunks, sizeof total, cudaMemcpyDeviceToHost, s));
+    SAR_CUDA(cudaMemcpyAsync(&total, base + o.off_offsets + o.n_chunks * sizeof(unsigned long long), sizeof total, cudaMemcpyDeviceToHost, s));
     SAR_CUDA(cudaStreamSynchronize(s));
-    if (total == 0 || total > p.pay_bound) return fail(SAR_ERR_CUDA, "deflate produced %llu bytes (bound %zu)", total, p.pay_bound);
-    const size_t need = p.o.header + (size_t)total + 20;
+    if (total == 0 || total > o.pay_bound) return fail(SAR_ERR_CUDA, "deflate produced %llu bytes (bound %zu)", total, o.pay_bound);
+    const size_t need = o.header + (size_t)total + 20;
     if (out_capacity < need) return fail(SAR_ERR_INVALID, "output needs %zu bytes (got %zu; sar_png_bound gives the worst case)", need, out_capacity);
     const size_t n_crc = ((size_t)total + PNG_CHUNK - 1) / PNG_CHUNK;
     std::vector<uint32_t> crc(n_crc);
-    std::vector<unsigned long long> adler(2 * p.n_adler);
-    memcpy(out, p.o.head, p.o.header);
-    put_be32(out + p.o.header - 10, (uint32_t)(2 + total + 4));      // IDAT length: zlib header + deflate stream + Adler-32
-    SAR_CUDA(cudaMemcpyAsync(out + p.o.header, base + p.off_pay, (size_t)total, cudaMemcpyDeviceToHost, s));
-    SAR_CUDA(cudaMemcpyAsync(crc.data(), base + p.off_crc, n_crc * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    SAR_CUDA(cudaMemcpyAsync(adler.data(), base + p.off_adler, adler.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    std::vector<unsigned long long> adler(2 * o.n_adler);
+    memcpy(out, o.head, o.header);
+    put_be32(out + o.header - 10, (uint32_t)(2 + total + 4));        // IDAT length: zlib header + deflate stream + Adler-32
+    SAR_CUDA(cudaMemcpyAsync(out + o.header, base + o.off_pay, (size_t)total, cudaMemcpyDeviceToHost, s));
+    SAR_CUDA(cudaMemcpyAsync(crc.data(), base + o.off_crc, n_crc * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    SAR_CUDA(cudaMemcpyAsync(adler.data(), base + o.off_adler, adler.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     SAR_CUDA(cudaStreamSynchronize(s));
-    png_fold(crc.data(), n_crc, (size_t)total, adler.data(), p.n_adler, p.o.raw_len, out + p.o.header + (size_t)total);
+    png_fold(crc.data(), n_crc, (size_t)total, adler.data(), o.n_adler, o.raw_len, out + o.header + (size_t)total);
     *out_bytes = need;
     return SAR_OK;
 }
@@ -1506,6 +1520,7 @@ static int seq_prepare(sar_renderer *r, size_t d, const sar_config &cfg, bool ne
         q.img_bytes = bytes;
     }
     if (!q.copy_stream) SAR_CUDA(cudaStreamCreateWithFlags(&q.copy_stream, cudaStreamNonBlocking));
+    if (!q.pay_stream) SAR_CUDA(cudaStreamCreateWithFlags(&q.pay_stream, cudaStreamNonBlocking));
     if (!q.h_max) SAR_CUDA(cudaHostAlloc((void **)&q.h_max, 2 * sizeof(uint32_t), cudaHostAllocPortable));
     for (int k = 0; k < 2; ++k) {
         if (!q.rt[k]) if (int rc = sar_runtime_new(cfg.width, cfg.height, r->devices[d], &q.rt[k])) return rc;
@@ -1515,7 +1530,7 @@ static int seq_prepare(sar_renderer *r, size_t d, const sar_config &cfg, bool ne
             SAR_CUDA(cudaHostAlloc((void **)&q.stage[k], o.total, cudaHostAllocPortable));
         }
         const bool convert = !(o.fmt == SAR_PIX_RGBA16 && o.order == ORDER_NATIVE) || o.container == SAR_FILE_PNG;
-        const size_t enc_need = align_up(o.payload, 256) + o.sums_bytes;
+        const size_t enc_need = o.deflate ? o.scratch : align_up(o.payload, 256) + o.sums_bytes;
         if (convert && (!q.enc[k] || q.enc_bytes < enc_need)) {
             cudaFree(q.enc[k]);
             q.enc[k] = nullptr;
@@ -1532,8 +1547,8 @@ static int seq_prepare(sar_renderer *r, size_t d, const sar_config &cfg, bool ne
     }
     // capacities of what was (re)allocated above
     if (need_stage && q.stage_bytes < o.total) q.stage_bytes = o.total;
-    if ((!(o.fmt == SAR_PIX_RGBA16 && o.order == ORDER_NATIVE) || o.container == SAR_FILE_PNG) &&
-        q.enc_bytes < align_up(o.payload, 256) + o.sums_bytes) q.enc_bytes = align_up(o.payload, 256) + o.sums_bytes;
+    const size_t enc_cap = o.deflate ? o.scratch : align_up(o.payload, 256) + o.sums_bytes;
+    if ((!(o.fmt == SAR_PIX_RGBA16 && o.order == ORDER_NATIVE) || o.container == SAR_FILE_PNG) && q.enc_bytes < enc_cap) q.enc_bytes = enc_cap;
     if (o.sums_bytes && q.sums_cap < o.sums_bytes) q.sums_cap = o.sums_bytes;
     return SAR_OK;
 }
@@ -1546,8 +1561,10 @@ static int sequence_core(sar_renderer *r, const sar_config *cfg_in, const double
     if (!r || !cfg_in || (!angles_rad && n_frames)) return fail(SAR_ERR_INVALID, "NULL argument");
     if (!frames_out && !cb16 && !cb8) return fail(SAR_ERR_INVALID, "need a frame array or a callback");
     uint8_t *const rgba_frames = frames_out;
-    const bool png = o.container == SAR_FILE_PNG;
-    const bool convert = !(o.fmt == SAR_PIX_RGBA16 && o.order == ORDER_NATIVE) || png;
+    const bool pngz = o.deflate;                                   // compressed PNG: frames of different sizes, callback only
+    const bool png = o.container == SAR_FILE_PNG && !pngz;
+    const bool convert = !(o.fmt == SAR_PIX_RGBA16 && o.order == ORDER_NATIVE) || png || pngz;
+    if (pngz && (frames_out || !cb8)) return fail(SAR_ERR_INVALID, "compressed PNG frames differ in size: pass a callback and no frame array");
     if (jobs_per_thread == 0) return fail(SAR_ERR_INVALID, "jobs_per_thread must be non-zero");
     if (flags & ~SAR_SEQ_SHARED_POINTS) return fail(SAR_ERR_INVALID, "unknown flags 0x%x", flags);
     if (int rc = check_config(cfg_in, nullptr)) return rc;
@@ -1587,6 +1604,22 @@ static int sequence_core(sar_renderer *r, const sar_config *cfg_in, const double
         SAR_CUDA(cudaSetDevice(r->devices[d]));
         SAR_CUDA(cudaEventSynchronize(r->seq[d].copied[slot]));
         uint8_t *bytes = rgba_frames ? rgba_frames + (size_t)g * frame_u16 : r->seq[d].stage[slot];
+        if (pngz) {
+            // the frame's stream length, CRC and Adler partial sums have arrived; fetch exactly that many bytes
+            seq_device &q = r->seq[d];
+            const uint8_t *hs = q.h_sums[slot];
+            const unsigned long long total = *reinterpret_cast<const unsigned long long *>(hs);
+            if (total == 0 || total > o.pay_bound) return fail(SAR_ERR_CUDA, "deflate produced %llu bytes (bound %zu)", total, o.pay_bound);
+            memcpy(bytes, o.head, o.header);
+            put_be32(bytes + o.header - 10, (uint32_t)(2 + total + 4));
+            SAR_CUDA(cudaMemcpyAsync(bytes + o.header, q.enc[slot] + o.off_pay, (size_t)total, cudaMemcpyDeviceToHost, q.pay_stream));
+            SAR_CUDA(cudaStreamSynchronize(q.pay_stream));
+            png_fold(reinterpret_cast<const uint32_t *>(hs + 8), ((size_t)total + PNG_CHUNK - 1) / PNG_CHUNK, (size_t)total,
+                     reinterpret_cast<const unsigned long long *>(hs + 8 + align_up(o.n_crc_max * sizeof(uint32_t), 8)), o.n_adler, o.raw_len,
+                     bytes + o.header + (size_t)total);
+            cb8(user, g, bytes, o.header + (size_t)total + 20);
+            return SAR_OK;
+        }
         if (png) png_trailer(o, r->seq[d].h_sums[slot], bytes + o.header + o.payload);   // Adler-32, IDAT CRC, IEND
         if (cb16) cb16(user, g, reinterpret_cast<const uint16_t *>(bytes));
         if (cb8) cb8(user, g, bytes, o.total);
@@ -1606,6 +1639,9 @@ static int sequence_core(sar_renderer *r, const sar_config *cfg_in, const double
         seq_device &q = r->seq[d];
         sar_runtime *rt = q.rt[slot];
         SAR_CUDA(cudaSetDevice(rt->device));
+        // compressed PNG: the slot's previous frame still sits in the slot's device buffers until finalize() has fetched it
+        if (pngz && g >= 2 * nd) if (int rc = finalize(g - 2 * (uint32_t)nd)) return rc;
+        SAR_CUDA(cudaSetDevice(rt->device));
         SAR_CUDA(cudaEventSynchronize(q.max_ready[slot]));
         sar_config cfg = cfgs[d];
         cfg.angle = angles_rad[g];
@@ -1616,7 +1652,10 @@ static int sequence_core(sar_renderer *r, const sar_config *cfg_in, const double
         launch_colorize(cp, rt->fast, rt->rec, rt->scal, rt->image, nullptr, cs);           // colorize, lib.rs:1080
         SAR_CUDA(cudaGetLastError());
         const size_t sums_off = align_up(o.payload, 256);
-        if (png) {                                                              // main.rs:78-89 minus the compressor
+        if (pngz) {                                                             // main.rs:78-89, compressor included
+            png_deflate_launch(rt, o, q.enc[slot], cs);
+            SAR_CUDA(cudaGetLastError());
+        } else if (png) {                                                       // main.rs:78-89 minus the compressor
             launch_png_pack(rt->image, q.enc[slot], rt->w, rt->h, o.fmt, o.raw_row, o.raw_len, o.n_blocks, cs);
             launch_png_sums(q.enc[slot], o.payload, o.raw_len, (uint32_t *)(q.enc[slot] + sums_off),
                             (unsigned long long *)(q.enc[slot] + sums_off + align_up(o.n_crc * 4, 8)), o.n_crc, o.n_adler, cs);
@@ -1629,6 +1668,16 @@ static int sequence_core(sar_renderer *r, const sar_config *cfg_in, const double
         SAR_CUDA(cudaStreamWaitEvent(q.copy_stream, q.rendered[slot], 0));
         // the slot's previous frame (g - 2 nd) is handed to the caller here — its copy finished a frame ago, so the
         // host does not stall, and the slot's staging buffer is free again before this frame's copy is queued
+        if (pngz) {
+            // only the stream's length and the partial checksums now; the stream itself is fetched by finalize(), exact size
+            uint8_t *hs = q.h_sums[slot];
+            SAR_CUDA(cudaMemcpyAsync(hs, q.enc[slot] + o.off_offsets + o.n_chunks * sizeof(unsigned long long), 8, cudaMemcpyDeviceToHost, q.copy_stream));
+            SAR_CUDA(cudaMemcpyAsync(hs + 8, q.enc[slot] + o.off_crc, o.n_crc_max * sizeof(uint32_t), cudaMemcpyDeviceToHost, q.copy_stream));
+            SAR_CUDA(cudaMemcpyAsync(hs + 8 + align_up(o.n_crc_max * sizeof(uint32_t), 8), q.enc[slot] + o.off_adler,
+                                     o.n_adler * 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, q.copy_stream));
+            SAR_CUDA(cudaEventRecord(q.copied[slot], q.copy_stream));
+            return SAR_OK;
+        }
         if (g >= 2 * nd) if (int rc = finalize(g - 2 * (uint32_t)nd)) return rc;
         uint8_t *dst = rgba_frames ? rgba_frames + (size_t)g * frame_u16 : q.stage[slot];
         memcpy(dst, o.head, o.header);
@@ -1690,7 +1739,9 @@ int sar_render_sequence_encoded(sar_renderer *r, const sar_config *cfg_in, const
     if (!cfg_in) return fail(SAR_ERR_INVALID, "NULL argument");
     OutSpec o;
     if (int rc = check_dims(cfg_in->width, cfg_in->height)) return rc;
-    if (int rc = make_outspec(cfg_in->width, cfg_in->height, pixel_format, container, o)) return rc;
+    if (container == SAR_FILE_PNG_DEFLATE) {
+        if (int rc = png_plan(cfg_in->width, cfg_in->height, pixel_format, o)) return rc;
+    } else if (int rc = make_outspec(cfg_in->width, cfg_in->height, pixel_format, container, o)) return rc;
     return sequence_core(r, cfg_in, angles_rad, n_frames, jobs_per_thread, seed, flags, o, frames_out, nullptr, cb, user);
 }
 

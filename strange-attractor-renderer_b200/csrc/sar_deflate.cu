@@ -43,38 +43,152 @@ __global__ void png_filter_kernel(const ushort4 *__restrict__ img, uint8_t *__re
 struct AtomicOr { __device__ __forceinline__ void operator()(uint32_t *w, uint32_t v) const { if (v) atomicOr(w, v); } };
 
 // One warp per CHUNK bytes of the scanline stream -> one deflate block in out[chunk * CHUNK_CAP ...] (zeroed by the caller),
-// its byte size in sizes[chunk].
+// its byte size in sizes[chunk].  The block's bytes are staged in shared memory, lane l's 512-byte range at l * 516 so that
+// the 32 lanes walk 32 different banks; the symbol sort, the canonical codes and the header are spread over the lanes,
+// only the two-queue Huffman construction itself runs on lane 0.
 constexpr unsigned int DFL_WARPS = 4;
+constexpr unsigned int DFL_PITCH = dfl::SUB + 4;                           // bytes between two lanes' ranges in shared memory
+constexpr unsigned int DFL_MASK_PITCH = dfl::SUB / 32u + 1u;               // words of match-start bits per lane (+1: bank spread)
+struct DflShared {
+    uint8_t bytes[dfl::LANES * DFL_PITCH];
+    uint32_t mask[dfl::LANES * DFL_MASK_PITCH];
+    uint32_t freq[dfl::NSYM + 2];
+    uint16_t code[dfl::NSYM + 2];
+    uint8_t len[dfl::NSYM + 2];
+    dfl::CodeScratch scratch;
+};
+struct SmemAt {                                                            // position of the stream -> staged byte
+    const uint8_t *sm; size_t base; uint32_t before;
+    __device__ __forceinline__ uint8_t operator()(size_t g) const
+    {
+        if (g < base) return (uint8_t)before;
+        const uint32_t r = (uint32_t)(g - base);
+        return sm[(r >> 9) * DFL_PITCH + (r & (dfl::SUB - 1u))];
+    }
+};
+static_assert(dfl::SUB == 512, "SmemAt shifts by 9");
+
 __global__ void __launch_bounds__(DFL_WARPS * 32) deflate_chunks_kernel(const uint8_t *__restrict__ raw, size_t raw_len,
                                                                         uint8_t *__restrict__ out, uint32_t *__restrict__ sizes,
                                                                         unsigned int n_chunks)
 {
-    __shared__ uint32_t s_freq[DFL_WARPS][dfl::NSYM + 2];
-    __shared__ uint16_t s_code[DFL_WARPS][dfl::NSYM + 2];
-    __shared__ uint8_t s_len[DFL_WARPS][dfl::NSYM + 2];
-    __shared__ dfl::CodeScratch s_scratch[DFL_WARPS];
+    extern __shared__ __align__(16) uint8_t dfl_smem[];
     const unsigned int warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    uint32_t *freq = s_freq[warp];
-    uint16_t *code = s_code[warp];
-    uint8_t *len = s_len[warp];
+    DflShared &S = reinterpret_cast<DflShared *>(dfl_smem)[warp];
+    uint32_t *freq = S.freq;
+    uint16_t *code = S.code;
+    uint8_t *len = S.len;
     for (unsigned int chunk = blockIdx.x * DFL_WARPS + warp; chunk < n_chunks; chunk += gridDim.x * DFL_WARPS) {
         const size_t g0 = (size_t)chunk * dfl::CHUNK;
         const size_t g1 = raw_len - g0 < dfl::CHUNK ? raw_len : g0 + dfl::CHUNK;
+        const uint32_t n_bytes = (uint32_t)(g1 - g0);
         const bool final = chunk + 1u == n_chunks;
         size_t a = g0 + (size_t)lane * dfl::SUB, b = a + dfl::SUB;
         if (a > g1) a = g1;
         if (b > g1) b = g1;
-        for (unsigned int s = lane; s < dfl::NSYM; s += 32u) freq[s] = s == dfl::EOB ? 1u : 0u;
+        // stage the block: 16-byte loads (g0 is a multiple of CHUNK, raw is 256-byte aligned), the tail byte by byte
+        for (uint32_t i = lane; i < dfl::CHUNK / 16u; i += 32u) {
+            const uint32_t r = i * 16u;
+            if (r >= n_bytes) break;
+            uint32_t *dst = reinterpret_cast<uint32_t *>(S.bytes + (r >> 9) * DFL_PITCH + (r & (dfl::SUB - 1u)));
+            if (r + 16u <= n_bytes) {
+                const uint4 v = *reinterpret_cast<const uint4 *>(raw + g0 + r);
+                dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+            } else {
+                for (uint32_t k = r; k < n_bytes; ++k) S.bytes[(k >> 9) * DFL_PITCH + (k & (dfl::SUB - 1u))] = raw[g0 + k];
+            }
+        }
+        for (unsigned int s = lane; s < dfl::NSYM + 2u; s += 32u) { freq[s] = s == dfl::EOB ? 1u : 0u; len[s] = 0; }
+        const SmemAt at{S.bytes, g0, g0 > 0 ? (uint32_t)raw[g0 - 1] : 0u};
         __syncwarp();
-        dfl::parse(raw, a, b, [&](uint32_t v) { atomicAdd(&freq[v], 1u); },
-                   [&](uint32_t l) { uint32_t sy, eb, ev; dfl::length_symbol(l, sy, eb, ev); atomicAdd(&freq[sy], 1u); });
-        __syncwarp();
-        if (lane == 0) {
-            dfl::code_lengths(freq, len, s_scratch[warp]);
-            dfl::canonical_codes(len, code);
+        // pass 1: the parse of dfl::parse(), done once: histogram of the tokens, and the tokens themselves left in place for
+        // the two later passes — a match overwrites its first byte with (length - 3) and sets that position's bit in the
+        // lane's mask; its other bytes are skipped from then on.  Runs are scanned a 32-bit word at a time.  (The last byte of
+        // a range is never overwritten — a match is at least 3 long — so the next lane's predecessor byte stays intact.)
+        uint8_t *my = S.bytes + lane * DFL_PITCH;
+        uint32_t *mask = S.mask + lane * DFL_MASK_PITCH;
+        const uint32_t n_my = (uint32_t)(b - a);
+        for (unsigned int w = 0; w < dfl::SUB / 32u; ++w) mask[w] = 0u;
+        {
+            uint32_t prev = a == 0 ? 256u : (lane == 0 ? at.before : (uint32_t)S.bytes[(lane - 1u) * DFL_PITCH + dfl::SUB - 1u]);
+            uint32_t i = 0;
+            while (i < n_my) {
+                const uint32_t bv = my[i];
+                if (bv == prev) {
+                    const uint32_t lim = n_my - i < 258u ? n_my : i + 258u;
+                    uint32_t e = i + 1u;
+                    bool stop = false;
+                    while (e < lim && (e & 3u)) { if (my[e] != bv) { stop = true; break; } ++e; }
+                    if (!stop) {
+                        const uint32_t pat = bv * 0x01010101u;
+                        while (e + 4u <= lim) {
+                            const uint32_t x = *reinterpret_cast<const uint32_t *>(my + e) ^ pat;
+                            if (x) { e += (uint32_t)(__ffs((int)x) - 1) >> 3; stop = true; break; }
+                            e += 4u;
+                        }
+                        if (!stop) while (e < lim && my[e] == bv) ++e;
+                    }
+                    const uint32_t l = e - i;
+                    if (l >= 3u) {
+                        uint32_t sy, eb, ev;
+                        dfl::length_symbol(l, sy, eb, ev);
+                        atomicAdd(&freq[sy], 1u);
+                        my[i] = (uint8_t)(l - 3u);
+                        mask[i >> 5] |= 1u << (i & 31u);
+                        i = e;
+                        continue;
+                    }
+                }
+                atomicAdd(&freq[bv], 1u);
+                prev = bv;
+                ++i;
+            }
         }
         __syncwarp();
-        const uint32_t mine = dfl::range_bits(raw, a, b, len);
+        // used symbols in ascending (frequency, symbol) order: every lane ranks its symbols against all of them
+        uint32_t n_used = 0;
+        for (unsigned int s = lane; s < dfl::NSYM; s += 32u) n_used += freq[s] ? 1u : 0u;
+        for (unsigned int d = 16; d > 0; d >>= 1) n_used += __shfl_xor_sync(0xFFFFFFFFu, n_used, d);
+        for (unsigned int s = lane; s < dfl::NSYM; s += 32u) {
+            const uint32_t f = freq[s];
+            if (f == 0u) continue;
+            uint32_t rank = 0;
+            for (unsigned int j = 0; j < dfl::NSYM; ++j) {
+                const uint32_t fj = freq[j];
+                rank += (fj != 0u && (fj < f || (fj == f && j < s))) ? 1u : 0u;
+            }
+            S.scratch.key[rank] = f;
+            S.scratch.sym[rank] = (uint16_t)s;
+        }
+        __syncwarp();
+        if (lane == 0) dfl::lengths_from_sorted(S.scratch, n_used, len);
+        __syncwarp();
+        // canonical codes (RFC 1951 §3.2.2): lane b owns the codes of length b
+        {
+            uint32_t cnt = 0;
+            if (lane >= 1u && lane <= dfl::MAX_BITS)
+                for (unsigned int s = 0; s < dfl::NSYM; ++s) cnt += len[s] == lane ? 1u : 0u;
+            uint32_t c = 0, mine = 0;
+            for (unsigned int bits = 1; bits <= dfl::MAX_BITS; ++bits) {
+                c = (c + __shfl_sync(0xFFFFFFFFu, cnt, bits - 1u)) << 1;
+                if (bits == lane) mine = c;
+            }
+            if (lane >= 1u && lane <= dfl::MAX_BITS)
+                for (unsigned int s = 0; s < dfl::NSYM; ++s)
+                    if (len[s] == lane) code[s] = (uint16_t)dfl::bit_reverse(mine++, lane);
+        }
+        __syncwarp();
+        // pass 2: what each lane's range costs, prefix sum -> where it starts
+        uint32_t mine = 0;
+        for (uint32_t i = 0; i < n_my;) {
+            if ((mask[i >> 5] >> (i & 31u)) & 1u) {
+                const uint32_t l = (uint32_t)my[i] + 3u;
+                uint32_t sy, eb, ev;
+                dfl::length_symbol(l, sy, eb, ev);
+                mine += len[sy] + eb + 1u;
+                i += l;
+            } else { mine += len[my[i]]; ++i; }
+        }
         uint32_t incl = mine;
         for (unsigned int d = 1; d < 32u; d <<= 1) {
             const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, d);
@@ -82,17 +196,32 @@ __global__ void __launch_bounds__(DFL_WARPS * 32) deflate_chunks_kernel(const ui
         }
         const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
         const size_t dyn_bits = (size_t)dfl::HEADER_BITS + total + len[dfl::EOB];
-        const size_t dyn_bytes = dfl::dynamic_block_bytes(dyn_bits, final), st_bytes = dfl::stored_block_bytes(g1 - g0);
+        const size_t dyn_bytes = dfl::dynamic_block_bytes(dyn_bits, final), st_bytes = dfl::stored_block_bytes(n_bytes);
         uint8_t *dst = out + (size_t)chunk * dfl::CHUNK_CAP;
         uint32_t *words = reinterpret_cast<uint32_t *>(dst);
         if (dyn_bytes < st_bytes) {
+            // header: lane 0 the fixed part, then every lane 9 of the 288 code lengths (4 bits each)
             if (lane == 0) {
                 dfl::BitSink<AtomicOr> hs(words, 0, AtomicOr());
-                dfl::put_header(hs, len, final);
+                dfl::put_header_fixed(hs, final);
                 hs.flush();
             }
+            {
+                dfl::BitSink<AtomicOr> ls(words, (size_t)dfl::HEADER_FIXED_BITS + 36u * lane, AtomicOr());
+                for (unsigned int k = lane * 9u; k < lane * 9u + 9u; ++k) ls.put(dfl::bit_reverse(k < dfl::NSYM ? len[k] : 1u, 4u), 4u);
+                ls.flush();
+            }
+            // pass 3: the tokens
             dfl::BitSink<AtomicOr> bs(words, (size_t)dfl::HEADER_BITS + (incl - mine), AtomicOr());
-            dfl::range_emit(bs, raw, a, b, len, code);
+            for (uint32_t i = 0; i < n_my;) {
+                if ((mask[i >> 5] >> (i & 31u)) & 1u) {
+                    const uint32_t l = (uint32_t)my[i] + 3u;
+                    uint32_t sy, eb, ev;
+                    dfl::length_symbol(l, sy, eb, ev);
+                    bs.put((uint32_t)code[sy] | (ev << len[sy]), len[sy] + eb + 1u);      // symbol, extra bits, distance code "0"
+                    i += l;
+                } else { const uint32_t v = my[i]; bs.put(code[v], len[v]); ++i; }
+            }
             bs.flush();
             if (lane == 31u) {
                 dfl::BitSink<AtomicOr> ts(words, (size_t)dfl::HEADER_BITS + total, AtomicOr());
@@ -105,13 +234,12 @@ __global__ void __launch_bounds__(DFL_WARPS * 32) deflate_chunks_kernel(const ui
             }
             if (lane == 0) sizes[chunk] = (uint32_t)dyn_bytes;
         } else {
-            const size_t n = g1 - g0;
             if (lane == 0) {
                 dst[0] = final ? 1 : 0;
-                dst[1] = (uint8_t)n; dst[2] = (uint8_t)(n >> 8); dst[3] = (uint8_t)~n; dst[4] = (uint8_t)(~n >> 8);
+                dst[1] = (uint8_t)n_bytes; dst[2] = (uint8_t)(n_bytes >> 8); dst[3] = (uint8_t)~n_bytes; dst[4] = (uint8_t)(~n_bytes >> 8);
                 sizes[chunk] = (uint32_t)st_bytes;
             }
-            for (size_t k = lane; k < n; k += 32u) dst[5 + k] = raw[g0 + k];
+            for (uint32_t k = lane; k < n_bytes; k += 32u) dst[5 + k] = raw[g0 + k];
         }
         __syncwarp();
     }
@@ -163,16 +291,37 @@ __global__ void deflate_sums_kernel(const uint8_t *__restrict__ pay, const unsig
     __syncthreads();
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t pay_len = (size_t)*total;
+    // pieces start at multiples of PNG_CHUNK of 256-byte aligned buffers: whole pieces are read 16 bytes at a time
     if (t < n_crc_max) {
         const size_t lo = t * PNG_CHUNK, hi = lo + PNG_CHUNK < pay_len ? lo + PNG_CHUNK : pay_len;
         uint32_t c = 0;
-        for (size_t i = lo; i < hi; ++i) c = table[(c ^ pay[i]) & 0xFFu] ^ (c >> 8);
+        size_t i = lo;
+        for (; i + 16 <= hi; i += 16) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(pay + i);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                c ^= w[q];
+                c = table[c & 0xFFu] ^ (c >> 8); c = table[c & 0xFFu] ^ (c >> 8);
+                c = table[c & 0xFFu] ^ (c >> 8); c = table[c & 0xFFu] ^ (c >> 8);
+            }
+        }
+        for (; i < hi; ++i) c = table[(c ^ pay[i]) & 0xFFu] ^ (c >> 8);
         crc[t] = c;
     }
     if (t < n_adler) {
         const size_t lo = t * PNG_CHUNK, hi = lo + PNG_CHUNK < raw_len ? lo + PNG_CHUNK : raw_len;
         unsigned long long a = 0, b = 0;
-        for (size_t k = lo; k < hi; ++k) { a += raw[k]; b += a; }
+        size_t k = lo;
+        for (; k + 16 <= hi; k += 16) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(raw + k);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { a += (w[q] >> (8 * e)) & 0xFFu; b += a; }
+        }
+        for (; k < hi; ++k) { a += raw[k]; b += a; }
         adler[2 * t] = a; adler[2 * t + 1] = b;
     }
 }
@@ -188,7 +337,15 @@ void launch_png_deflate(const uint16_t *rgba, unsigned int W, unsigned int H, un
     png_filter_kernel<<<(unsigned int)(g > 148u * 16u ? 148u * 16u : g), 256, 0, s>>>(reinterpret_cast<const ushort4 *>(rgba), raw, W, H, fmt, raw_row);
     cudaMemsetAsync(chunks, 0, (size_t)n_chunks * dfl::CHUNK_CAP, s);
     const unsigned int blocks = (n_chunks + DFL_WARPS - 1) / DFL_WARPS;
-    deflate_chunks_kernel<<<blocks > 148u * 8u ? 148u * 8u : blocks, DFL_WARPS * 32, 0, s>>>(raw, raw_len, chunks, sizes, n_chunks);
+    const size_t smem = DFL_WARPS * sizeof(DflShared);
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+        cudaFuncSetAttribute(deflate_chunks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set[dev] = true;
+    }
+    deflate_chunks_kernel<<<blocks > 148u * 2u ? 148u * 2u : blocks, DFL_WARPS * 32, smem, s>>>(raw, raw_len, chunks, sizes, n_chunks);
     deflate_scan_kernel<<<1, 1024, 0, s>>>(sizes, offsets, n_chunks);
     deflate_gather_kernel<<<n_chunks > 148u * 8u ? 148u * 8u : n_chunks, 256, 0, s>>>(chunks, sizes, offsets, pay, n_chunks);
     const size_t n = n_crc_max > n_adler ? n_crc_max : n_adler;

@@ -9,7 +9,8 @@
 //     own 1/32 of the block, and on these images it is what zlib's Z_RLE strategy does — 3.60 MB for the reference's
 //     poisson-saturne frame against the 3.63 MB of the file the reference published;
 //   * each block carries its own dynamic Huffman code (literal/length alphabet from the block's histogram, built by
-//     one lane, length-limited to 15 bits); a block that would not shrink is stored instead.
+//     the warp — the two-queue construction itself on one lane —, length-limited to 15 bits); a block that would not
+//     shrink is stored instead.
 // Everything that decides bits is in this header as host+device inline functions, so the very same code is exercised
 // on the CPU by tests/cpp/deflate_host.cpp (lanes emulated by a loop) against zlib's inflate.
 #pragma once
@@ -34,7 +35,8 @@ constexpr uint32_t MAX_BITS = 15;
 constexpr uint32_t CHUNK_CAP = CHUNK + 64;     // bytes reserved per block: the stored fallback needs 5 + CHUNK
 // block header: BFINAL + BTYPE (3), HLIT (5), HDIST (5), HCLEN (4), 19 code-length-code lengths (3 each), then the
 // 286 + 2 code lengths themselves in a flat 4-bit code (symbols 0..15 all of length 4: complete, no repeat codes)
-constexpr uint32_t HEADER_BITS = 3 + 5 + 5 + 4 + 19 * 3 + (NSYM + 2) * 4;
+constexpr uint32_t HEADER_FIXED_BITS = 3 + 5 + 5 + 4 + 19 * 3;
+constexpr uint32_t HEADER_BITS = HEADER_FIXED_BITS + (NSYM + 2) * 4;
 
 // length 3..258 -> (symbol 257..285, extra bits, extra value), RFC 1951 §3.2.5
 SAR_HD void length_symbol(uint32_t len, uint32_t &sym, uint32_t &ebits, uint32_t &eval)
@@ -51,46 +53,50 @@ SAR_HD void length_symbol(uint32_t len, uint32_t &sym, uint32_t &ebits, uint32_t
 
 SAR_HD uint32_t bit_reverse(uint32_t v, uint32_t n)
 {
+#ifdef __CUDA_ARCH__
+    return n ? __brev(v) >> (32u - n) : 0u;
+#endif
     uint32_t r = 0u;
     for (uint32_t i = 0; i < n; ++i) { r = (r << 1) | (v & 1u); v >>= 1; }
     return r;
 }
 
-// Greedy run-length parse of raw[g0, g1): a position whose byte equals its predecessor opens a match of distance 1 over
-// the rest of the run (at most 258 bytes, never past g1, at least 3), anything else is a literal.  The predecessor of g0
-// may lie in an earlier block: the 32 KB window of a deflate stream runs across blocks.
-template <class Lit, class Match>
-SAR_HD void parse(const uint8_t *raw, size_t g0, size_t g1, Lit &&lit, Match &&match)
+// Greedy run-length parse of positions [g0, g1) of the scanline stream, read through `at(g)`: a position whose byte equals
+// its predecessor opens a match of distance 1 over the rest of the run (at most 258 bytes, never past g1, at least 3),
+// anything else is a literal.  The predecessor of g0 may lie in an earlier block: the 32 KB window of a deflate stream
+// runs across blocks.  (`at` is a plain pointer read on the host and a shared-memory read on the device.)
+template <class At, class Lit, class Match>
+SAR_HD void parse(At &&at, size_t g0, size_t g1, Lit &&lit, Match &&match)
 {
     size_t g = g0;
+    uint32_t prev = g0 > 0 ? (uint32_t)at(g0 - 1) : 256u;     // 256: no predecessor (first byte of the stream)
     while (g < g1) {
-        const uint8_t b = raw[g];
-        if (g > 0 && raw[g - 1] == b) {
+        const uint32_t b = (uint32_t)at(g);
+        if (prev == b) {
             const size_t lim = g1 - g < 258u ? g1 : g + 258u;
             size_t e = g + 1;
-            while (e < lim && raw[e] == b) ++e;
+            while (e < lim && (uint32_t)at(e) == b) ++e;
             if (e - g >= 3u) { match((uint32_t)(e - g)); g = e; continue; }
         }
-        lit((uint32_t)b);
+        lit(b);
+        prev = b;
         ++g;
     }
 }
+struct PtrAt { const uint8_t *p; SAR_HD uint8_t operator()(size_t g) const { return p[g]; } };
 
 // Code lengths of an optimal prefix code for freq[0..NSYM), limited to MAX_BITS.  Serial (one lane): sort the used
 // symbols by frequency, run the in-place two-queue Huffman construction (Moffat & Katajainen: after the first pass a
 // node holds its parent's index, after the second its depth), then cap the depth by moving leaves down until the Kraft
 // sum is 1 again.  At least two symbols get a code, so the code is complete (zlib rejects incomplete literal codes).
 struct CodeScratch { uint32_t key[NSYM]; uint16_t sym[NSYM]; };
-SAR_HD void code_lengths(const uint32_t *freq, uint8_t *len, CodeScratch &w)
+// the used symbols in ascending (frequency, symbol) order -> w.key / w.sym; returns how many.  Serial form; the kernel
+// ranks the symbols with the whole warp instead (the order is unique, so both give the same arrays).
+SAR_HD uint32_t sort_symbols(const uint32_t *freq, CodeScratch &w)
 {
     uint32_t n = 0;
-    for (uint32_t s = 0; s < NSYM; ++s) { len[s] = 0; if (freq[s]) { w.key[n] = freq[s]; w.sym[n] = (uint16_t)s; ++n; } }
-    if (n < 2u) {                               // cannot happen for a block (EOB + one token), kept for safety
-        const uint32_t extra = (n == 1u && w.sym[0] == 0u) ? 1u : 0u;
-        w.key[n] = 1u; w.sym[n] = (uint16_t)extra; ++n;
-        if (n < 2u) { w.key[n] = 1u; w.sym[n] = (uint16_t)EOB; ++n; }
-    }
-    for (uint32_t gap = n / 2u; gap > 0u; gap /= 2u)           // shell sort, ascending by (frequency, symbol)
+    for (uint32_t s = 0; s < NSYM; ++s) if (freq[s]) { w.key[n] = freq[s]; w.sym[n] = (uint16_t)s; ++n; }
+    for (uint32_t gap = n / 2u; gap > 0u; gap /= 2u)           // shell sort
         for (uint32_t i = gap; i < n; ++i) {
             const uint32_t k = w.key[i]; const uint16_t s = w.sym[i];
             uint32_t j = i;
@@ -99,6 +105,11 @@ SAR_HD void code_lengths(const uint32_t *freq, uint8_t *len, CodeScratch &w)
             }
             w.key[j] = k; w.sym[j] = s;
         }
+    return n;
+}
+// w holds n >= 2 sorted symbols (a block always has its end-of-block symbol and at least one token); len[] must be zeroed
+SAR_HD void lengths_from_sorted(CodeScratch &w, uint32_t n, uint8_t *len)
+{
     uint32_t *a = w.key;
     if (n == 2u) { a[0] = 1u; a[1] = 1u; }
     else {
@@ -140,6 +151,21 @@ SAR_HD void code_lengths(const uint32_t *freq, uint8_t *len, CodeScratch &w)
     for (uint32_t bits = 1u; bits <= MAX_BITS; ++bits)
         for (uint32_t c = count[bits]; c > 0u; --c) len[w.sym[--j]] = (uint8_t)bits;
 }
+SAR_HD void code_lengths(const uint32_t *freq, uint8_t *len, CodeScratch &w)
+{
+    uint32_t fixed[NSYM];
+    bool patched = false;
+    uint32_t used = 0;
+    for (uint32_t s = 0; s < NSYM; ++s) { len[s] = 0; used += freq[s] ? 1u : 0u; }
+    if (used < 2u) {                             // cannot happen for a block, kept so that the function is total
+        for (uint32_t s = 0; s < NSYM; ++s) fixed[s] = freq[s];
+        fixed[EOB] = fixed[EOB] ? fixed[EOB] : 1u;
+        if (used == 0u || freq[EOB]) fixed[0] = fixed[0] ? fixed[0] : 1u;
+        patched = true;
+    }
+    const uint32_t n = sort_symbols(patched ? fixed : freq, w);
+    lengths_from_sorted(w, n, len);
+}
 
 // canonical codes (RFC 1951 §3.2.2), stored bit-reversed: deflate packs Huffman codes most significant bit first into a
 // stream that is otherwise filled from the least significant bit
@@ -169,9 +195,9 @@ struct BitSink {
     SAR_HD void flush() { if (fill) orw(words + word, (uint32_t)acc); acc = 0; }
 };
 
-// the block header for a dynamic block; `final` sets BFINAL
+// the block header for a dynamic block; `final` sets BFINAL.  The first HEADER_FIXED_BITS do not depend on the code.
 template <class Or>
-SAR_HD void put_header(BitSink<Or> &s, const uint8_t *len, bool final)
+SAR_HD void put_header_fixed(BitSink<Or> &s, bool final)
 {
     s.put(final ? 1u : 0u, 1u);
     s.put(2u, 2u);                                            // BTYPE = 10, dynamic Huffman
@@ -180,24 +206,30 @@ SAR_HD void put_header(BitSink<Or> &s, const uint8_t *len, bool final)
     s.put(15u, 4u);                                           // HCLEN: all 19 code-length-code lengths follow
     // order 16,17,18,0,8,7,9,6,10,5,11,4,12,3,13,2,14,1,15: the repeat codes unused (0), the lengths 0..15 in 4 bits each
     for (uint32_t i = 0; i < 19u; ++i) s.put(i < 3u ? 0u : 4u, 3u);
+}
+template <class Or>
+SAR_HD void put_header(BitSink<Or> &s, const uint8_t *len, bool final)
+{
+    put_header_fixed(s, final);
     for (uint32_t k = 0; k < NSYM; ++k) s.put(bit_reverse(len[k], 4u), 4u);
     s.put(bit_reverse(1u, 4u), 4u);
     s.put(bit_reverse(1u, 4u), 4u);
 }
 
 // bits one lane's range costs under the code `len` (a match adds its extra bits and the 1-bit distance code)
-SAR_HD uint32_t range_bits(const uint8_t *raw, size_t g0, size_t g1, const uint8_t *len)
+template <class At>
+SAR_HD uint32_t range_bits(At &&at, size_t g0, size_t g1, const uint8_t *len)
 {
     uint32_t bits = 0u;
-    parse(raw, g0, g1, [&](uint32_t b) { bits += len[b]; },
+    parse(at, g0, g1, [&](uint32_t b) { bits += len[b]; },
           [&](uint32_t l) { uint32_t sy, eb, ev; length_symbol(l, sy, eb, ev); bits += len[sy] + eb + 1u; });
     return bits;
 }
 
-template <class Or>
-SAR_HD void range_emit(BitSink<Or> &s, const uint8_t *raw, size_t g0, size_t g1, const uint8_t *len, const uint16_t *code)
+template <class Or, class At>
+SAR_HD void range_emit(BitSink<Or> &s, At &&at, size_t g0, size_t g1, const uint8_t *len, const uint16_t *code)
 {
-    parse(raw, g0, g1, [&](uint32_t b) { s.put(code[b], len[b]); },
+    parse(at, g0, g1, [&](uint32_t b) { s.put(code[b], len[b]); },
           [&](uint32_t l) {
               uint32_t sy, eb, ev;
               length_symbol(l, sy, eb, ev);

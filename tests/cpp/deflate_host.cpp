@@ -30,22 +30,27 @@ static size_t chunk_host(const uint8_t *raw, size_t raw_len, unsigned chunk, uns
     }
     for (unsigned s = 0; s < dfl::NSYM; ++s) freq[s] = s == dfl::EOB ? 1u : 0u;
     for (unsigned lane = 0; lane < 32; ++lane)
-        dfl::parse(raw, a[lane], b[lane], [&](uint32_t v) { ++freq[v]; },
+        dfl::parse(dfl::PtrAt{raw}, a[lane], b[lane], [&](uint32_t v) { ++freq[v]; },
                    [&](uint32_t l) { uint32_t sy, eb, ev; dfl::length_symbol(l, sy, eb, ev); ++freq[sy]; });
     dfl::code_lengths(freq, len, scratch);
     dfl::canonical_codes(len, code);
     uint32_t mine[32], excl[32], total = 0;
-    for (unsigned lane = 0; lane < 32; ++lane) { mine[lane] = dfl::range_bits(raw, a[lane], b[lane], len); excl[lane] = total; total += mine[lane]; }
+    for (unsigned lane = 0; lane < 32; ++lane) { mine[lane] = dfl::range_bits(dfl::PtrAt{raw}, a[lane], b[lane], len); excl[lane] = total; total += mine[lane]; }
     const size_t dyn_bits = (size_t)dfl::HEADER_BITS + total + len[dfl::EOB];
     const size_t dyn_bytes = dfl::dynamic_block_bytes(dyn_bits, final), st_bytes = dfl::stored_block_bytes(g1 - g0);
     uint32_t *words = reinterpret_cast<uint32_t *>(dst);
     if (dyn_bytes < st_bytes) {
-        dfl::BitSink<HostOr> hs(words, 0, HostOr());
-        dfl::put_header(hs, len, final);
+        dfl::BitSink<HostOr> hs(words, 0, HostOr());              // as the kernel: lane 0 the fixed part, every lane 9 lengths
+        dfl::put_header_fixed(hs, final);
         hs.flush();
         for (unsigned lane = 0; lane < 32; ++lane) {
+            dfl::BitSink<HostOr> ls(words, (size_t)dfl::HEADER_FIXED_BITS + 36u * lane, HostOr());
+            for (unsigned k = lane * 9u; k < lane * 9u + 9u; ++k) ls.put(dfl::bit_reverse(k < dfl::NSYM ? len[k] : 1u, 4u), 4u);
+            ls.flush();
+        }
+        for (unsigned lane = 0; lane < 32; ++lane) {
             dfl::BitSink<HostOr> bs(words, (size_t)dfl::HEADER_BITS + excl[lane], HostOr());
-            dfl::range_emit(bs, raw, a[lane], b[lane], len, code);
+            dfl::range_emit(bs, dfl::PtrAt{raw}, a[lane], b[lane], len, code);
             bs.flush();
         }
         dfl::BitSink<HostOr> ts(words, (size_t)dfl::HEADER_BITS + total, HostOr());

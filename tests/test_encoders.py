@@ -94,7 +94,7 @@ def test_device_conversion_matches_oracle_bytes(oracle):
         cfg.transparent = transparent
         img = S.colorize(cfg, rt)
         for fmt in S.PixelFormat:
-            for cont in S.Container:
+            for cont in S.Container:                              # PngDeflate: no fixed-size form on either side
                 ref = oracle.encode(img, fmt.value, cont.value)
                 if ref is None:
                     with pytest.raises(S.SarError):
@@ -228,4 +228,39 @@ def test_device_png_deflate_decodes_to_the_reference_pixels(oracle):
     raw_len = 1080 * (1 + 1920 * 6)
     print(f"\npng deflate 1920x1080 RGB16: {raw_len} -> {len(png)} bytes ({len(png) / raw_len:.3f}), {dt * 1e3:.2f} ms incl. copy-out")
     assert len(png) < 0.45 * raw_len
+    r.shutdown()
+
+
+@pytest.mark.gpu
+def test_sequence_of_compressed_png_frames(oracle):
+    """sar_render_sequence_encoded with SAR_FILE_PNG_DEFLATE (main.rs:496-512 with the default PNG branch of
+    write_image_matches): every frame a complete compressed PNG handed to the callback in frame order; decodes to the
+    pixels of the same frame rendered alone; the fixed-size entry points refuse the variable-size container."""
+    import strange_attractor_renderer_b200 as S
+
+    cfg = S.Config.solar_sail()
+    cfg.width, cfg.height, cfg.iterations, cfg.transparent = 320, 200, 2_000_000, False
+    angles = S.angle_iter(0.0, 70.0, 10.0)                        # 7 frames: more than the two slots per device
+    r = S.ParallelRenderer.new(threads=2048)
+    plain = S.render_sequence(r, cfg, angles, 2, seed=3)
+    order = []
+    frames = {}
+    S.render_sequence_encoded(r, cfg, angles, 2, S.PixelFormat.Rgb16, S.Container.PngDeflate, seed=3,
+                              callback=lambda f, b: (order.append(f), frames.__setitem__(f, bytes(b))))
+    assert order == list(range(len(angles)))
+    for f in range(len(angles)):
+        samples, n = _png_rows(frames[f], 320, 200, 6)
+        assert np.array_equal(samples, plain[f][..., :3].astype(">u2").view(np.uint8).reshape(200, 320 * 6)), f
+        assert len(frames[f]) < 0.7 * 200 * (1 + 320 * 6)
+    # without a callback the wrapper collects the frames; 8-bit RGBA
+    got = S.render_sequence_encoded(r, cfg, angles[:3], 2, S.PixelFormat.Rgba8, S.Container.PngDeflate, seed=3)
+    for f in range(3):
+        samples, _ = _png_rows(got[f].tobytes(), 320, 200, 4)
+        want = ((plain[f].astype(np.uint32) + 128) // 257).astype(np.uint8)
+        want[..., 3] = 255                                        # cfg.transparent = False: alpha 65535
+        assert np.array_equal(samples, want.reshape(200, 320 * 4)), f
+    L = S._native.lib()
+    assert L.sar_encoded_size(320, 200, 1, 4) == 0
+    with pytest.raises(S.SarError):
+        S.encode_image(r.runtime(), S.PixelFormat.Rgb16, S.Container.PngDeflate)
     r.shutdown()
