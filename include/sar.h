@@ -265,8 +265,8 @@ int  sar_render_sequence(sar_renderer *r, const sar_config *cfg, const double *a
  * (main.rs:52-57): RGBA16 as is, to_rgb16(), to_rgba8(), to_rgb8(), and hands
  * image.as_bytes() to an `image`-crate encoder (PAM main.rs:62-68, BMP
  * main.rs:70-76, PNG main.rs:78-89).  Here the conversion runs on the device
- * and the two RAW containers are written around it; PNG (deflate) is left to
- * the caller, who gets the converted bytes (SAR_FILE_RAW).
+ * and the containers are written around it; the PNG branch exists both with
+ * the compressor (sar_runtime_encode_png, below) and without (SAR_FILE_PNG).
  * Third-party arithmetic: the u16 -> u8 narrowing of to_rgba8/to_rgb8 is
  * image 0.25's `FromPrimitive<u16> for u8`, (c + 128) / 257 =
  * round(c*255/65535); that crate is not vendored in the reference, so this is

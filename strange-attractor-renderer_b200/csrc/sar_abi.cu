@@ -1218,7 +1218,7 @@ int sar_render_parallel(sar_renderer *r, const sar_config *cfg_in, uint64_t jobs
 // `write_image_matches` converts the FinalImage (main.rs:52-57: RGBA16 as is, to_rgb16, to_rgba8, to_rgb8)
 // and hands `image.as_bytes()` to an encoder of the `image` crate (PAM main.rs:62-68, BMP :70-76, PNG :78-89).
 // Here the conversion runs on the device (convert_kernel) and the two RAW containers are written around it:
-// the host only formats the header.  PNG (deflate) stays with the caller: hand it the RAW bytes.
+// the host only formats the header.  The PNG branch: stored blocks (SAR_FILE_PNG) or compressed on the device (sar_runtime_encode_png).
 struct OutSpec {
     uint32_t fmt = SAR_PIX_RGBA16, container = SAR_FILE_RAW;
     uint32_t order = ORDER_NATIVE;

@@ -349,7 +349,9 @@ void launch_png_deflate(const uint16_t *rgba, unsigned int W, unsigned int H, un
     deflate_scan_kernel<<<1, 1024, 0, s>>>(sizes, offsets, n_chunks);
     deflate_gather_kernel<<<n_chunks > 148u * 8u ? 148u * 8u : n_chunks, 256, 0, s>>>(chunks, sizes, offsets, pay, n_chunks);
     const size_t n = n_crc_max > n_adler ? n_crc_max : n_adler;
-    deflate_sums_kernel<<<(unsigned int)((n + 127) / 128), 128, 0, s>>>(pay, offsets + n_chunks, raw, raw_len, crc, adler, n_crc_max, n_adler);
+    // one piece per thread is a long serial chain (4 096 dependent table look-ups): few threads per block, so that the
+    // ~3 000 pieces of a frame spread over all SMs
+    deflate_sums_kernel<<<(unsigned int)((n + 31) / 32), 32, 0, s>>>(pay, offsets + n_chunks, raw, raw_len, crc, adler, n_crc_max, n_adler);
     bump_launches(5);
 }
 
