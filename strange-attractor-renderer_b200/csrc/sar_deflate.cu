@@ -42,13 +42,16 @@ __global__ void png_filter_kernel(const ushort4 *__restrict__ img, uint8_t *__re
 
 struct AtomicOr { __device__ __forceinline__ void operator()(uint32_t *w, uint32_t v) const { if (v) atomicOr(w, v); } };
 
-// One warp per CHUNK bytes of the scanline stream -> one deflate block in out[chunk * CHUNK_CAP ...] (zeroed by the caller),
-// its byte size in sizes[chunk].  The block's bytes are staged in shared memory, lane l's 512-byte range at l * 516 so that
-// the 32 lanes walk 32 different banks; the symbol sort, the canonical codes and the header are spread over the lanes,
-// only the two-queue Huffman construction itself runs on lane 0.
-constexpr unsigned int DFL_WARPS = 4;
+// One thread block of dfl::LANES lanes per CHUNK bytes of the scanline stream -> one deflate block in
+// out[chunk * CHUNK_CAP ...] (zeroed by the caller), its byte size in sizes[chunk].  The block's bytes are staged in shared
+// memory, lane l's SUB-byte range at l * (SUB + 4) so that the lanes of a warp walk 32 different banks; the symbol sort, the
+// canonical codes and the header are spread over the lanes, only the two-queue Huffman construction itself runs on one.
+// A deflate block is one chain of dependent work (ncu: 115 K warp instructions when one warp did it all, §profiles), so
+// its latency is what a frame's encode costs: hence several warps per block of the stream, not several blocks per warp.
 constexpr unsigned int DFL_PITCH = dfl::SUB + 4;                           // bytes between two lanes' ranges in shared memory
 constexpr unsigned int DFL_MASK_PITCH = dfl::SUB / 32u + 1u;               // words of match-start bits per lane (+1: bank spread)
+constexpr unsigned int DFL_SUB_SHIFT = 8;
+static_assert(dfl::SUB == (1u << DFL_SUB_SHIFT) && dfl::LANES % 32u == 0 && dfl::LANES * dfl::SUB == dfl::CHUNK, "lane geometry");
 struct DflShared {
     uint8_t bytes[dfl::LANES * DFL_PITCH];
     uint32_t mask[dfl::LANES * DFL_MASK_PITCH];
@@ -56,29 +59,21 @@ struct DflShared {
     uint16_t code[dfl::NSYM + 2];
     uint8_t len[dfl::NSYM + 2];
     dfl::CodeScratch scratch;
+    uint32_t warp_bits[dfl::LANES / 32u];
+    uint32_t n_used;
 };
-struct SmemAt {                                                            // position of the stream -> staged byte
-    const uint8_t *sm; size_t base; uint32_t before;
-    __device__ __forceinline__ uint8_t operator()(size_t g) const
-    {
-        if (g < base) return (uint8_t)before;
-        const uint32_t r = (uint32_t)(g - base);
-        return sm[(r >> 9) * DFL_PITCH + (r & (dfl::SUB - 1u))];
-    }
-};
-static_assert(dfl::SUB == 512, "SmemAt shifts by 9");
+__device__ __forceinline__ uint32_t dfl_slot(uint32_t r) { return (r >> DFL_SUB_SHIFT) * DFL_PITCH + (r & (dfl::SUB - 1u)); }
 
-__global__ void __launch_bounds__(DFL_WARPS * 32) deflate_chunks_kernel(const uint8_t *__restrict__ raw, size_t raw_len,
-                                                                        uint8_t *__restrict__ out, uint32_t *__restrict__ sizes,
-                                                                        unsigned int n_chunks)
+__global__ void __launch_bounds__(dfl::LANES) deflate_chunks_kernel(const uint8_t *__restrict__ raw, size_t raw_len,
+                                                                   uint8_t *__restrict__ out, uint32_t *__restrict__ sizes,
+                                                                   unsigned int n_chunks)
 {
-    extern __shared__ __align__(16) uint8_t dfl_smem[];
-    const unsigned int warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    DflShared &S = reinterpret_cast<DflShared *>(dfl_smem)[warp];
+    __shared__ __align__(16) DflShared S;
+    const unsigned int lane = threadIdx.x, wlane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     uint32_t *freq = S.freq;
     uint16_t *code = S.code;
     uint8_t *len = S.len;
-    for (unsigned int chunk = blockIdx.x * DFL_WARPS + warp; chunk < n_chunks; chunk += gridDim.x * DFL_WARPS) {
+    for (unsigned int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
         const size_t g0 = (size_t)chunk * dfl::CHUNK;
         const size_t g1 = raw_len - g0 < dfl::CHUNK ? raw_len : g0 + dfl::CHUNK;
         const uint32_t n_bytes = (uint32_t)(g1 - g0);
@@ -87,20 +82,21 @@ __global__ void __launch_bounds__(DFL_WARPS * 32) deflate_chunks_kernel(const ui
         if (a > g1) a = g1;
         if (b > g1) b = g1;
         // stage the block: 16-byte loads (g0 is a multiple of CHUNK, raw is 256-byte aligned), the tail byte by byte
-        for (uint32_t i = lane; i < dfl::CHUNK / 16u; i += 32u) {
+        for (uint32_t i = lane; i < dfl::CHUNK / 16u; i += dfl::LANES) {
             const uint32_t r = i * 16u;
             if (r >= n_bytes) break;
-            uint32_t *dst = reinterpret_cast<uint32_t *>(S.bytes + (r >> 9) * DFL_PITCH + (r & (dfl::SUB - 1u)));
             if (r + 16u <= n_bytes) {
+                uint32_t *dst = reinterpret_cast<uint32_t *>(S.bytes + dfl_slot(r));
                 const uint4 v = *reinterpret_cast<const uint4 *>(raw + g0 + r);
                 dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
             } else {
-                for (uint32_t k = r; k < n_bytes; ++k) S.bytes[(k >> 9) * DFL_PITCH + (k & (dfl::SUB - 1u))] = raw[g0 + k];
+                for (uint32_t k = r; k < n_bytes; ++k) S.bytes[dfl_slot(k)] = raw[g0 + k];
             }
         }
-        for (unsigned int s = lane; s < dfl::NSYM + 2u; s += 32u) { freq[s] = s == dfl::EOB ? 1u : 0u; len[s] = 0; }
-        const SmemAt at{S.bytes, g0, g0 > 0 ? (uint32_t)raw[g0 - 1] : 0u};
-        __syncwarp();
+        for (unsigned int s = lane; s < dfl::NSYM + 2u; s += dfl::LANES) { freq[s] = s == dfl::EOB ? 1u : 0u; len[s] = 0; }
+        if (lane == 0) S.n_used = 0u;
+        const uint32_t before = g0 > 0 ? (uint32_t)raw[g0 - 1] : 0u;
+        __syncthreads();
         // pass 1: the parse of dfl::parse(), done once: histogram of the tokens, and the tokens themselves left in place for
         // the two later passes — a match overwrites its first byte with (length - 3) and sets that position's bit in the
         // lane's mask; its other bytes are skipped from then on.  Runs are scanned a 32-bit word at a time.  (The last byte of
@@ -110,7 +106,7 @@ __global__ void __launch_bounds__(DFL_WARPS * 32) deflate_chunks_kernel(const ui
         const uint32_t n_my = (uint32_t)(b - a);
         for (unsigned int w = 0; w < dfl::SUB / 32u; ++w) mask[w] = 0u;
         {
-            uint32_t prev = a == 0 ? 256u : (lane == 0 ? at.before : (uint32_t)S.bytes[(lane - 1u) * DFL_PITCH + dfl::SUB - 1u]);
+            uint32_t prev = a == 0 ? 256u : (lane == 0 ? before : (uint32_t)S.bytes[(lane - 1u) * DFL_PITCH + dfl::SUB - 1u]);
             uint32_t i = 0;
             while (i < n_my) {
                 const uint32_t bv = my[i];
@@ -144,12 +140,15 @@ __global__ void __launch_bounds__(DFL_WARPS * 32) deflate_chunks_kernel(const ui
                 ++i;
             }
         }
-        __syncwarp();
+        __syncthreads();
         // used symbols in ascending (frequency, symbol) order: every lane ranks its symbols against all of them
-        uint32_t n_used = 0;
-        for (unsigned int s = lane; s < dfl::NSYM; s += 32u) n_used += freq[s] ? 1u : 0u;
-        for (unsigned int d = 16; d > 0; d >>= 1) n_used += __shfl_xor_sync(0xFFFFFFFFu, n_used, d);
-        for (unsigned int s = lane; s < dfl::NSYM; s += 32u) {
+        {
+            uint32_t used = 0;
+            for (unsigned int s = lane; s < dfl::NSYM; s += dfl::LANES) used += freq[s] ? 1u : 0u;
+            for (unsigned int d = 16; d > 0; d >>= 1) used += __shfl_xor_sync(0xFFFFFFFFu, used, d);
+            if (wlane == 0) atomicAdd(&S.n_used, used);
+        }
+        for (unsigned int s = lane; s < dfl::NSYM; s += dfl::LANES) {
             const uint32_t f = freq[s];
             if (f == 0u) continue;
             uint32_t rank = 0;
@@ -160,25 +159,25 @@ __global__ void __launch_bounds__(DFL_WARPS * 32) deflate_chunks_kernel(const ui
             S.scratch.key[rank] = f;
             S.scratch.sym[rank] = (uint16_t)s;
         }
-        __syncwarp();
-        if (lane == 0) dfl::lengths_from_sorted(S.scratch, n_used, len);
-        __syncwarp();
-        // canonical codes (RFC 1951 §3.2.2): lane b owns the codes of length b
-        {
+        __syncthreads();
+        if (lane == 0) dfl::lengths_from_sorted(S.scratch, S.n_used, len);
+        __syncthreads();
+        // canonical codes (RFC 1951 §3.2.2): lane b of the first warp owns the codes of length b
+        if (warp == 0) {
             uint32_t cnt = 0;
-            if (lane >= 1u && lane <= dfl::MAX_BITS)
-                for (unsigned int s = 0; s < dfl::NSYM; ++s) cnt += len[s] == lane ? 1u : 0u;
-            uint32_t c = 0, mine = 0;
+            if (wlane >= 1u && wlane <= dfl::MAX_BITS)
+                for (unsigned int s = 0; s < dfl::NSYM; ++s) cnt += len[s] == wlane ? 1u : 0u;
+            uint32_t c = 0, first = 0;
             for (unsigned int bits = 1; bits <= dfl::MAX_BITS; ++bits) {
                 c = (c + __shfl_sync(0xFFFFFFFFu, cnt, bits - 1u)) << 1;
-                if (bits == lane) mine = c;
+                if (bits == wlane) first = c;
             }
-            if (lane >= 1u && lane <= dfl::MAX_BITS)
+            if (wlane >= 1u && wlane <= dfl::MAX_BITS)
                 for (unsigned int s = 0; s < dfl::NSYM; ++s)
-                    if (len[s] == lane) code[s] = (uint16_t)dfl::bit_reverse(mine++, lane);
+                    if (len[s] == wlane) code[s] = (uint16_t)dfl::bit_reverse(first++, wlane);
         }
-        __syncwarp();
-        // pass 2: what each lane's range costs, prefix sum -> where it starts
+        __syncthreads();
+        // pass 2: what each lane's range costs; prefix sum over the block -> where it starts
         uint32_t mine = 0;
         for (uint32_t i = 0; i < n_my;) {
             if ((mask[i >> 5] >> (i & 31u)) & 1u) {
@@ -192,27 +191,33 @@ __global__ void __launch_bounds__(DFL_WARPS * 32) deflate_chunks_kernel(const ui
         uint32_t incl = mine;
         for (unsigned int d = 1; d < 32u; d <<= 1) {
             const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-            if (lane >= d) incl += up;
+            if (wlane >= d) incl += up;
         }
-        const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        if (wlane == 31u) S.warp_bits[warp] = incl;
+        __syncthreads();
+        uint32_t total = 0, start = incl - mine;
+        for (unsigned int w = 0; w < dfl::LANES / 32u; ++w) {
+            if (w < warp) start += S.warp_bits[w];
+            total += S.warp_bits[w];
+        }
         const size_t dyn_bits = (size_t)dfl::HEADER_BITS + total + len[dfl::EOB];
         const size_t dyn_bytes = dfl::dynamic_block_bytes(dyn_bits, final), st_bytes = dfl::stored_block_bytes(n_bytes);
         uint8_t *dst = out + (size_t)chunk * dfl::CHUNK_CAP;
         uint32_t *words = reinterpret_cast<uint32_t *>(dst);
         if (dyn_bytes < st_bytes) {
-            // header: lane 0 the fixed part, then every lane 9 of the 288 code lengths (4 bits each)
+            // header: lane 0 the fixed part, then each lane of the first warp 9 of the 288 code lengths (4 bits each)
             if (lane == 0) {
                 dfl::BitSink<AtomicOr> hs(words, 0, AtomicOr());
                 dfl::put_header_fixed(hs, final);
                 hs.flush();
             }
-            {
-                dfl::BitSink<AtomicOr> ls(words, (size_t)dfl::HEADER_FIXED_BITS + 36u * lane, AtomicOr());
-                for (unsigned int k = lane * 9u; k < lane * 9u + 9u; ++k) ls.put(dfl::bit_reverse(k < dfl::NSYM ? len[k] : 1u, 4u), 4u);
+            if (warp == 0) {
+                dfl::BitSink<AtomicOr> ls(words, (size_t)dfl::HEADER_FIXED_BITS + 36u * wlane, AtomicOr());
+                for (unsigned int k = wlane * 9u; k < wlane * 9u + 9u; ++k) ls.put(dfl::bit_reverse(k < dfl::NSYM ? len[k] : 1u, 4u), 4u);
                 ls.flush();
             }
             // pass 3: the tokens
-            dfl::BitSink<AtomicOr> bs(words, (size_t)dfl::HEADER_BITS + (incl - mine), AtomicOr());
+            dfl::BitSink<AtomicOr> bs(words, (size_t)dfl::HEADER_BITS + start, AtomicOr());
             for (uint32_t i = 0; i < n_my;) {
                 if ((mask[i >> 5] >> (i & 31u)) & 1u) {
                     const uint32_t l = (uint32_t)my[i] + 3u;
@@ -223,7 +228,7 @@ __global__ void __launch_bounds__(DFL_WARPS * 32) deflate_chunks_kernel(const ui
                 } else { const uint32_t v = my[i]; bs.put(code[v], len[v]); ++i; }
             }
             bs.flush();
-            if (lane == 31u) {
+            if (lane == dfl::LANES - 1u) {
                 dfl::BitSink<AtomicOr> ts(words, (size_t)dfl::HEADER_BITS + total, AtomicOr());
                 ts.put(code[dfl::EOB], len[dfl::EOB]);
                 ts.flush();
@@ -239,9 +244,9 @@ __global__ void __launch_bounds__(DFL_WARPS * 32) deflate_chunks_kernel(const ui
                 dst[1] = (uint8_t)n_bytes; dst[2] = (uint8_t)(n_bytes >> 8); dst[3] = (uint8_t)~n_bytes; dst[4] = (uint8_t)(~n_bytes >> 8);
                 sizes[chunk] = (uint32_t)st_bytes;
             }
-            for (uint32_t k = lane; k < n_bytes; k += 32u) dst[5 + k] = raw[g0 + k];
+            for (uint32_t k = lane; k < n_bytes; k += dfl::LANES) dst[5 + k] = raw[g0 + k];
         }
-        __syncwarp();
+        __syncthreads();
     }
 }
 
@@ -336,16 +341,8 @@ void launch_png_deflate(const uint16_t *rgba, unsigned int W, unsigned int H, un
     size_t g = (npix + 255) / 256;
     png_filter_kernel<<<(unsigned int)(g > 148u * 16u ? 148u * 16u : g), 256, 0, s>>>(reinterpret_cast<const ushort4 *>(rgba), raw, W, H, fmt, raw_row);
     cudaMemsetAsync(chunks, 0, (size_t)n_chunks * dfl::CHUNK_CAP, s);
-    const unsigned int blocks = (n_chunks + DFL_WARPS - 1) / DFL_WARPS;
-    const size_t smem = DFL_WARPS * sizeof(DflShared);
-    static bool attr_set[64] = {false};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-        cudaFuncSetAttribute(deflate_chunks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_set[dev] = true;
-    }
-    deflate_chunks_kernel<<<blocks > 148u * 2u ? 148u * 2u : blocks, DFL_WARPS * 32, smem, s>>>(raw, raw_len, chunks, sizes, n_chunks);
+    static_assert(sizeof(DflShared) <= 48 * 1024, "static shared memory");
+    deflate_chunks_kernel<<<n_chunks > 148u * 9u ? 148u * 9u : n_chunks, dfl::LANES, 0, s>>>(raw, raw_len, chunks, sizes, n_chunks);
     deflate_scan_kernel<<<1, 1024, 0, s>>>(sizes, offsets, n_chunks);
     deflate_gather_kernel<<<n_chunks > 148u * 8u ? 148u * 8u : n_chunks, 256, 0, s>>>(chunks, sizes, offsets, pay, n_chunks);
     const size_t n = n_crc_max > n_adler ? n_crc_max : n_adler;

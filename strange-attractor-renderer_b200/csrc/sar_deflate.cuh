@@ -3,10 +3,10 @@
 // stream is free to choose its own blocks and matches — only what it DECODES to is specified (RFC 1951) — so this is not a
 // restatement of that crate but a compressor shaped for a GPU:
 //   * the scanline stream (Sub-filtered, so the untouched 80 % of a frame is zeros) is cut into CHUNK-byte pieces, one
-//     deflate block each, one warp per block; every block ends on a byte boundary (an empty stored block, the "sync
+//     deflate block each, two warps per block; every block ends on a byte boundary (an empty stored block, the "sync
 //     flush" of zlib), so blocks are produced independently and concatenated;
 //   * matches are run-length only (distance 1, length 3..258): finding them needs no hash table, each lane parses its
-//     own 1/32 of the block, and on these images it is what zlib's Z_RLE strategy does — 3.60 MB for the reference's
+//     own 1/64 of the block, and on these images it is what zlib's Z_RLE strategy does — 3.60 MB for the reference's
 //     poisson-saturne frame against the 3.63 MB of the file the reference published;
 //   * each block carries its own dynamic Huffman code (literal/length alphabet from the block's histogram, built by
 //     the warp — the two-queue construction itself on one lane —, length-limited to 15 bits); a block that would not
@@ -27,7 +27,7 @@ namespace sar {
 namespace dfl {
 
 constexpr uint32_t CHUNK = 16384;              // scanline bytes per deflate block
-constexpr uint32_t LANES = 32;
+constexpr uint32_t LANES = 64;                 // lanes (two warps) that share one block of the stream
 constexpr uint32_t SUB = CHUNK / LANES;        // bytes parsed by one lane
 constexpr uint32_t NSYM = 286;                 // literal/length alphabet, RFC 1951 §3.2.5
 constexpr uint32_t EOB = 256;

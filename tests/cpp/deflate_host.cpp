@@ -1,5 +1,5 @@
 // Host harness for strange-attractor-renderer_b200/csrc/sar_deflate.cuh: the same inline functions the CUDA kernel
-// (sar_deflate.cu: deflate_chunks_kernel) calls, driven with the 32 lanes of a warp emulated by a loop, so that the
+// (sar_deflate.cu: deflate_chunks_kernel) calls, driven with the lanes of a block emulated by a loop, so that the
 // bit-level logic (run-length parse, length symbols, Huffman code construction and its 15-bit cap, canonical codes, block
 // header, bit packing at arbitrary offsets, sync flush, stored fallback) is checked on the CPU against zlib's inflate
 // (tests/test_deflate_host.py).  Built by the test with g++; not part of the product library.
@@ -22,20 +22,20 @@ static size_t chunk_host(const uint8_t *raw, size_t raw_len, unsigned chunk, uns
     const size_t g0 = (size_t)chunk * dfl::CHUNK;
     const size_t g1 = raw_len - g0 < dfl::CHUNK ? raw_len : g0 + dfl::CHUNK;
     const bool final = chunk + 1u == n_chunks;
-    size_t a[32], b[32];
-    for (unsigned lane = 0; lane < 32; ++lane) {
+    size_t a[dfl::LANES], b[dfl::LANES];
+    for (unsigned lane = 0; lane < dfl::LANES; ++lane) {
         a[lane] = g0 + (size_t)lane * dfl::SUB; b[lane] = a[lane] + dfl::SUB;
         if (a[lane] > g1) a[lane] = g1;
         if (b[lane] > g1) b[lane] = g1;
     }
     for (unsigned s = 0; s < dfl::NSYM; ++s) freq[s] = s == dfl::EOB ? 1u : 0u;
-    for (unsigned lane = 0; lane < 32; ++lane)
+    for (unsigned lane = 0; lane < dfl::LANES; ++lane)
         dfl::parse(dfl::PtrAt{raw}, a[lane], b[lane], [&](uint32_t v) { ++freq[v]; },
                    [&](uint32_t l) { uint32_t sy, eb, ev; dfl::length_symbol(l, sy, eb, ev); ++freq[sy]; });
     dfl::code_lengths(freq, len, scratch);
     dfl::canonical_codes(len, code);
-    uint32_t mine[32], excl[32], total = 0;
-    for (unsigned lane = 0; lane < 32; ++lane) { mine[lane] = dfl::range_bits(dfl::PtrAt{raw}, a[lane], b[lane], len); excl[lane] = total; total += mine[lane]; }
+    uint32_t mine[dfl::LANES], excl[dfl::LANES], total = 0;
+    for (unsigned lane = 0; lane < dfl::LANES; ++lane) { mine[lane] = dfl::range_bits(dfl::PtrAt{raw}, a[lane], b[lane], len); excl[lane] = total; total += mine[lane]; }
     const size_t dyn_bits = (size_t)dfl::HEADER_BITS + total + len[dfl::EOB];
     const size_t dyn_bytes = dfl::dynamic_block_bytes(dyn_bits, final), st_bytes = dfl::stored_block_bytes(g1 - g0);
     uint32_t *words = reinterpret_cast<uint32_t *>(dst);
@@ -48,7 +48,7 @@ static size_t chunk_host(const uint8_t *raw, size_t raw_len, unsigned chunk, uns
             for (unsigned k = lane * 9u; k < lane * 9u + 9u; ++k) ls.put(dfl::bit_reverse(k < dfl::NSYM ? len[k] : 1u, 4u), 4u);
             ls.flush();
         }
-        for (unsigned lane = 0; lane < 32; ++lane) {
+        for (unsigned lane = 0; lane < dfl::LANES; ++lane) {
             dfl::BitSink<HostOr> bs(words, (size_t)dfl::HEADER_BITS + excl[lane], HostOr());
             dfl::range_emit(bs, dfl::PtrAt{raw}, a[lane], b[lane], len, code);
             bs.flush();
