@@ -64,6 +64,10 @@ extern "C" {
     fn sar_colorize(cfg: *const SarConfig, rt: *const SarRuntime, rgba_u16: *mut u16, rgba_f32: *mut f32) -> c_int;
     fn sar_renderer_new(devices: *const c_int, n_devices: c_int, threads_per_device: u32, out: *mut *mut SarRenderer) -> c_int;
     fn sar_renderer_shutdown(r: *mut SarRenderer);
+    fn sar_renderer_runtime(r: *mut SarRenderer, out: *mut *mut SarRuntime) -> c_int;
+    fn sar_png_bound(width: u32, height: u32, pixel_format: u32) -> usize;
+    fn sar_runtime_encode_png(rt: *mut SarRuntime, pixel_format: u32, out: *mut u8, out_capacity: usize, out_bytes: *mut usize,
+                              stream: *mut std::ffi::c_void) -> c_int;
     fn sar_render_parallel(r: *mut SarRenderer, cfg: *const SarConfig, jobs_per_thread: u64, seed: u64,
                            init_xyz: *const f64, rgba_u16: *mut u16) -> c_int;
 }
@@ -218,6 +222,26 @@ pub fn colorize(config: &impl DeviceConfig, runtime: &Runtime) -> FinalImage {
     image::ImageBuffer::from_raw(pod.width, pod.height, raw).unwrap()
 }
 
+/// The default branch of `write_image_matches` (src/bin/main.rs:52-57, 78-89) for the image of the last `colorize` /
+/// `render_parallel` on this runtime: `(transparent, eight_bit)` picks RGBA16 / RGB16 / RGBA8 / RGB8, and the complete PNG
+/// file — filtered, deflated and checksummed on the device — comes back as bytes to hand to `File::write_all`.
+#[must_use]
+pub fn encode_png(runtime: &Runtime, width: u32, height: u32, transparent: bool, eight_bit: bool) -> Vec<u8> {
+    let fmt = match (transparent, eight_bit) {
+        (true, false) => 0u32,
+        (false, false) => 1,
+        (true, true) => 2,
+        (false, true) => 3,
+    };
+    let cap = unsafe { sar_png_bound(width, height, fmt) };
+    assert!(cap != 0, "image too large for one IDAT chunk");
+    let mut out = vec![0u8; cap];
+    let mut n = 0usize;
+    check(unsafe { sar_runtime_encode_png(runtime.handle, fmt, out.as_mut_ptr(), cap, &mut n, std::ptr::null_mut()) });
+    out.truncate(n);
+    out
+}
+
 /// `ParallelRenderer` (lib.rs:908-915): the worker threads are the GPU's trajectory lanes.
 pub struct ParallelRenderer {
     handle: *mut SarRenderer,
@@ -231,6 +255,13 @@ impl ParallelRenderer {
     }
     /// `shutdown(self)`, lib.rs:1020.
     pub fn shutdown(self) {}
+    /// The merged Runtime of the last `render_parallel` (borrowed from the renderer): what `encode_png` reads.
+    pub fn with_runtime<R>(&mut self, f: impl FnOnce(&Runtime) -> R) -> R {
+        let mut handle = std::ptr::null_mut();
+        check(unsafe { sar_renderer_runtime(self.handle, &mut handle) });
+        let borrowed = std::mem::ManuallyDrop::new(Runtime { handle, seed: 0, draws: 0 });
+        f(&borrowed)
+    }
 }
 impl Default for ParallelRenderer {
     fn default() -> Self {

@@ -282,18 +282,27 @@ __global__ void deflate_gather_kernel(const uint8_t *__restrict__ chunks, const 
 }
 
 // crc[t]: CRC-32 register (from 0, no conditioning) over bytes [t * PNG_CHUNK, ...) of the payload, whose length is the
-// device-side total; adler[2t], adler[2t+1]: (sum d, sum (len - j) d_j) over piece t of the scanline stream
+// device-side total; adler[2t], adler[2t+1]: (sum d, sum (len - j) d_j) over piece t of the scanline stream.  A piece is one
+// serial chain per thread, so the chain is kept short: CRC four bytes per step (slicing-by-4: four independent look-ups),
+// and the Adler pieces go to threads of their own (threads [n_crc_max, n_crc_max + n_adler)).
 __global__ void deflate_sums_kernel(const uint8_t *__restrict__ pay, const unsigned long long *__restrict__ total,
                                     const uint8_t *__restrict__ raw, size_t raw_len, uint32_t *__restrict__ crc,
                                     unsigned long long *__restrict__ adler, size_t n_crc_max, size_t n_adler)
 {
-    __shared__ uint32_t table[256];
+    __shared__ uint32_t table[4][256];
     for (unsigned int n = threadIdx.x; n < 256; n += blockDim.x) {
         uint32_t c = n;
         for (int k = 0; k < 8; ++k) c = (c & 1u) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
-        table[n] = c;
+        table[0][n] = c;
     }
     __syncthreads();
+    for (int k = 1; k < 4; ++k) {
+        for (unsigned int n = threadIdx.x; n < 256; n += blockDim.x) {
+            const uint32_t p = table[k - 1][n];
+            table[k][n] = (p >> 8) ^ table[0][p & 0xFFu];
+        }
+        __syncthreads();
+    }
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t pay_len = (size_t)*total;
     // pieces start at multiples of PNG_CHUNK of 256-byte aligned buffers: whole pieces are read 16 bytes at a time
@@ -307,15 +316,14 @@ __global__ void deflate_sums_kernel(const uint8_t *__restrict__ pay, const unsig
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 c ^= w[q];
-                c = table[c & 0xFFu] ^ (c >> 8); c = table[c & 0xFFu] ^ (c >> 8);
-                c = table[c & 0xFFu] ^ (c >> 8); c = table[c & 0xFFu] ^ (c >> 8);
+                c = table[3][c & 0xFFu] ^ table[2][(c >> 8) & 0xFFu] ^ table[1][(c >> 16) & 0xFFu] ^ table[0][c >> 24];
             }
         }
-        for (; i < hi; ++i) c = table[(c ^ pay[i]) & 0xFFu] ^ (c >> 8);
+        for (; i < hi; ++i) c = table[0][(c ^ pay[i]) & 0xFFu] ^ (c >> 8);
         crc[t] = c;
-    }
-    if (t < n_adler) {
-        const size_t lo = t * PNG_CHUNK, hi = lo + PNG_CHUNK < raw_len ? lo + PNG_CHUNK : raw_len;
+    } else if (t < n_crc_max + n_adler) {
+        const size_t u = t - n_crc_max;
+        const size_t lo = u * PNG_CHUNK, hi = lo + PNG_CHUNK < raw_len ? lo + PNG_CHUNK : raw_len;
         unsigned long long a = 0, b = 0;
         size_t k = lo;
         for (; k + 16 <= hi; k += 16) {
@@ -327,7 +335,7 @@ __global__ void deflate_sums_kernel(const uint8_t *__restrict__ pay, const unsig
                 for (int e = 0; e < 4; ++e) { a += (w[q] >> (8 * e)) & 0xFFu; b += a; }
         }
         for (; k < hi; ++k) { a += raw[k]; b += a; }
-        adler[2 * t] = a; adler[2 * t + 1] = b;
+        adler[2 * u] = a; adler[2 * u + 1] = b;
     }
 }
 
@@ -345,7 +353,7 @@ void launch_png_deflate(const uint16_t *rgba, unsigned int W, unsigned int H, un
     deflate_chunks_kernel<<<n_chunks > 148u * 9u ? 148u * 9u : n_chunks, dfl::LANES, 0, s>>>(raw, raw_len, chunks, sizes, n_chunks);
     deflate_scan_kernel<<<1, 1024, 0, s>>>(sizes, offsets, n_chunks);
     deflate_gather_kernel<<<n_chunks > 148u * 8u ? 148u * 8u : n_chunks, 256, 0, s>>>(chunks, sizes, offsets, pay, n_chunks);
-    const size_t n = n_crc_max > n_adler ? n_crc_max : n_adler;
+    const size_t n = n_crc_max + n_adler;
     // one piece per thread is a long serial chain (4 096 dependent table look-ups): few threads per block, so that the
     // ~3 000 pieces of a frame spread over all SMs
     deflate_sums_kernel<<<(unsigned int)((n + 31) / 32), 32, 0, s>>>(pay, offsets + n_chunks, raw, raw_len, crc, adler, n_crc_max, n_adler);
