@@ -264,3 +264,18 @@ def test_sequence_of_compressed_png_frames(oracle):
     with pytest.raises(S.SarError):
         S.encode_image(r.runtime(), S.PixelFormat.Rgb16, S.Container.PngDeflate)
     r.shutdown()
+
+
+def test_png_bound_and_variable_size_container_without_a_gpu():
+    """Host-only parts of the compressed-PNG API: the worst case is every 16 KB block stored (5 bytes each) around the
+    filtered scanlines; the variable-size container has no fixed-size form."""
+    from strange_attractor_renderer_b200 import _native as N
+
+    L = N.lib()
+    for (w, h, fmt, bpp) in ((1920, 1080, 1, 6), (1, 1, 0, 8), (2048, 2048, 3, 3), (8300, 5, 2, 4)):
+        raw = h * (1 + w * bpp)
+        blocks = (raw + 16383) // 16384
+        assert L.sar_png_bound(w, h, fmt) == 43 + raw + 5 * blocks + 20
+    assert L.sar_png_bound(0, 10, 1) == 0 and L.sar_png_bound(10, 10, 9) == 0
+    assert L.sar_encoded_size(64, 64, 1, N.SAR_FILE_PNG_DEFLATE) == 0
+    assert L.sar_encode_header(64, 64, 1, N.SAR_FILE_PNG_DEFLATE, None, 0, None) == N.SAR_ERR_INVALID
