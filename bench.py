@@ -219,6 +219,42 @@ def parity_frame(world, rank, local, group, preset="solar", depth=False, per_gpu
 
 
 # --------------------------------------------------------------------------------------------
+# The GPU's frame against the REFERENCE's own published output (outside every timed region)
+# --------------------------------------------------------------------------------------------
+def reference_image_check(count, steps, mx):
+    """`count` / `steps` / `max` of a 1e9-iteration poisson-saturne frame at 1920x1080 (the README's command, README.md:73)
+    against what tests/golden/make_inverse_fixtures.py recovered from media/poisson-saturne.png by inverting colorize
+    (integer counts and palette positions of 50 000 pixels that reproduce the PNG's 16-bit channels exactly, max 95 125).
+    The reference's seeds are unknowable, so equality is statistical: chi-square per pixel ~ 1 when both count fields are
+    Poisson draws of the same density (oracle vs oracle with another seed: 0.992); one pixel of shift gives > 60."""
+    import numpy as np
+
+    inv = np.load(os.path.join(ROOT, "tests", "golden", "media_inverse.npz"))
+    idx = inv["poisson_saturne_idx"].astype(np.int64)
+    n = inv["poisson_saturne_n"].astype(np.float64)
+    v = inv["poisson_saturne_v"].astype(np.float64)
+    rmax = int(inv["poisson_saturne_max"])
+    c = np.asarray(count).ravel().astype(np.float64)
+    st = np.asarray(steps).ravel()
+
+    def chi2(at):
+        y = c[np.clip(at, 0, c.size - 1)]
+        return float((((n - y) ** 2) / np.maximum(n + y, 1.0)).mean())
+
+    chi = chi2(idx)
+    off = min(chi2(idx + d) for d in (1, -1, 1920, -1920))
+    o = st[idx]
+    keep = (v < 5.0 / 6.0 - 1e-3) & (o < 5.0 / 6.0 - 1e-3) & (c[idx] > 0)      # the last palette segment is constant
+    dv = float(np.median(np.abs(v[keep] - o[keep]))) if keep.any() else None
+    mass = float(n.sum() / max(c[idx].sum(), 1.0))
+    ok = bool(0.85 < chi < 1.25 and off > 15.0 and abs(mass - 1.0) < 2e-3 and abs(mx - rmax) < 5.0 * rmax ** 0.5
+              and dv is not None and dv < 1e-4)
+    return {"vs": "media/poisson-saturne.png (reference's published image; count field recovered by inverting colorize)",
+            "pixels": int(idx.size), "chi2_per_pixel": chi, "chi2_one_pixel_off": off, "mass_ratio": mass,
+            "max": int(mx), "max_reference": rmax, "palette_position_median_abs_diff": dv, "ok": ok}
+
+
+# --------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------
 def run_ours(args):
@@ -373,6 +409,18 @@ def run_ours(args):
         if rank == 0:
             out["parity"] = {k: bool(p1[k] and p2[k]) for k in ("count", "zbuf", "steps", "image")}
             out["parity"].update({"vs": "oracle", "frames": [p1, p2]})
+    if rank == 0 and world == 1 and not args.no_parity and "parity" in out:
+        try:   # one more frame, the README's own command, against the reference's published image
+            rcfg = S.Config.poisson_saturne()
+            rcfg.width, rcfg.height, rcfg.iterations, rcfg.transparent = 1920, 1080, 1_000_000_000, False
+            rcfg.colors.brighness.offset = -0.25
+            rr = S.ParallelRenderer.new(devices=[local])
+            S.render_parallel(rr, rcfg, 1, seed=SEED)
+            rcount, rsteps, _rz, rmx = rr.runtime().download()
+            rr.shutdown()
+            out["parity"]["reference_image"] = reference_image_check(rcount, rsteps, rmx)
+        except Exception as e:  # never lose the bench line over the extra check
+            out["parity"]["reference_image"] = {"error": str(e)[:300]}
     if rank == 0 and world == 1 and not args.no_cpu_baseline and not (args.size or args.iterations_per_gpu or args.preset != "poisson-saturne"):
         threads = os.cpu_count() or 8
         iters = cpu_sample_size(threads)

@@ -178,3 +178,18 @@ def test_reference_palette_positions_equal_oracle_steps(oracle_renders, inverse,
         neg = v < -1e-3
         assert neg.sum() > 5_000 and np.median(np.abs(v[neg] - o[neg])) < 1e-4
         assert (o[neg] < 0).mean() > 0.99
+
+
+@pytest.mark.slow
+def test_bench_reference_image_check_on_oracle_data(oracle_renders):
+    """bench.py adds `parity.reference_image` to its JSON line (the GPU's README frame vs the published PNG); the function
+    that computes it is exercised here with the oracle's frame — bit-identical to what the GPU produces for the same jobs."""
+    import bench
+
+    img, count, steps, omax = oracle_renders("poisson_saturne")
+    res = bench.reference_image_check(count.reshape(1080, 1920), steps.reshape(1080, 1920), omax)
+    assert res["ok"], res
+    assert 0.9 < res["chi2_per_pixel"] < 1.1 and res["chi2_one_pixel_off"] > 50 and res["max_reference"] == 95_125
+    # a frame that is not the reference's (flipped) must fail it
+    bad = bench.reference_image_check(count.reshape(1080, 1920)[:, ::-1], steps.reshape(1080, 1920)[:, ::-1], omax)
+    assert not bad["ok"]
