@@ -390,6 +390,8 @@ def run_ours(args):
                     "ms_per_step": 1e3 * e2e_s / args.steps, "api": "sar_render_parallel (C ABI) with pinned host buffers" if world == 1
                     else "dist.Frame.step_host: per-rank C-ABI calls + NVLink stripe merge, image gathered on rank 0"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the round's ncu --set full capture "
+                                           "(profiles/roofline_traffic.json, profiles/r2_iterate_ncu_full.md); per launch, not re-measured per run",
                          "kernel": "iterate_kernel", "kernel_ms": it_ms, "algorithmic_bytes_per_iteration": ALGO_BYTES_PER_ITER,
                          "peak_source": peak_src,
                          "note": "the working set is L2-resident, so HBM is not what binds: the ceiling of this kernel is the rate of "
