@@ -193,3 +193,48 @@ def test_bench_reference_image_check_on_oracle_data(oracle_renders):
     # a frame that is not the reference's (flipped) must fail it
     bad = bench.reference_image_check(count.reshape(1080, 1920)[:, ::-1], steps.reshape(1080, 1920)[:, ::-1], omax)
     assert not bad["ok"]
+
+
+@pytest.mark.slow
+def test_the_pin_resolves_known_pitfalls(oracle, inverse):
+    """How sharp is "chi-square per pixel ~ 1"?  The same comparison with one deliberate error each (oracle side at 1e8
+    iterations, scaled): the subtleties SURVEY §0 lists are far outside the noise floor.  Measured at 2e8 iterations: correct
+    1.02-1.04; camera centre off by a quarter / half pixel 4.3 / 11.5; one map coefficient off by 1e-4 / 1e-3 13.7 / 86;
+    solar-sail's rotation axis normalised (debug-build semantics, lib.rs:181-183) 728; 220 taken as radians 705."""
+    def chi(name, mutate):
+        w, h = (1920, 1080) if name == "poisson_saturne" else (1800, 2000)
+        cfg = _config(oracle, name, w, h)
+        cfg.iterations = 100_000_000
+        mutate(cfg)
+        img, rt = oracle.render_parallel(cfg, 12, 12, oracle.seed_points(77, 0, 144), want_runtime=True)
+        count = rt.count.ravel()
+        idx, n = inverse[name + "_idx"].astype(np.int64), inverse[name + "_n"]
+        rmax = int(inverse[name + "_max"])
+        if name == "poisson_saturne":
+            s = 1e9 / float(count.sum())
+        else:
+            s = (144.0 * PER_JOB - rmax) / (float(count.sum()) - float(count[0]))
+        return _chi2(n, count[idx], s)
+
+    def quarter_pixel(c):
+        c.center_camera[0] += 0.25 / (c.width * c.scale)
+
+    def coefficient(c):
+        c.coef[0][3] += 1e-4
+
+    def normalised_axis(c):
+        a = np.array(list(c.axis))
+        a /= np.linalg.norm(a)
+        for k in range(3):
+            c.axis[k] = a[k]
+
+    def degrees_as_radians(c):
+        c.angle = 220.0
+
+    # (at 1e8 iterations the scaled oracle counts are small and the statistic of a CORRECT frame sits at 1.05-1.2)
+    assert chi("poisson_saturne", lambda c: None) < 1.3
+    assert chi("poisson_saturne", quarter_pixel) > 2.0
+    assert chi("poisson_saturne", coefficient) > 4.0
+    assert chi("solar_sail", lambda c: None) < 1.3
+    assert chi("solar_sail", normalised_axis) > 100.0
+    assert chi("solar_sail_220", degrees_as_radians) > 100.0
