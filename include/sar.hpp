@@ -11,6 +11,7 @@
 //   sar::render(config, runtime), sar::colorize(config, runtime) -> FinalImage             lib.rs:747, 841
 //   sar::ParallelRenderer::{ParallelRenderer(), shutdown}, sar::render_parallel(...)       lib.rs:919, 1020, 1051
 //   sar::PixelFormat, Container, encode_image(runtime, ...), encode_png(...), write_image(...)  src/bin/main.rs:40-100
+//   sar::angle_iter, render_sequence(...), render_sequence_encoded(...)                    src/bin/main.rs:107-176, 496-512
 //   sar::autoframe(config, ...) -> AutoFrame                                               lib.rs:326-334 (the author's TODO)
 #pragma once
 #include <array>
@@ -18,6 +19,7 @@
 #include <random>
 #include <stdexcept>
 #include <string>
+#include <type_traits>
 #include <variant>
 #include <vector>
 
@@ -181,7 +183,8 @@ inline FinalImage render_parallel(ParallelRenderer &renderer, const Config &conf
 
 // ---- output conversion + raw encoders (src/bin/main.rs:40-100) ----------------------------------
 enum class PixelFormat { Rgba16 = SAR_PIX_RGBA16, Rgb16 = SAR_PIX_RGB16, Rgba8 = SAR_PIX_RGBA8, Rgb8 = SAR_PIX_RGB8 };
-enum class Container { Raw = SAR_FILE_RAW, Pam = SAR_FILE_PAM, Bmp = SAR_FILE_BMP, Png = SAR_FILE_PNG };
+enum class Container { Raw = SAR_FILE_RAW, Pam = SAR_FILE_PAM, Bmp = SAR_FILE_BMP, Png = SAR_FILE_PNG,
+                       PngDeflate = SAR_FILE_PNG_DEFLATE /* frame sequences only; single images: encode_png() */ };
 // the match at main.rs:52-57
 inline PixelFormat pixel_format(bool transparent, bool eight_bit) {
     return transparent ? (eight_bit ? PixelFormat::Rgba8 : PixelFormat::Rgba16) : (eight_bit ? PixelFormat::Rgb8 : PixelFormat::Rgb16);
@@ -208,6 +211,48 @@ inline void write_image(const Runtime &runtime, const Config &config, const std:
     const auto bytes = cont == Container::Png ? encode_png(runtime, config.width, config.height, pixel_format(config.transparent, eight_bit))
                                               : encode_image(runtime, config.width, config.height, pixel_format(config.transparent, eight_bit), cont);
     check(sar_write_file(path.c_str(), bytes.data(), bytes.size()));
+}
+
+// ---- frame sequences: AngleIter and the binary's frame loop (src/bin/main.rs:107-176, 496-512) ------
+// The angles AngleIter yields (main.rs:136-176): while curr + step/2 < end { yield curr (DEGREES) converted to radians,
+// main.rs:166; curr += step }; if that is nothing, the single value `start` UNCONVERTED, like the reference's
+// single-image branch (main.rs:168-170).  (A non-positive step, with which the reference never terminates, yields that too.)
+inline std::vector<double> angle_iter(double start, double end, double step) {
+    std::vector<double> out;
+    const double pi = 3.14159265358979323846;
+    if (step > 0.0)
+        for (double curr = start; curr + step / 2. < end; curr += step) out.push_back(curr * pi / 180.);
+    if (out.empty()) out.push_back(start);
+    return out;
+}
+namespace detail {
+template <class F> struct Thunk {
+    static void frame16(void *user, uint32_t frame, const uint16_t *rgba) { (*static_cast<F *>(user))(frame, rgba); }
+    static void bytes(void *user, uint32_t frame, const uint8_t *data, size_t n) { (*static_cast<F *>(user))(frame, data, n); }
+};
+}  // namespace detail
+// for angle in angles { config.angle = angle; image = render_parallel(..); on_frame(index, rgba16 pixels) } — frames are
+// rendered back to back on the renderer's devices, each frame's copy-out overlapping the next frame's render; on_frame is
+// called in frame order from the calling thread (the pixels are only valid inside it).
+template <class F>
+inline void render_sequence(ParallelRenderer &renderer, const Config &config, const std::vector<double> &angles_rad,
+                            size_t jobs_per_thread, uint64_t seed, F &&on_frame, bool shared_points = false) {
+    const sar_config c = config.to_pod();
+    using Fn = std::remove_reference_t<F>;
+    check(sar_render_sequence(renderer.handle(), &c, angles_rad.data(), uint32_t(angles_rad.size()), jobs_per_thread, seed,
+                              shared_points ? SAR_SEQ_SHARED_POINTS : 0u, nullptr, &detail::Thunk<Fn>::frame16, &on_frame));
+}
+// the same with every frame converted on the device and handed over encoded — what the reference's encoder side threads
+// write (main.rs:508-511): on_frame(index, bytes, n_bytes).  Container::PngDeflate = complete compressed PNG files.
+template <class F>
+inline void render_sequence_encoded(ParallelRenderer &renderer, const Config &config, const std::vector<double> &angles_rad,
+                                    size_t jobs_per_thread, uint64_t seed, PixelFormat fmt, Container cont, F &&on_frame,
+                                    bool shared_points = false) {
+    const sar_config c = config.to_pod();
+    using Fn = std::remove_reference_t<F>;
+    check(sar_render_sequence_encoded(renderer.handle(), &c, angles_rad.data(), uint32_t(angles_rad.size()), jobs_per_thread, seed,
+                                      shared_points ? SAR_SEQ_SHARED_POINTS : 0u, uint32_t(fmt), uint32_t(cont), nullptr,
+                                      &detail::Thunk<Fn>::bytes, &on_frame));
 }
 
 // ---- auto-framing first pass (lib.rs:326-334) ----------------------------------------------------

@@ -72,6 +72,26 @@ int main(int argc, char **argv)
                 fnv_bytes(png.data(), png.size()));
     try { (void)encode_image(runtime, cfg.width, cfg.height, PixelFormat::Rgb16, Container::Bmp); std::puts("BMP16_DID_NOT_FAIL"); return 6; }
     catch (const Error &e) { std::printf("BMP16 code=%d\n", e.code); }
+    // the binary's frame loop (main.rs:496-512) through the mirror: raw RGBA16 frames and complete compressed PNG files
+    {
+        Config seq = Config::solar_sail();
+        seq.iterations = 600000; seq.width = 160; seq.height = 120; seq.transparent = false;
+        ParallelRenderer r2({}, 512);
+        const std::vector<double> angles = angle_iter(0.0, 50.0, 10.0);
+        unsigned long long h16 = 1469598103934665603ull, hpng = 1469598103934665603ull;
+        size_t n16 = 0, npng = 0, png_bytes = 0;
+        render_sequence(r2, seq, angles, 2, /*seed=*/5, [&](uint32_t f, const uint16_t *px) {
+            (void)f; ++n16;
+            const uint8_t *b = reinterpret_cast<const uint8_t *>(px);
+            for (size_t i = 0; i < size_t(seq.width) * seq.height * 8; ++i) h16 = (h16 ^ b[i]) * 1099511628211ull;
+        });
+        render_sequence_encoded(r2, seq, angles, 2, /*seed=*/5, PixelFormat::Rgb16, Container::PngDeflate,
+                                [&](uint32_t f, const uint8_t *b, size_t n) {
+                                    (void)f; ++npng; png_bytes += n;
+                                    for (size_t i = 0; i < n; ++i) hpng = (hpng ^ b[i]) * 1099511628211ull;
+                                });
+        std::printf("SEQUENCE frames=%zu hash=%llu pngframes=%zu pngbytes=%zu pnghash=%llu first=%.17g\n", n16, h16, npng, png_bytes, hpng, angles[0]);
+    }
     const AutoFrame af = autoframe(Config::poisson_saturne(), 1024, 2000, /*seed=*/3);
     std::printf("AUTOFRAME xmin=%.17g ymax=%.17g diverged=%llu\n", af.box[0], af.box[3], (unsigned long long)af.diverged);
     return 0;

@@ -79,6 +79,18 @@ def test_cpp_mirror_matches_python_api(exe):
     png = S.encode_png(rt, S.PixelFormat.of(False, False))      # deterministic: same bytes from both hosts
     assert lines["ENCODED"][0] == {"pam": str(_fnv(pam)), "bmp": str(_fnv(bmp)), "png": str(_fnv(png))}
     assert lines["BMP16"][0]["code"] == str(S._native.SAR_ERR_UNSUPPORTED)
+    # the frame loop through the C++ mirror == through api.py: same frames, same compressed PNG files
+    seq = S.Config.solar_sail()
+    seq.iterations, seq.width, seq.height, seq.transparent = 600000, 160, 120, False
+    r2 = S.ParallelRenderer.new(threads=512)
+    angles = S.angle_iter(0.0, 50.0, 10.0)
+    frames = S.render_sequence(r2, seq, angles, 2, seed=5)
+    pngs = S.render_sequence_encoded(r2, seq, angles, 2, S.PixelFormat.Rgb16, S.Container.PngDeflate, seed=5)
+    r2.shutdown()
+    got = lines["SEQUENCE"][0]
+    assert got["frames"] == got["pngframes"] == str(len(angles)) == "5"
+    assert got["hash"] == str(_fnv(frames)) and got["pngbytes"] == str(sum(p.size for p in pngs))
+    assert got["pnghash"] == str(_fnv(np.concatenate(pngs)))
     af = S.autoframe(S.Config.poisson_saturne(), n_jobs=1024, iterations=2000, seed=3)
     assert float(lines["AUTOFRAME"][0]["xmin"]) == af.box[0] and float(lines["AUTOFRAME"][0]["ymax"]) == af.box[3]
     assert lines["AUTOFRAME"][0]["diverged"] == str(af.diverged)
