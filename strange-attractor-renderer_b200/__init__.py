@@ -7,7 +7,7 @@ The directory name carries a hyphen (it mirrors the reference's crate name); imp
 from .api import (  # noqa: F401
     BrighnessConstants, Colors, Config, EulerAxisRotation, FinalImage, Palette, ParallelRenderer,
     RenderKind, Runtime, SarConfig, SarError, Vec3, View, attractors, color_transforms, colorize,
-    render, render_parallel, seed_points, angle_iter, render_sequence,
+    render, render_parallel, seed_points, angle_iter, angle_iter_files, render_sequence,
     PixelFormat, Container, encode_image, encode_png, write_image, render_sequence_encoded, AutoFrame, autoframe,
 )
 from . import _native, build  # noqa: F401
@@ -16,6 +16,6 @@ __all__ = [
     "BrighnessConstants", "Colors", "Config", "EulerAxisRotation", "FinalImage", "Palette",
     "ParallelRenderer", "RenderKind", "Runtime", "SarConfig", "SarError", "Vec3", "View",
     "attractors", "color_transforms", "colorize", "render", "render_parallel", "seed_points",
-    "angle_iter", "render_sequence", "PixelFormat", "Container", "encode_image", "encode_png", "write_image",
+    "angle_iter", "angle_iter_files", "render_sequence", "PixelFormat", "Container", "encode_image", "encode_png", "write_image",
     "render_sequence_encoded", "AutoFrame", "autoframe",
 ]

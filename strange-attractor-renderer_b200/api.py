@@ -536,6 +536,31 @@ def angle_iter(start: float, end: float, step: float) -> List[float]:
     return out if out else [float(start)]
 
 
+def angle_iter_files(start: float, end: float, step: float, file: str) -> List[tuple]:
+    """AngleIter as the binary uses it (main.rs:106-176): (angle, path) pairs.  Frame i of a sequence is written to
+    `<stem><i zero-padded to needed_digits><.ext>` next to `file`, with needed_digits = ceil(log10((end - start - step/2) / step))
+    (0 when that count is <= 1, main.rs:116-122); a range that yields no frame gives the single pair (start, file)."""
+    import math
+
+    count = (end - start - step / 2.0) / step if step != 0 else 0.0
+    as_usize = 0 if not (count > 0.0) else int(min(count, float(2**64 - 1)))          # `count as usize`: saturating, NaN -> 0
+    digits = 0 if as_usize <= 1 else int(math.ceil(math.log10(count)))
+    folder, name = os.path.split(file)
+    stem, ext = os.path.splitext(name)                          # file_stem() / extension(), main.rs:141-156
+    stem = stem or "attractor"
+    out = []
+    for i, a in enumerate(angle_iter(start, end, step)):
+        if i == 0 and not (start + step / 2.0 < end):
+            return [(a, file)]                                  # the single-image branch, main.rs:168-170
+        idx = f"{i:0>{digits}}" if digits > 0 else ""
+        name = stem + idx
+        if ext:                                                 # PathBuf::set_extension: replaces what follows the last '.'
+            cut = name.rfind(".")
+            name = (name[:cut] if cut > 0 else name) + ext
+        out.append((a, os.path.join(folder, name)))
+    return out
+
+
 def render_sequence(renderer: ParallelRenderer, config, angles: Sequence[float], jobs_per_thread: int,
                     seed: Optional[int] = None, shared_points: bool = False, out: Optional[np.ndarray] = None,
                     callback=None) -> Optional[np.ndarray]:

@@ -119,3 +119,22 @@ def test_product_library_has_no_diagnostic_kernels():
     syms = subprocess.run(["cuobjdump", "-symbols", N.LIB_PATH], capture_output=True, text=True).stdout
     kernels = sorted({w for line in syms.splitlines() if "STO_ENTRY" in line for w in line.split() if "iterate_kernel" in w})
     assert kernels and all("ELi0ELi" in k for k in kernels)   # iterate_kernel<NT, MODE = 0, PIPE>, kernels
+
+
+def test_angle_iter_files_follow_the_binary_s_naming():
+    """AngleIter (src/bin/main.rs:106-176): degrees -> radians, zero-padded frame index sized by the estimated count, the
+    single-image branch for an empty range (angle left unconverted), and its quirks (no digits for <= 1.5 steps;
+    set_extension replacing a dotted stem's tail)."""
+    import math
+
+    import strange_attractor_renderer_b200 as S
+
+    seq = S.angle_iter_files(0.0, 360.0, 1.0, "out/attractor.png")
+    assert len(seq) == 360 and seq[0] == (0.0, "out/attractor000.png") and seq[359][1] == "out/attractor359.png"
+    assert seq[7][0] == 7.0 * math.pi / 180.0
+    assert [a for a, _ in seq] == S.angle_iter(0.0, 360.0, 1.0)
+    assert [p for _, p in S.angle_iter_files(0.0, 100.0, 10.0, "a.bmp")] == [f"a{i}.bmp" for i in range(10)]       # count 9.5 -> 1 digit
+    assert [p for _, p in S.angle_iter_files(0.0, 10.0, 5.0, "x.png")] == ["x.png", "x.png"]                        # count 1.5 -> no digits
+    assert S.angle_iter_files(90.0, 90.0, 1.0, "one.png") == [(90.0, "one.png")]                                    # single image, radians as given
+    assert S.angle_iter_files(0.0, 30.0, 1.0, "noext")[3][1] == "noext03"
+    assert S.angle_iter_files(0.0, 30.0, 1.0, "a.b.png")[3][1] == "a.png"                                           # "a.b03" -> set_extension("png")
